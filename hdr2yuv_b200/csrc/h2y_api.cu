@@ -1,0 +1,669 @@
+// h2y_api.cu -- the extern "C" boundary declared in include/hdr2yuv_b200.h: context, host-side
+// derivation of the per-launch constants, staged entry points, the fused forward / inverse calls
+// and the pinned-ring host pipelines.
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "h2y_internal.h"
+
+struct h2y_ctx : public h2y::h2y_ctx_impl {};
+
+namespace h2y {
+
+h2y_status cuda_fail(h2y_ctx_impl *c, cudaError_t e)
+{
+    if (c) c->last_cuda_error = (int)e;
+    cudaGetLastError();   // clear the sticky-less error state
+    return H2Y_ERR_CUDA;
+}
+
+h2y_status scratch_reserve(h2y_ctx_impl *c, int slot, size_t bytes, void **out)
+{
+    if (bytes > c->scratch_bytes[slot]) {
+        // buffers may be in flight on a stream; growing is rare, so settle the device first
+        H2Y_CUDA(c, cudaDeviceSynchronize());
+        if (c->scratch[slot]) cudaFree(c->scratch[slot]);
+        c->scratch[slot] = nullptr;
+        c->scratch_bytes[slot] = 0;
+        size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&c->scratch[slot], want);
+        if (e != cudaSuccess) { cudaGetLastError(); c->last_cuda_error = (int)e; return H2Y_ERR_NOMEM; }
+        c->scratch_bytes[slot] = want;
+    }
+    *out = c->scratch[slot];
+    return H2Y_OK;
+}
+
+void clip_of(int bit_depth, int full_range, h2y_clip_limits *c)
+{
+    c->minCV = 0;
+    c->maxCV = (1u << bit_depth) - 1u;
+    c->Half = (uint16_t)(1u << (bit_depth - 1));
+    c->_pad = 0;
+    if (full_range == 0) {
+        const unsigned D = 1u << (bit_depth - 8);
+        c->minVR = (uint16_t)(16 * D);
+        c->maxVR = (uint16_t)(219 * D + c->minVR);
+        c->minVRC = c->minVR;
+        c->maxVRC = (uint16_t)(224 * D + c->minVRC);
+    } else {
+        c->minVR = 0; c->maxVR = (uint16_t)c->maxCV; c->minVRC = 0; c->maxVRC = (uint16_t)c->maxCV;
+    }
+}
+
+static int tf_of(int transfer)
+{
+    switch (transfer) {
+    case H2Y_TRANSFER_PQ: return TF_PQ;
+    case H2Y_TRANSFER_RHO_GAMMA: return TF_RHO;
+    case H2Y_TRANSFER_BT709: case H2Y_TRANSFER_BT2020_10bit: case H2Y_TRANSFER_BT2020_12bit: case H2Y_TRANSFER_BT601:
+        return TF_GAMMA;
+    default: return TF_NONE;
+    }
+}
+
+static bool depth_ok(int d) { return d >= 8 && d <= 16; }
+
+h2y_status make_pixk(const h2y_pic_desc &in, const h2y_pic_desc &tmp, int out_bit_depth, int out_full_range,
+                     int clip_on_load, PixK *k)
+{
+    memset(k, 0, sizeof(*k));
+    const bool out_f32 = tmp.pic_buffer_type == H2Y_PIC_TYPE_F32;
+    if (!depth_ok(tmp.bit_depth) || !depth_ok(out_bit_depth)) return H2Y_ERR_ARG;
+    h2y_clip_limits tc;
+    clip_of(tmp.bit_depth, tmp.video_full_range_flag, &tc);
+    k->maxCV = tc.maxCV;
+    k->half_m1 = (int)tc.Half - 1;
+
+    // colour-difference family (convert.cpp:1159-1198)
+    if (tmp.matrix_coeffs == in.matrix_coeffs && tmp.colour_primaries == in.colour_primaries) k->mat_kind = MK_PASS;
+    else switch (tmp.matrix_coeffs) {
+        case H2Y_MATRIX_YDzDx: k->mat_kind = MK_YDZDX; break;
+        case H2Y_MATRIX_BT2020nc:
+            k->mat_kind = MK_YCBCR; k->wr = 0.2627; k->wg = 0.6780; k->wb = 0.0593; k->db = 1.8814; k->dr = 1.4746; break;
+        case H2Y_MATRIX_BT709:
+            k->mat_kind = MK_YCBCR; k->wr = 0.2126; k->wg = 0.7152; k->wb = 0.0722; k->db = 1.8556; k->dr = 1.5748; break;
+        case H2Y_MATRIX_YDzDx_Y100:
+            k->mat_kind = MK_Y100; k->P = -0.5; k->Q = 0.491722; k->RR = 0.5; k->S = -0.49495; break;
+        case H2Y_MATRIX_YDzDx_Y500:
+            k->mat_kind = MK_Y100; k->P = -0.5; k->Q = 0.493393; k->RR = 0.5; k->S = -0.49602; break;
+        case H2Y_MATRIX_YUVPRIME2: k->mat_kind = MK_PRIME2; break;
+        default: return H2Y_ERR_MATRIX;
+    }
+    if (k->mat_kind == MK_YCBCR) { k->rdb = 1.0 / k->db; k->rdr = 1.0 / k->dr; }
+
+    // transfer change (convert.cpp:930, 1021-1109)
+    k->convert_transfer = in.transfer_characteristics != tmp.transfer_characteristics;
+    if (k->convert_transfer) {
+        int cur = in.transfer_characteristics;
+        if (cur != H2Y_TRANSFER_LINEAR) {
+            k->tf_linearise = tf_of(cur);
+            if (k->tf_linearise != TF_NONE) cur = H2Y_TRANSFER_LINEAR;
+        }
+        if (cur == H2Y_TRANSFER_LINEAR && tmp.transfer_characteristics != H2Y_TRANSFER_LINEAR)
+            k->tf_encode = tf_of(tmp.transfer_characteristics);
+        if (out_f32) k->scale_mode = SC_FLOAT_OUT;
+        else if (tmp.video_full_range_flag) { k->scale_mode = SC_FULL; k->mulY = (float)tc.maxCV; }
+        else {
+            k->scale_mode = SC_VIDEO;
+            k->mulY = (float)tc.maxVR; k->addY = (float)tc.minVR;
+            if (tmp.matrix_coeffs == H2Y_MATRIX_GBR) { k->mulC = (float)tc.maxVR; k->addC = (float)tc.minVR; }
+            else { k->mulC = (float)tc.maxVRC; k->addC = (float)tc.minVRC; }
+        }
+    }
+
+    // write_yuv (tiff.cpp:394-401, 457-550)
+    k->down_shift = tmp.bit_depth - out_bit_depth;
+    h2y_clip_limits oc;
+    clip_of(out_bit_depth, out_full_range, &oc);
+    if (out_full_range == 0) { k->loY = oc.minVR; k->hiY = oc.maxVR; k->loC = oc.minVRC; k->hiC = oc.maxVRC; }
+    else { k->loY = 0; k->hiY = oc.maxCV; k->loC = 0; k->hiC = oc.maxCV; }
+
+    // read_tiff's clip (tiff.cpp:296-304)
+    k->clip_on_load = 0;
+    if (clip_on_load && in.video_full_range_flag == 0 && depth_ok(in.bit_depth)) {
+        h2y_clip_limits ic;
+        clip_of(in.bit_depth, 0, &ic);
+        k->clip_on_load = 1; k->loadLo = ic.minVR; k->loadHi = ic.maxVR;
+    }
+    return H2Y_OK;
+}
+
+static int pic_type_of_layout(int layout)
+{
+    return (layout == H2Y_LAYOUT_PLANAR_U16 || layout == H2Y_LAYOUT_RGB16 || layout == H2Y_LAYOUT_RGBA16)
+               ? H2Y_PIC_TYPE_U16 : H2Y_PIC_TYPE_F32;
+}
+
+static bool aligned16(const void *p, size_t stride) { return ((uintptr_t)p & 15) == 0 && (stride & 15) == 0; }
+
+}   // namespace h2y
+
+using namespace h2y;
+
+// ================================================================================================
+extern "C" {
+
+int h2y_abi_version(void) { return H2Y_ABI_VERSION; }
+
+const char *h2y_status_string(h2y_status s)
+{
+    switch (s) {
+    case H2Y_OK: return "ok";
+    case H2Y_ERR_PRECONDITION: return "picture precondition failed (4:4:4 / U16 required)";
+    case H2Y_ERR_MATRIX: return "can't determine color difference to use";
+    case H2Y_ERR_BIT_DEPTH: return "dst bitdepth > src bitdepth";
+    case H2Y_ERR_UNSUPPORTED: return "option not implemented by the B200 path";
+    case H2Y_ERR_ARG: return "bad argument";
+    case H2Y_ERR_CUDA: return "CUDA runtime error";
+    case H2Y_ERR_NOMEM: return "out of device memory";
+    }
+    return "unknown status";
+}
+
+h2y_status h2y_ctx_create(int device, h2y_ctx **out)
+{
+    if (!out) return H2Y_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { cudaGetLastError(); return H2Y_ERR_CUDA; }
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return H2Y_ERR_CUDA; }
+    h2y_ctx *c = new (std::nothrow) h2y_ctx();
+    if (!c) return H2Y_ERR_NOMEM;
+    memset(static_cast<h2y_ctx_impl *>(c), 0, sizeof(h2y_ctx_impl));
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; cudaGetLastError(); return H2Y_ERR_CUDA; }
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return H2Y_OK;
+}
+
+h2y_status h2y_ctx_destroy(h2y_ctx *c)
+{
+    if (!c) return H2Y_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 8; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
+    if (c->pipeline_ready) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_d2h); }
+    if (c->h_framek) cudaFreeHost(c->h_framek);
+    if (c->ev[0]) for (int i = 0; i < 3; i++) cudaEventDestroy(c->ev[i]);
+    delete c;
+    return H2Y_OK;
+}
+
+h2y_status h2y_profile_enable(h2y_ctx *c, int on)
+{
+    if (!c) return H2Y_ERR_ARG;
+    H2Y_CUDA(c, cudaSetDevice(c->device));
+    if (on && !c->ev[0]) for (int i = 0; i < 3; i++) H2Y_CUDA(c, cudaEventCreate(&c->ev[i]));
+    c->profile_on = on != 0;
+    c->profile_valid = 0;
+    return H2Y_OK;
+}
+
+h2y_status h2y_profile_last_ms(h2y_ctx *c, float *main_ms, float *prologue_ms)
+{
+    if (!c || !c->profile_valid) return H2Y_ERR_ARG;
+    H2Y_CUDA(c, cudaEventSynchronize(c->ev[2]));
+    float a = 0, b = 0;
+    H2Y_CUDA(c, cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+    H2Y_CUDA(c, cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
+    if (prologue_ms) *prologue_ms = a;
+    if (main_ms) *main_ms = b;
+    return H2Y_OK;
+}
+
+int h2y_last_cuda_error(const h2y_ctx *c) { return c ? c->last_cuda_error : 0; }
+uint64_t h2y_kernel_launches(const h2y_ctx *c) { return c ? c->launches : 0; }
+
+void *h2y_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void h2y_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+h2y_status h2y_set_pic_clip(int bit_depth, int full_range, h2y_clip_limits *out)
+{
+    if (!out || bit_depth < 8 || bit_depth > 16) return H2Y_ERR_ARG;
+    clip_of(bit_depth, full_range, out);
+    return H2Y_OK;
+}
+
+h2y_status h2y_plane_dims(int w, int h, int chroma, int pw[3], int ph[3])
+{
+    if (!pw || !ph || w < 1 || h < 1) return H2Y_ERR_ARG;
+    const int ws = chroma == H2Y_CHROMA_444 ? 0 : 1, hs = chroma == H2Y_CHROMA_420 ? 1 : 0;
+    pw[0] = w; ph[0] = h;
+    pw[1] = pw[2] = w >> ws;
+    ph[1] = ph[2] = h >> hs;
+    return H2Y_OK;
+}
+
+size_t h2y_src_frame_bytes(const h2y_pic_desc *s)
+{
+    if (!s) return 0;
+    const size_t n = (size_t)s->width * s->height;
+    switch (s->layout) {
+    case H2Y_LAYOUT_PLANAR_U16: case H2Y_LAYOUT_RGB16: case H2Y_LAYOUT_HALF_RGB: return n * 6;
+    case H2Y_LAYOUT_PLANAR_F32: return n * 12;
+    case H2Y_LAYOUT_RGBA16: case H2Y_LAYOUT_HALF_RGBA: return n * 8;
+    }
+    return 0;
+}
+
+size_t h2y_yuv_frame_bytes(int w, int h, int chroma)
+{
+    int pw[3], ph[3];
+    if (h2y_plane_dims(w, h, chroma, pw, ph) != H2Y_OK) return 0;
+    return ((size_t)pw[0] * ph[0] + 2 * (size_t)pw[1] * ph[1]) * 2;
+}
+
+size_t h2y_rgb_frame_bytes(const h2y_inverse_params *p)
+{
+    return p ? (size_t)p->width * p->height * (p->alpha ? 4 : 3) * 2 : 0;
+}
+
+int h2y_tmp_bit_depth(const h2y_pic_desc *src, const h2y_pic_desc *dst)
+{
+    // destination of a .yuv is U16 (hdr2yuv.cpp:421-424); rule at hdr2yuv.cpp:803-808
+    return pic_type_of_layout(src->layout) == H2Y_PIC_TYPE_U16 ? src->bit_depth : dst->bit_depth;
+}
+
+// ---- staged ----------------------------------------------------------------------------------------
+
+static void framek_to_stats(const FrameK &f, int is_f32, h2y_pic_stats_t *o)
+{
+    for (int c = 0; c < 3; c++) {
+        o->f_min[c] = f.fmin[c]; o->f_max[c] = f.fmax[c];
+        o->i_min[c] = is_f32 ? 0 : (uint16_t)f.fmin[c];
+        o->i_max[c] = is_f32 ? 0 : (uint16_t)f.fmax[c];
+        o->estimated_floor[c] = f.est_floor[c];
+        o->estimated_ceiling[c] = f.est_ceiling[c];
+    }
+}
+
+h2y_status h2y_pic_stats(h2y_ctx *c, const h2y_pic_desc *pic, const void *const d_planes[3], h2y_pic_stats_t *out, void *stream)
+{
+    if (!c || !pic || !d_planes || !out) return H2Y_ERR_ARG;
+    if (pic->pic_buffer_type != H2Y_PIC_TYPE_U16 && pic->pic_buffer_type != H2Y_PIC_TYPE_F32) return H2Y_ERR_ARG;
+    if (pic->pic_buffer_type == H2Y_PIC_TYPE_U16 && !depth_ok(pic->bit_depth)) return H2Y_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    H2Y_CUDA(c, cudaSetDevice(c->device));
+    FrameK *dfk;
+    h2y_status s = launch_stats_planar(c, *pic, d_planes, &dfk, st);
+    if (s != H2Y_OK) return s;
+    FrameK h;
+    H2Y_CUDA(c, cudaMemcpyAsync(&h, dfk, sizeof(h), cudaMemcpyDeviceToHost, st));
+    H2Y_CUDA(c, cudaStreamSynchronize(st));
+    framek_to_stats(h, pic->pic_buffer_type == H2Y_PIC_TYPE_F32, out);
+    return H2Y_OK;
+}
+
+h2y_status h2y_matrix_convert(h2y_ctx *c, const h2y_pic_desc *out, void *const d_out[3], const h2y_pic_desc *in,
+                              const void *const d_in[3], const h2y_pic_stats_t *in_stats, void *stream)
+{
+    if (!c || !out || !in || !d_out || !d_in) return H2Y_ERR_ARG;
+    if (in->chroma_format_idc != H2Y_CHROMA_444 || out->chroma_format_idc != H2Y_CHROMA_444) return H2Y_ERR_PRECONDITION;
+    if (in->width != out->width || in->height != out->height || in->width < 1 || in->height < 1) return H2Y_ERR_ARG;
+    const bool in_f32 = in->pic_buffer_type == H2Y_PIC_TYPE_F32, out_f32 = out->pic_buffer_type == H2Y_PIC_TYPE_F32;
+    PixK k;
+    h2y_status s = make_pixk(*in, *out, out->bit_depth, out->video_full_range_flag, 0, &k);
+    if (s != H2Y_OK) return s;
+    NormK nk;
+    memset(&nk, 0, sizeof(nk));
+    if (k.convert_transfer) {
+        if (!in_stats) return H2Y_ERR_ARG;
+        for (int ch = 0; ch < 3; ch++) {
+            nk.range[ch] = (float)(in_stats->estimated_ceiling[ch] - in_stats->estimated_floor[ch]);
+            nk.offset[ch] = (float)in_stats->estimated_floor[ch];
+        }
+    }
+    H2Y_CUDA(c, cudaSetDevice(c->device));
+    return launch_matrix_convert(c, k, nk, in->width, in->height, in_f32, d_in, out_f32, d_out, (cudaStream_t)stream);
+}
+
+h2y_status h2y_convert(h2y_ctx *c, const h2y_pic_desc *out, void *const d_out[3], const h2y_pic_desc *in,
+                       const void *const d_in[3], int resampler, void *stream)
+{
+    if (!c || !out || !in || !d_out || !d_in) return H2Y_ERR_ARG;
+    if (in->pic_buffer_type != H2Y_PIC_TYPE_U16 || out->pic_buffer_type != H2Y_PIC_TYPE_U16) return H2Y_ERR_PRECONDITION;
+    if (out->matrix_coeffs == H2Y_MATRIX_YUVPRIME2 && out->chroma_format_idc == H2Y_CHROMA_420) return H2Y_ERR_UNSUPPORTED;
+    if (!depth_ok(in->bit_depth)) return H2Y_ERR_ARG;
+    const int w = in->width, h = in->height;
+    cudaStream_t st = (cudaStream_t)stream;
+    H2Y_CUDA(c, cudaSetDevice(c->device));
+    h2y_clip_limits clip;
+    clip_of(in->bit_depth, in->video_full_range_flag, &clip);     // clip of the INPUT picture, convert.cpp:520
+    h2y_status s = H2Y_OK;
+    const size_t plane = (size_t)w * h * 2;
+    if (out->chroma_format_idc == H2Y_CHROMA_420) {
+        if ((w & 1) || (h & 1)) return H2Y_ERR_ARG;
+        if (resampler == 0) {
+            if ((w & 3) || (h & 3)) return H2Y_ERR_ARG;
+            for (int p = 1; p < 3 && s == H2Y_OK; p++) s = launch_box_420(c, (const uint16_t *)d_in[p], (uint16_t *)d_out[p], w, h, st);
+        } else {
+            void *mid;
+            if ((s = scratch_reserve(c, SCR_TMP444, (size_t)(w / 2) * h * 2, &mid)) != H2Y_OK) return s;
+            for (int p = 1; p < 3 && s == H2Y_OK; p++)
+                s = launch_fir_420(c, (const uint16_t *)d_in[p], (uint16_t *)d_out[p], (uint16_t *)mid, w, h, clip.maxCV, st);
+        }
+    } else if (out->chroma_format_idc == H2Y_CHROMA_444) {
+        for (int p = 1; p < 3; p++) H2Y_CUDA(c, cudaMemcpyAsync(d_out[p], d_in[p], plane, cudaMemcpyDeviceToDevice, st));
+    } else if (out->chroma_format_idc == H2Y_CHROMA_422) {
+        if (resampler == 0 || (w & 1)) return H2Y_ERR_UNSUPPORTED;
+        for (int p = 1; p < 3 && s == H2Y_OK; p++) s = launch_fir_422(c, (const uint16_t *)d_in[p], (uint16_t *)d_out[p], w, h, clip.maxCV, st);
+    } else return H2Y_ERR_ARG;
+    if (s != H2Y_OK) return s;
+    H2Y_CUDA(c, cudaMemcpyAsync(d_out[0], d_in[0], plane, cudaMemcpyDeviceToDevice, st));   // convert.cpp:857-859
+    return H2Y_OK;
+}
+
+h2y_status h2y_write_yuv_clamp(h2y_ctx *c, const h2y_pic_desc *pic, void *const d_planes[3], int src_bit_depth, void *stream)
+{
+    if (!c || !pic || !d_planes || !depth_ok(pic->bit_depth)) return H2Y_ERR_ARG;
+    const int shift = src_bit_depth - pic->bit_depth;
+    if (shift < 0) return H2Y_ERR_BIT_DEPTH;
+    h2y_clip_limits oc;
+    clip_of(pic->bit_depth, pic->video_full_range_flag, &oc);
+    int pw[3], ph[3];
+    h2y_plane_dims(pic->width, pic->height, pic->chroma_format_idc, pw, ph);
+    H2Y_CUDA(c, cudaSetDevice(c->device));
+    for (int p = 0; p < 3; p++) {
+        unsigned lo, hi;
+        if (pic->video_full_range_flag == 0) { lo = p ? oc.minVRC : oc.minVR; hi = p ? oc.maxVRC : oc.maxVR; }
+        else { lo = 0; hi = oc.maxCV; }
+        h2y_status s = launch_out_clamp(c, (uint16_t *)d_planes[p], (size_t)pw[p] * ph[p], shift, lo, hi, (cudaStream_t)stream);
+        if (s != H2Y_OK) return s;
+    }
+    return H2Y_OK;
+}
+
+h2y_status h2y_subsample_420_to_444(h2y_ctx *c, const void *d_src, void *d_dst, int w, int h, int algorithm,
+                                    uint16_t minCV, uint16_t maxCV, void *stream)
+{
+    if (!c || !d_src || !d_dst || w < 2 || h < 2 || (w & 1) || (h & 1)) return H2Y_ERR_ARG;
+    H2Y_CUDA(c, cudaSetDevice(c->device));
+    void *mid = nullptr;
+    h2y_status s;
+    if (algorithm && (s = scratch_reserve(c, SCR_TMP444, (size_t)(w / 2) * h * 2, &mid)) != H2Y_OK) return s;
+    return launch_upsample(c, (const uint16_t *)d_src, (uint16_t *)d_dst, (uint16_t *)mid, w, h, algorithm, minCV, maxCV,
+                           (cudaStream_t)stream);
+}
+
+// ---- fused forward ------------------------------------------------------------------------------------
+
+static h2y_status forward_validate(const h2y_forward_params *p, h2y_pic_desc *tmp, PixK *k)
+{
+    const h2y_pic_desc &s = p->src, &d = p->dst;
+    if (s.width < 2 || s.height < 2 || s.width > 16384 || s.height > 16384) return H2Y_ERR_ARG;
+    if (s.layout < H2Y_LAYOUT_PLANAR_U16 || s.layout > H2Y_LAYOUT_HALF_RGBA) return H2Y_ERR_ARG;
+    if (s.chroma_format_idc != H2Y_CHROMA_444) return H2Y_ERR_PRECONDITION;        // convert.cpp:886-890
+    if (d.chroma_format_idc != H2Y_CHROMA_444 && d.chroma_format_idc != H2Y_CHROMA_420 &&
+        d.chroma_format_idc != H2Y_CHROMA_422) return H2Y_ERR_ARG;
+    if (d.width != s.width || d.height != s.height) return H2Y_ERR_UNSUPPORTED;     // picture resize is not in the path
+    if (pic_type_of_layout(s.layout) == H2Y_PIC_TYPE_U16 && !depth_ok(s.bit_depth)) return H2Y_ERR_ARG;
+    if (!depth_ok(d.bit_depth)) return H2Y_ERR_ARG;
+    *tmp = d;
+    tmp->chroma_format_idc = H2Y_CHROMA_444;
+    tmp->bit_depth = h2y_tmp_bit_depth(&s, &d);
+    tmp->pic_buffer_type = H2Y_PIC_TYPE_U16;
+    tmp->layout = H2Y_LAYOUT_PLANAR_U16;
+    h2y_status st = make_pixk(s, *tmp, d.bit_depth, d.video_full_range_flag, p->clip_on_load, k);
+    if (st != H2Y_OK) return st;
+    if (k->down_shift < 0) return H2Y_ERR_BIT_DEPTH;
+    if (d.matrix_coeffs == H2Y_MATRIX_YUVPRIME2 && d.chroma_format_idc == H2Y_CHROMA_420) return H2Y_ERR_UNSUPPORTED;
+    if (d.chroma_format_idc == H2Y_CHROMA_420) {
+        if ((s.width & 1) || (s.height & 1)) return H2Y_ERR_ARG;
+        if (p->chroma_resampler_type == 0 && ((s.width & 3) || (s.height & 3))) return H2Y_ERR_ARG;
+    }
+    if (d.chroma_format_idc == H2Y_CHROMA_422 && (p->chroma_resampler_type == 0 || (s.width & 1))) return H2Y_ERR_UNSUPPORTED;
+    return H2Y_OK;
+}
+
+// general-geometry route: the staged kernels, one frame at a time
+static h2y_status forward_staged(h2y_ctx *c, const h2y_forward_params *p, const h2y_pic_desc &tmp, const PixK &k,
+                                 const uint8_t *d_src, uint8_t *d_dst, cudaStream_t st)
+{
+    const int w = p->src.width, h = p->src.height;
+    const size_t n = (size_t)w * h;
+    const bool in_f32 = pic_type_of_layout(p->src.layout) == H2Y_PIC_TYPE_F32;
+    h2y_status s;
+    void *unp, *t444;
+    if ((s = scratch_reserve(c, SCR_UNPACK, n * 3 * (in_f32 ? 4 : 2), &unp)) != H2Y_OK) return s;
+    if ((s = scratch_reserve(c, SCR_OUT, n * 3 * 2, &t444)) != H2Y_OK) return s;
+    void *inpl[3];
+    const size_t es = in_f32 ? 4 : 2;
+    if (p->src.layout == H2Y_LAYOUT_PLANAR_F32) {
+        for (int i = 0; i < 3; i++) inpl[i] = (void *)(d_src + i * n * 4);
+    } else {
+        for (int i = 0; i < 3; i++) inpl[i] = (uint8_t *)unp + i * n * es;
+        if ((s = launch_unpack(c, p->src.layout, w, h, d_src, inpl, k.clip_on_load, k.loadLo, k.loadHi, st)) != H2Y_OK) return s;
+    }
+    NormK nk;
+    memset(&nk, 0, sizeof(nk));
+    if (k.convert_transfer) {
+        h2y_pic_desc sp = p->src;
+        sp.pic_buffer_type = in_f32 ? H2Y_PIC_TYPE_F32 : H2Y_PIC_TYPE_U16;
+        FrameK *dfk, hf;
+        if ((s = launch_stats_planar(c, sp, inpl, &dfk, st)) != H2Y_OK) return s;
+        H2Y_CUDA(c, cudaMemcpyAsync(&hf, dfk, sizeof(hf), cudaMemcpyDeviceToHost, st));
+        H2Y_CUDA(c, cudaStreamSynchronize(st));
+        for (int i = 0; i < 3; i++) { nk.offset[i] = hf.offset[i]; nk.range[i] = hf.range[i]; }
+    }
+    void *tpl[3] = {(uint8_t *)t444, (uint8_t *)t444 + n * 2, (uint8_t *)t444 + 2 * n * 2};
+    if ((s = launch_matrix_convert(c, k, nk, w, h, in_f32, inpl, 0, tpl, st)) != H2Y_OK) return s;
+    int pw[3], ph[3];
+    h2y_plane_dims(w, h, p->dst.chroma_format_idc, pw, ph);
+    uint16_t *oY = (uint16_t *)d_dst, *oCb = oY + n, *oCr = oCb + (size_t)pw[1] * ph[1];
+    void *opl[3] = {oY, oCb, oCr};
+    h2y_pic_desc od = p->dst;
+    od.pic_buffer_type = H2Y_PIC_TYPE_U16;
+    h2y_pic_desc td = tmp;
+    if ((s = h2y_convert(c, &od, opl, &td, tpl, p->chroma_resampler_type, st)) != H2Y_OK) return s;
+    return h2y_write_yuv_clamp(c, &od, opl, tmp.bit_depth, st);
+}
+
+h2y_status h2y_forward(h2y_ctx *c, const h2y_forward_params *p, const void *d_src, size_t src_stride, void *d_dst,
+                       size_t dst_stride, int nframes, void *stream)
+{
+    if (!c || !p || !d_src || !d_dst || nframes < 0) return H2Y_ERR_ARG;
+    if (nframes == 0) return H2Y_OK;
+    h2y_pic_desc tmp;
+    PixK k;
+    h2y_status s = forward_validate(p, &tmp, &k);
+    if (s != H2Y_OK) return s;
+    if (src_stride < h2y_src_frame_bytes(&p->src) ||
+        dst_stride < h2y_yuv_frame_bytes(p->src.width, p->src.height, p->dst.chroma_format_idc)) return H2Y_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    H2Y_CUDA(c, cudaSetDevice(c->device));
+    c->last_nframes = 0;
+    const bool fused = fused_forward_supported(*p) && k.mat_kind != MK_PRIME2 && aligned16(d_src, src_stride) &&
+                       aligned16(d_dst, dst_stride) && !getenv("H2Y_FORCE_STAGED");
+    if (!fused) {
+        for (int f = 0; f < nframes; f++)
+            if ((s = forward_staged(c, p, tmp, k, (const uint8_t *)d_src + (size_t)f * src_stride,
+                                    (uint8_t *)d_dst + (size_t)f * dst_stride, st)) != H2Y_OK) return s;
+        return H2Y_OK;
+    }
+    // bounded groups keep the LUT scratch (768 KiB per frame) small
+    const int GROUP = 64;
+    for (int f0 = 0; f0 < nframes; f0 += GROUP) {
+        const int nf = nframes - f0 < GROUP ? nframes - f0 : GROUP;
+        const uint8_t *src = (const uint8_t *)d_src + (size_t)f0 * src_stride;
+        uint8_t *dst = (uint8_t *)d_dst + (size_t)f0 * dst_stride;
+        FrameK *dfk = nullptr;
+        float *dl = nullptr;
+        if (c->profile_on) cudaEventRecord(c->ev[0], st);
+        if (k.convert_transfer) {
+            if ((s = launch_stats_and_luts(c, *p, k, src, src_stride, nf, &dfk, &dl, st)) != H2Y_OK) return s;
+            c->last_nframes = nf;
+            c->last_stream = st;
+        }
+        if (c->profile_on) cudaEventRecord(c->ev[1], st);
+        if ((s = launch_forward_fused(c, *p, k, src, src_stride, dst, dst_stride, nf, dfk, dl, st)) != H2Y_OK) return s;
+        if (c->profile_on) { cudaEventRecord(c->ev[2], st); c->profile_valid = 1; }
+    }
+    return H2Y_OK;
+}
+
+h2y_status h2y_forward_last_stats(h2y_ctx *c, int frame, h2y_pic_stats_t *out)
+{
+    if (!c || !out || frame < 0 || frame >= c->last_nframes || !c->scratch[SCR_FRAMEK]) return H2Y_ERR_ARG;
+    H2Y_CUDA(c, cudaSetDevice(c->device));
+    FrameK h;
+    H2Y_CUDA(c, cudaStreamSynchronize(c->last_stream));
+    H2Y_CUDA(c, cudaMemcpy(&h, (FrameK *)c->scratch[SCR_FRAMEK] + frame, sizeof(h), cudaMemcpyDeviceToHost));
+    framek_to_stats(h, 1, out);
+    for (int i = 0; i < 3; i++) { out->i_min[i] = (uint16_t)h.fmin[i]; out->i_max[i] = (uint16_t)h.fmax[i]; }
+    return H2Y_OK;
+}
+
+}   // extern "C"
+
+// ---- host pipelines --------------------------------------------------------------------------------------
+
+static h2y_status pipeline_init(h2y_ctx *c)
+{
+    if (c->pipeline_ready) return H2Y_OK;
+    H2Y_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    H2Y_CUDA(c, cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+    H2Y_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    c->pipeline_ready = 1;
+    return H2Y_OK;
+}
+
+// Three-deep device ring; chunk i: H2D on s_h2d -> compute on s_compute -> D2H on s_d2h, so the
+// PCIe directions and the kernels of neighbouring chunks overlap.
+template <class Compute>
+static h2y_status run_pipeline(h2y_ctx *c, const uint8_t *h_in, size_t in_stride, size_t in_bytes, uint8_t *h_out,
+                               size_t out_stride, size_t out_bytes, int nframes, Compute compute)
+{
+    h2y_status s = pipeline_init(c);
+    if (s != H2Y_OK) return s;
+    const int NB = 3;
+    // frames per chunk: about 64 MiB of input, at most 8 frames
+    int per = (int)((64u << 20) / (in_bytes ? in_bytes : 1));
+    per = per < 1 ? 1 : (per > 8 ? 8 : per);
+    if (per > nframes) per = nframes;
+    const size_t in_pitch = (in_bytes + 255) & ~(size_t)255, out_pitch = (out_bytes + 255) & ~(size_t)255;
+    void *din, *dout;
+    if ((s = scratch_reserve(c, SCR_RING_IN, in_pitch * per * NB, &din)) != H2Y_OK) return s;
+    if ((s = scratch_reserve(c, SCR_RING_OUT, out_pitch * per * NB, &dout)) != H2Y_OK) return s;
+    cudaEvent_t ev_h2d[NB], ev_comp[NB], ev_d2h[NB];
+    for (int i = 0; i < NB; i++) {
+        H2Y_CUDA(c, cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
+        H2Y_CUDA(c, cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
+        H2Y_CUDA(c, cudaEventCreateWithFlags(&ev_d2h[i], cudaEventDisableTiming));
+    }
+    h2y_status rs = H2Y_OK;
+    int chunk = 0;
+    for (int f0 = 0; f0 < nframes && rs == H2Y_OK; f0 += per, chunk++) {
+        const int nf = nframes - f0 < per ? nframes - f0 : per;
+        const int slot = chunk % NB;
+        uint8_t *di = (uint8_t *)din + (size_t)slot * per * in_pitch;
+        uint8_t *dob = (uint8_t *)dout + (size_t)slot * per * out_pitch;
+        if (chunk >= NB) {
+            // the slot's previous input must have been consumed, its output drained
+            cudaStreamWaitEvent(c->s_h2d, ev_comp[slot], 0);
+            cudaStreamWaitEvent(c->s_compute, ev_d2h[slot], 0);
+        }
+        if (in_stride == in_bytes && in_pitch == in_bytes)
+            cudaMemcpyAsync(di, h_in + (size_t)f0 * in_stride, in_bytes * nf, cudaMemcpyHostToDevice, c->s_h2d);
+        else
+            cudaMemcpy2DAsync(di, in_pitch, h_in + (size_t)f0 * in_stride, in_stride, in_bytes, nf, cudaMemcpyHostToDevice, c->s_h2d);
+        cudaEventRecord(ev_h2d[slot], c->s_h2d);
+        cudaStreamWaitEvent(c->s_compute, ev_h2d[slot], 0);
+        rs = compute(di, in_pitch, dob, out_pitch, nf, c->s_compute);
+        cudaEventRecord(ev_comp[slot], c->s_compute);
+        cudaStreamWaitEvent(c->s_d2h, ev_comp[slot], 0);
+        if (out_stride == out_bytes && out_pitch == out_bytes)
+            cudaMemcpyAsync(h_out + (size_t)f0 * out_stride, dob, out_bytes * nf, cudaMemcpyDeviceToHost, c->s_d2h);
+        else
+            cudaMemcpy2DAsync(h_out + (size_t)f0 * out_stride, out_stride, dob, out_pitch, out_bytes, nf, cudaMemcpyDeviceToHost, c->s_d2h);
+        cudaEventRecord(ev_d2h[slot], c->s_d2h);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(c->s_h2d), e2 = cudaStreamSynchronize(c->s_compute), e3 = cudaStreamSynchronize(c->s_d2h);
+    for (int i = 0; i < NB; i++) { cudaEventDestroy(ev_h2d[i]); cudaEventDestroy(ev_comp[i]); cudaEventDestroy(ev_d2h[i]); }
+    if (rs != H2Y_OK) return rs;
+    if (e1 != cudaSuccess) return cuda_fail(c, e1);
+    if (e2 != cudaSuccess) return cuda_fail(c, e2);
+    if (e3 != cudaSuccess) return cuda_fail(c, e3);
+    return H2Y_OK;
+}
+
+extern "C" {
+
+h2y_status h2y_forward_host(h2y_ctx *c, const h2y_forward_params *p, const void *h_src, size_t src_stride, void *h_dst,
+                            size_t dst_stride, int nframes)
+{
+    if (!c || !p || !h_src || !h_dst || nframes < 0) return H2Y_ERR_ARG;
+    if (nframes == 0) return H2Y_OK;
+    h2y_pic_desc tmp;
+    PixK k;
+    h2y_status s = forward_validate(p, &tmp, &k);
+    if (s != H2Y_OK) return s;
+    const size_t inb = h2y_src_frame_bytes(&p->src), outb = h2y_yuv_frame_bytes(p->src.width, p->src.height, p->dst.chroma_format_idc);
+    if (src_stride < inb || dst_stride < outb) return H2Y_ERR_ARG;
+    H2Y_CUDA(c, cudaSetDevice(c->device));
+    return run_pipeline(c, (const uint8_t *)h_src, src_stride, inb, (uint8_t *)h_dst, dst_stride, outb, nframes,
+                        [&](uint8_t *di, size_t ip, uint8_t *dob, size_t op, int nf, cudaStream_t st) {
+                            return h2y_forward(c, p, di, ip, dob, op, nf, st);
+                        });
+}
+
+// ---- inverse ------------------------------------------------------------------------------------------------
+
+h2y_status h2y_inverse(h2y_ctx *c, const h2y_inverse_params *p, const void *d_yuv, size_t yuv_stride, void *d_rgb,
+                       size_t rgb_stride, int nframes, uint32_t *d_invalid, void *stream)
+{
+    if (!c || !p || !d_yuv || !d_rgb || nframes < 0) return H2Y_ERR_ARG;
+    if (nframes == 0) return H2Y_OK;
+    InvK k;
+    h2y_status s = make_invk(*p, &k);
+    if (s != H2Y_OK) return s;
+    if (yuv_stride < h2y_yuv_frame_bytes(p->width, p->height, H2Y_CHROMA_420) || rgb_stride < h2y_rgb_frame_bytes(p)) return H2Y_ERR_ARG;
+    if (!aligned16(d_yuv, yuv_stride) || !aligned16(d_rgb, rgb_stride)) return H2Y_ERR_ARG;
+    H2Y_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_invalid) H2Y_CUDA(c, cudaMemsetAsync(d_invalid, 0, sizeof(uint32_t) * nframes, st));
+    if (c->profile_on) { cudaEventRecord(c->ev[0], st); cudaEventRecord(c->ev[1], st); }
+    s = launch_inverse(c, k, d_yuv, yuv_stride, d_rgb, rgb_stride, nframes, d_invalid, st);
+    if (c->profile_on && s == H2Y_OK) { cudaEventRecord(c->ev[2], st); c->profile_valid = 1; }
+    return s;
+}
+
+h2y_status h2y_inverse_host(h2y_ctx *c, const h2y_inverse_params *p, const void *h_yuv, size_t yuv_stride, void *h_rgb,
+                            size_t rgb_stride, int nframes, uint32_t *h_invalid)
+{
+    if (!c || !p || !h_yuv || !h_rgb || nframes < 0) return H2Y_ERR_ARG;
+    if (nframes == 0) return H2Y_OK;
+    InvK k;
+    h2y_status s = make_invk(*p, &k);
+    if (s != H2Y_OK) return s;
+    const size_t inb = h2y_yuv_frame_bytes(p->width, p->height, H2Y_CHROMA_420), outb = h2y_rgb_frame_bytes(p);
+    if (yuv_stride < inb || rgb_stride < outb) return H2Y_ERR_ARG;
+    H2Y_CUDA(c, cudaSetDevice(c->device));
+    uint32_t *d_inv = nullptr;
+    if (h_invalid) {
+        void *v;
+        if ((s = scratch_reserve(c, SCR_STATS, sizeof(uint32_t) * (size_t)nframes + 64, &v)) != H2Y_OK) return s;
+        d_inv = (uint32_t *)v;
+    }
+    int done = 0;
+    s = run_pipeline(c, (const uint8_t *)h_yuv, yuv_stride, inb, (uint8_t *)h_rgb, rgb_stride, outb, nframes,
+                     [&](uint8_t *di, size_t ip, uint8_t *dob, size_t op, int nf, cudaStream_t st) {
+                         if (d_inv) cudaMemsetAsync(d_inv + done, 0, sizeof(uint32_t) * nf, st);
+                         h2y_status r = launch_inverse(c, k, di, ip, dob, op, nf, d_inv ? d_inv + done : nullptr, st);
+                         done += nf;
+                         return r;
+                     });
+    if (s != H2Y_OK) return s;
+    if (h_invalid) H2Y_CUDA(c, cudaMemcpy(h_invalid, d_inv, sizeof(uint32_t) * (size_t)nframes, cudaMemcpyDeviceToHost));
+    return H2Y_OK;
+}
+
+}   // extern "C"

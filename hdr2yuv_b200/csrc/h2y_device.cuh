@@ -1,0 +1,231 @@
+// h2y_device.cuh -- device-side building blocks shared by every kernel of the hot path.
+//
+// Everything here reproduces the reference's C++ arithmetic bit for bit:
+// float vs double per sub-expression, no FMA contraction (this TU set is compiled with
+// -fmad=false and the parity-critical expressions use the explicit _rn intrinsics anyway),
+// truncation toward zero, the signed/unsigned clamp quirk and the Half-1 chroma offset.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hdr2yuv_b200.h"
+
+namespace h2y {
+
+// ---- per-launch constants ------------------------------------------------------------------
+
+// colour-difference family selected by out->matrix_coeffs (convert.cpp:1159-1198)
+enum MatKind : int { MK_PASS = 0, MK_YDZDX = 1, MK_YCBCR = 2, MK_Y100 = 3, MK_PRIME2 = 4 };
+
+// transfer functions of convert.cpp:12-87 as used by the two steps of convert.cpp:1021-1109
+enum TfKind : int { TF_NONE = 0, TF_PQ = 1, TF_RHO = 2, TF_GAMMA = 3 };
+
+enum ScaleMode : int { SC_NONE = 0, SC_FULL = 1, SC_VIDEO = 2, SC_FLOAT_OUT = 3 };
+
+struct PixK {
+    // matrix stage
+    int mat_kind;
+    double wr, wg, wb;   // luma weights (convert.cpp:1177, 1182)
+    double db, dr;       // chroma divisors 1.8814/1.4746 or 1.8556/1.5748
+    double rdb, rdr;     // RN(1/db), RN(1/dr) for the reciprocal fast path
+    float P, Q, RR, S;   // Y100/Y500 (convert.cpp:911-925)
+    int half_m1;         // clip->Half - 1 of the tmp picture (convert.cpp:1200-1201)
+    unsigned maxCV;      // clip->maxCV of the tmp picture (convert.cpp:1207-1213)
+    // transfer stage (only when the transfer changes)
+    int convert_transfer;
+    int tf_linearise;    // TfKind applied when src transfer != LINEAR (convert.cpp:1024-1064)
+    int tf_encode;       // TfKind applied when dst transfer != LINEAR (convert.cpp:1068-1109)
+    int scale_mode;      // convert.cpp:1116-1144
+    float mulY, addY, mulC, addC;
+    // write_yuv stage (tiff.cpp:457-550) at the output depth
+    int down_shift;
+    unsigned loY, hiY, loC, hiC;
+    // on-read clip of read_tiff (tiff.cpp:296-304), applied to 16-bit codes when enabled
+    int clip_on_load;
+    unsigned loadLo, loadHi;
+};
+
+// ---- x86-64 conversion semantics -------------------------------------------------------------
+
+// (unsigned int)float on x86-64 is a 64-bit cvttss2si whose low half is kept.
+__device__ __forceinline__ unsigned f2u_x86(float x) { return (unsigned)__float2ll_rz(x); }
+
+// (int)double is a 32-bit cvttsd2si: NaN / out of range give INT_MIN.
+__device__ __forceinline__ int d2i_x86(double x)
+{
+    int k = __double2int_rz(x);
+    if (!(x > -2147483649.0 && x < 2147483648.0)) k = (int)0x80000000;
+    return k;
+}
+
+__device__ __forceinline__ int f2i_x86(float x)
+{
+    int k = __float2int_rz(x);
+    if (!(x > -2147483904.0f && x < 2147483648.0f)) k = (int)0x80000000;
+    return k;
+}
+
+__device__ __forceinline__ float half_bits_to_float(unsigned h) { return __half2float(__ushort_as_half((unsigned short)h)); }
+
+// ---- transfer functions in double, float in/out (convert.cpp:12-87) --------------------------
+
+__device__ __forceinline__ float tf_pq_eotf(float V)
+{
+    double vp = pow((double)V, 1.0 / 78.84375);
+    double num = fmax(__dadd_rn(vp, -0.8359375), 0.0);
+    double den = __dadd_rn(18.8515625, -__dmul_rn(18.6875, vp));
+    return __double2float_rn(pow(__ddiv_rn(num, den), 1.0 / 0.1593017578));
+}
+
+__device__ __forceinline__ float tf_pq_oetf(float L)
+{
+    double lp = pow((double)L, 0.1593017578);
+    double num = __dadd_rn(0.8359375, __dmul_rn(18.8515625, lp));
+    double den = __dadd_rn(1.0, __dmul_rn(18.6875, lp));
+    return __double2float_rn(pow(__ddiv_rn(num, den), 78.84375));
+}
+
+// BT.1886 with the fixed call arguments gamma=2.4f, Lw=1, Lb=0: a = 1, b = 0 (convert.cpp:67-87, 1051-1057)
+__device__ __forceinline__ float tf_gamma_eotf(float V)
+{
+    float vb = __fadd_rn(V, 0.0f);
+    return __double2float_rn(__dmul_rn(1.0, pow(fmax((double)vb, 0.0), (double)2.4f)));
+}
+
+__device__ __forceinline__ float tf_gamma_oetf(float L)
+{
+    float la = __fdiv_rn(L, 1.0f);
+    return __double2float_rn(__dadd_rn(pow(fmax((double)la, 0.0), __ddiv_rn(1.0, (double)2.4f)), -0.0));
+}
+
+// rho-gamma: pow(rho, V) and log(rho) resolve to the float overloads in the reference's C++
+// (convert.cpp:24, 36); glibc's powf/logf are correctly rounded in practice, emulated by
+// rounding the double result.
+__device__ __forceinline__ float tf_rho_eotf(float V)
+{
+    float rv = __double2float_rn(pow(25.0, (double)V));
+    double base = __ddiv_rn(__dadd_rn((double)rv, -1.0), 24.0);
+    return __double2float_rn(pow(base, (double)2.4f));
+}
+
+__device__ __forceinline__ float tf_rho_oetf(float L)
+{
+    double lg = pow((double)L, __ddiv_rn(1.0, (double)2.4f));
+    double num = log(__dadd_rn(1.0, __dmul_rn(24.0, lg)));
+    float lrho = __double2float_rn(log(25.0));
+    return __double2float_rn(__ddiv_rn(num, (double)lrho));
+}
+
+// normalised sample -> destination transfer domain (convert.cpp:1021-1109)
+__device__ __forceinline__ float change_transfer(float x, int tf_linearise, int tf_encode)
+{
+    if (tf_linearise == TF_PQ) x = tf_pq_eotf(x);
+    else if (tf_linearise == TF_RHO) x = tf_rho_eotf(x);
+    else if (tf_linearise == TF_GAMMA) x = tf_gamma_eotf(x);
+    if (tf_encode == TF_PQ) x = tf_pq_oetf(x);
+    else if (tf_encode == TF_RHO) x = tf_rho_oetf(x);
+    else if (tf_encode == TF_GAMMA) x = tf_gamma_oetf(x);
+    return x;
+}
+
+// range scale after the transfer change (convert.cpp:1116-1144), U16 destination
+__device__ __forceinline__ void scale_to_codes(float &G, float &B, float &R, const PixK &k)
+{
+    if (k.scale_mode == SC_FULL) {
+        G = __fmul_rn(G, k.mulY);
+        B = __fmul_rn(B, k.mulY);
+        R = __fmul_rn(R, k.mulY);
+    } else if (k.scale_mode == SC_VIDEO) {
+        G = __fadd_rn(__fmul_rn(G, k.mulY), k.addY);
+        B = __fadd_rn(__fmul_rn(B, k.mulC), k.addC);
+        R = __fadd_rn(__fmul_rn(R, k.mulC), k.addC);
+    }
+}
+
+// ---- colour-difference stage, exact form (convert.cpp:1146-1220) -----------------------------
+
+template <int MK>
+__device__ __forceinline__ void px_matrix_exact(float G, float B, float R, const PixK &k, unsigned &Yo,
+                                                unsigned &Cbo, unsigned &Cro)
+{
+    unsigned y;
+    long long cb, cr;
+    if (MK == MK_PASS) {
+        y = f2u_x86(G);
+        cb = f2u_x86(B);
+        cr = f2u_x86(R);
+    } else {
+        if (MK == MK_YDZDX) {
+            y = f2u_x86(G);
+            double hg = __dmul_rn((double)(-G), 0.5);   // -G/2.0 is exact
+            cb = d2i_x86(__dadd_rn(__dadd_rn(hg, __dmul_rn((double)B, 0.5)), 0.5));
+            cr = d2i_x86(__dadd_rn(__dadd_rn(hg, __dmul_rn((double)R, 0.5)), 0.5));
+        } else if (MK == MK_YCBCR) {
+            double s = __dadd_rn(__dadd_rn(__dmul_rn(k.wr, (double)R), __dmul_rn(k.wg, (double)G)),
+                                 __dmul_rn(k.wb, (double)B));
+            float tmpF = __double2float_rn(__dadd_rn(s, 0.5));
+            y = f2u_x86(tmpF);
+            cb = d2i_x86(__dadd_rn(__ddiv_rn((double)__fsub_rn(B, tmpF), k.db), 0.5));
+            cr = d2i_x86(__dadd_rn(__ddiv_rn((double)__fsub_rn(R, tmpF), k.dr), 0.5));
+        } else if (MK == MK_Y100) {
+            y = f2u_x86(G);
+            cb = d2i_x86(__dadd_rn((double)__fadd_rn(__fmul_rn(k.P, G), __fmul_rn(k.Q, B)), 0.5));
+            cr = d2i_x86(__dadd_rn((double)__fadd_rn(__fmul_rn(k.RR, R), __fmul_rn(k.S, G)), 0.5));
+        } else {   // MK_PRIME2 in the 4:4:4 stage is a copy (convert.cpp:1191-1194)
+            y = f2u_x86(G);
+            cb = f2u_x86(B);
+            cr = f2u_x86(R);
+        }
+        cb += k.half_m1;
+        cr += k.half_m1;
+    }
+    // Y is unsigned; chroma is compared through unsigned long, so negatives clamp to maxCV
+    Yo = y > k.maxCV ? k.maxCV : y;
+    Cbo = (unsigned long long)cb > (unsigned long long)k.maxCV ? k.maxCV : (unsigned)cb;
+    Cro = (unsigned long long)cr > (unsigned long long)k.maxCV ? k.maxCV : (unsigned)cr;
+}
+
+// ---- write_yuv's shift + range clamp (tiff.cpp:457-550) --------------------------------------
+__device__ __forceinline__ unsigned out_clamp(unsigned v, int shift, unsigned lo, unsigned hi)
+{
+    v >>= shift;
+    v = v < lo ? lo : v;
+    return v > hi ? hi : v;
+}
+
+// ---- FIR taps in the reference's float order (convert.cpp:305-311, 365-370) ------------------
+// 7-tap horizontal, co-sited: inputs are s[x-5],s[x-3],s[x-1],s[x],s[x+1],s[x+3],s[x+5]
+__device__ __forceinline__ unsigned fir_h7(float m5, float m3, float m1, float c, float p1, float p3, float p5,
+                                           float maxCV)
+{
+    const float k21 = 21.0f / 512.0f, k52 = 52.0f / 512.0f, k159 = 159.0f / 512.0f, k256 = 256.0f / 512.0f;
+    float t = __fmul_rn(k21, __fadd_rn(m5, p5));
+    t = __fsub_rn(t, __fmul_rn(k52, __fadd_rn(m3, p3)));
+    t = __fadd_rn(t, __fmul_rn(k159, __fadd_rn(m1, p1)));
+    t = __fadd_rn(t, __fmul_rn(k256, c));
+    t = __fadd_rn(t, 0.5f);
+    t = fminf(t, maxCV);
+    t = fmaxf(t, 0.0f);
+    return (unsigned)__float2int_rz(t);
+}
+
+// 12-tap vertical, half-phase: r[0..11] are rows y-5 .. y+6
+__device__ __forceinline__ unsigned fir_v12(const float r[12], float maxCV)
+{
+    const float k228 = 228.0f / 512.0f, k70 = 70.0f / 512.0f, k37 = 37.0f / 512.0f, k21 = 21.0f / 512.0f,
+                k11 = 11.0f / 512.0f, k5 = 5.0f / 512.0f;
+    float t = __fmul_rn(k228, __fadd_rn(r[5], r[6]));
+    t = __fadd_rn(t, __fmul_rn(k70, __fadd_rn(r[4], r[7])));
+    t = __fsub_rn(t, __fmul_rn(k37, __fadd_rn(r[3], r[8])));
+    t = __fsub_rn(t, __fmul_rn(k21, __fadd_rn(r[2], r[9])));
+    t = __fadd_rn(t, __fmul_rn(k11, __fadd_rn(r[1], r[10])));
+    t = __fadd_rn(t, __fmul_rn(k5, __fadd_rn(r[0], r[11])));
+    t = __fadd_rn(t, 0.5f);
+    t = fminf(t, maxCV);
+    t = fmaxf(t, 0.0f);
+    return (unsigned)__float2int_rz(t);
+}
+
+}   // namespace h2y

@@ -1,0 +1,326 @@
+// h2y_staged.cu -- one simple kernel per reference function, planar buffers, any geometry.
+//
+// These back the staged C-ABI entry points (h2y_matrix_convert, h2y_convert,
+// h2y_write_yuv_clamp, h2y_subsample_420_to_444) that exist so parity of INTERMEDIATES can be
+// tested, and they are the general-geometry route of h2y_forward when the fused kernel's
+// vector path does not apply (width not a multiple of 8, planar-float input, ...).  They
+// evaluate the transfer functions directly in FP64 per pixel (no LUT), which also makes them an
+// independent on-GPU check of the LUT route.  One thread per sample; not the fast path.
+#include "h2y_internal.h"
+
+namespace h2y {
+
+// ---- matrix_convert (convert.cpp:879-1315) -----------------------------------------------------
+
+__device__ __forceinline__ void px_matrix_f32out(int mk, float G, float B, float R, const PixK &k, float half,
+                                                 float &Y, float &Cb, float &Cr)
+{
+    if (mk == MK_PASS) { Y = G; Cb = B; Cr = R; }
+    else {
+        if (mk == MK_YDZDX) {
+            Y = G;
+            double hg = __dmul_rn((double)(-G), 0.5);
+            Cb = __double2float_rn(__dadd_rn(__dadd_rn(hg, __dmul_rn((double)B, 0.5)), 0.5));
+            Cr = __double2float_rn(__dadd_rn(__dadd_rn(hg, __dmul_rn((double)R, 0.5)), 0.5));
+        } else if (mk == MK_YCBCR) {
+            double s = __dadd_rn(__dadd_rn(__dmul_rn(k.wr, (double)R), __dmul_rn(k.wg, (double)G)),
+                                 __dmul_rn(k.wb, (double)B));
+            float tmpF = __double2float_rn(__dadd_rn(s, 0.5));
+            Y = tmpF;
+            Cb = __double2float_rn(__dadd_rn(__ddiv_rn((double)__fsub_rn(B, tmpF), k.db), 0.5));
+            Cr = __double2float_rn(__dadd_rn(__ddiv_rn((double)__fsub_rn(R, tmpF), k.dr), 0.5));
+        } else if (mk == MK_Y100) {
+            Y = G;
+            Cb = __double2float_rn(__dadd_rn((double)__fadd_rn(__fmul_rn(k.P, G), __fmul_rn(k.Q, B)), 0.5));
+            Cr = __double2float_rn(__dadd_rn((double)__fadd_rn(__fmul_rn(k.RR, R), __fmul_rn(k.S, G)), 0.5));
+        } else { Y = G; Cb = B; Cr = R; }
+        Cb = __fsub_rn(__fadd_rn(Cb, half), 1.0f);     // Cb + clip->Half - 1, convert.cpp:1280-1281
+        Cr = __fsub_rn(__fadd_rn(Cr, half), 1.0f);
+    }
+    const float hi = (float)k.maxCV;
+    if (Y > hi) Y = hi;
+    if (Y < 0.0f) Y = 0.0f;
+    if (Cb > hi) Cb = hi;
+    if (Cb < 0.0f) Cb = 0.0f;
+    if (Cr > hi) Cr = hi;
+    if (Cr < 0.0f) Cr = 0.0f;
+}
+
+template <bool IN_F32, bool OUT_F32>
+__global__ void __launch_bounds__(256)
+k_matrix_convert(PixK k, NormK nk, long npix, const void *in0, const void *in1, const void *in2, void *out0,
+                 void *out1, void *out2)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float G, B, R;
+    if (IN_F32) {
+        G = ((const float *)in0)[i]; B = ((const float *)in1)[i]; R = ((const float *)in2)[i];
+    } else {
+        G = (float)((const uint16_t *)in0)[i]; B = (float)((const uint16_t *)in1)[i]; R = (float)((const uint16_t *)in2)[i];
+    }
+    if (k.convert_transfer) {
+        G = change_transfer(__fdiv_rn(__fsub_rn(G, nk.offset[0]), nk.range[0]), k.tf_linearise, k.tf_encode);
+        B = change_transfer(__fdiv_rn(__fsub_rn(B, nk.offset[1]), nk.range[1]), k.tf_linearise, k.tf_encode);
+        R = change_transfer(__fdiv_rn(__fsub_rn(R, nk.offset[2]), nk.range[2]), k.tf_linearise, k.tf_encode);
+        if (OUT_F32) {                                  // convert.cpp:1116-1122
+            G = __fadd_rn(__fmul_rn(G, nk.range[0]), nk.offset[0]);
+            B = __fadd_rn(__fmul_rn(B, nk.range[1]), nk.offset[1]);
+            R = __fadd_rn(__fmul_rn(R, nk.range[2]), nk.offset[2]);
+        } else scale_to_codes(G, B, R, k);
+    }
+    if (OUT_F32) {
+        float Y, Cb, Cr;
+        px_matrix_f32out(k.mat_kind, G, B, R, k, (float)(k.half_m1 + 1), Y, Cb, Cr);
+        ((float *)out0)[i] = Y; ((float *)out1)[i] = Cb; ((float *)out2)[i] = Cr;
+    } else {
+        unsigned Y, Cb, Cr;
+        switch (k.mat_kind) {
+        case MK_PASS: px_matrix_exact<MK_PASS>(G, B, R, k, Y, Cb, Cr); break;
+        case MK_YDZDX: px_matrix_exact<MK_YDZDX>(G, B, R, k, Y, Cb, Cr); break;
+        case MK_YCBCR: px_matrix_exact<MK_YCBCR>(G, B, R, k, Y, Cb, Cr); break;
+        case MK_Y100: px_matrix_exact<MK_Y100>(G, B, R, k, Y, Cb, Cr); break;
+        default: px_matrix_exact<MK_PRIME2>(G, B, R, k, Y, Cb, Cr); break;
+        }
+        ((uint16_t *)out0)[i] = (uint16_t)Y; ((uint16_t *)out1)[i] = (uint16_t)Cb; ((uint16_t *)out2)[i] = (uint16_t)Cr;
+    }
+}
+
+h2y_status launch_matrix_convert(h2y_ctx_impl *c, const PixK &k, const NormK &nk, int w, int h, int in_is_f32,
+                                 const void *const d_in[3], int out_is_f32, void *const d_out[3], cudaStream_t st)
+{
+    const long npix = (long)w * h;
+    const int blocks = (int)((npix + 255) / 256);
+#define MC(A, B) k_matrix_convert<A, B><<<blocks, 256, 0, st>>>(k, nk, npix, d_in[0], d_in[1], d_in[2], d_out[0], d_out[1], d_out[2])
+    if (in_is_f32 && out_is_f32) MC(true, true);
+    else if (in_is_f32) MC(true, false);
+    else if (out_is_f32) MC(false, true);
+    else MC(false, false);
+#undef MC
+    c->launches++;
+    H2Y_CUDA(c, cudaGetLastError());
+    return H2Y_OK;
+}
+
+// ---- reader de-interleave (tiff.cpp:265-315, exr.cpp:209-235) -----------------------------------
+// u16 layouts -> three u16 planes (with the on-read clip); half layouts -> three float planes.
+__global__ void __launch_bounds__(256)
+k_unpack(int layout, long npix, const uint16_t *__restrict__ src, void *o0, void *o1, void *o2, int clip_on,
+         unsigned lo, unsigned hi)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    unsigned v[3];
+    if (layout == H2Y_LAYOUT_PLANAR_U16) { v[0] = src[i]; v[1] = src[npix + i]; v[2] = src[2 * npix + i]; }
+    else {
+        const int nch = (layout == H2Y_LAYOUT_RGBA16 || layout == H2Y_LAYOUT_HALF_RGBA) ? 4 : 3;
+        const uint16_t *p = src + i * nch;
+        v[0] = p[1]; v[1] = p[2]; v[2] = p[0];
+    }
+    if (layout == H2Y_LAYOUT_HALF_RGB || layout == H2Y_LAYOUT_HALF_RGBA) {
+        ((float *)o0)[i] = half_bits_to_float(v[0]);
+        ((float *)o1)[i] = half_bits_to_float(v[1]);
+        ((float *)o2)[i] = half_bits_to_float(v[2]);
+    } else {
+        if (clip_on)
+            for (int c = 0; c < 3; c++) { v[c] = v[c] < lo ? lo : v[c]; v[c] = v[c] > hi ? hi : v[c]; }
+        ((uint16_t *)o0)[i] = (uint16_t)v[0];
+        ((uint16_t *)o1)[i] = (uint16_t)v[1];
+        ((uint16_t *)o2)[i] = (uint16_t)v[2];
+    }
+}
+
+h2y_status launch_unpack(h2y_ctx_impl *c, int layout, int w, int h, const void *d_src, void *const d_planes[3],
+                         int clip_on_load, unsigned lo, unsigned hi, cudaStream_t st)
+{
+    const long npix = (long)w * h;
+    k_unpack<<<(int)((npix + 255) / 256), 256, 0, st>>>(layout, npix, (const uint16_t *)d_src, d_planes[0], d_planes[1],
+                                                         d_planes[2], clip_on_load, lo, hi);
+    c->launches++;
+    H2Y_CUDA(c, cudaGetLastError());
+    return H2Y_OK;
+}
+
+// ---- Subsample444to420_FIR (convert.cpp:261-383), two passes with the u16 intermediate ---------
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__global__ void __launch_bounds__(256)
+k_fir_h(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int w, int h, float maxCV)
+{
+    const int wh = w >> 1;
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)wh * h) return;
+    const int y = (int)(i / wh), x = 2 * (int)(i % wh);
+    const uint16_t *s = src + (long)y * w;
+    dst[i] = (uint16_t)fir_h7((float)s[clampi(x - 5, 0, w - 1)], (float)s[clampi(x - 3, 0, w - 1)],
+                              (float)s[clampi(x - 1, 0, w - 1)], (float)s[x], (float)s[clampi(x + 1, 0, w - 1)],
+                              (float)s[clampi(x + 3, 0, w - 1)], (float)s[clampi(x + 5, 0, w - 1)], maxCV);
+}
+
+__global__ void __launch_bounds__(256)
+k_fir_v(const uint16_t *__restrict__ mid, uint16_t *__restrict__ dst, int wh, int h, float maxCV)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int hh = h >> 1;
+    if (i >= (long)wh * hh) return;
+    const int j = (int)(i / wh), x = (int)(i % wh), y = 2 * j;
+    float r[12];
+#pragma unroll
+    for (int t = 0; t < 12; t++) r[t] = (float)mid[(long)clampi(y - 5 + t, 0, h - 1) * wh + x];
+    dst[i] = (uint16_t)fir_v12(r, maxCV);
+}
+
+h2y_status launch_fir_420(h2y_ctx_impl *c, const uint16_t *d_src, uint16_t *d_dst, uint16_t *d_mid, int w, int h,
+                          unsigned maxCV, cudaStream_t st)
+{
+    const int wh = w >> 1;
+    const long n1 = (long)wh * h, n2 = (long)wh * (h >> 1);
+    k_fir_h<<<(int)((n1 + 255) / 256), 256, 0, st>>>(d_src, d_mid, w, h, (float)maxCV);
+    k_fir_v<<<(int)((n2 + 255) / 256), 256, 0, st>>>(d_mid, d_dst, wh, h, (float)maxCV);
+    c->launches += 2;
+    H2Y_CUDA(c, cudaGetLastError());
+    return H2Y_OK;
+}
+
+h2y_status launch_fir_422(h2y_ctx_impl *c, const uint16_t *d_src, uint16_t *d_dst, int w, int h, unsigned maxCV,
+                          cudaStream_t st)
+{
+    const long n1 = (long)(w >> 1) * h;
+    k_fir_h<<<(int)((n1 + 255) / 256), 256, 0, st>>>(d_src, d_dst, w, h, (float)maxCV);
+    c->launches++;
+    H2Y_CUDA(c, cudaGetLastError());
+    return H2Y_OK;
+}
+
+// ---- Subsample444to420_box (convert.cpp:91-172) --------------------------------------------------
+// The reference walks 4x4 blocks and reads out of bounds unless w and h are multiples of 4; the
+// API layer rejects other sizes.
+__global__ void __launch_bounds__(256)
+k_box(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int w, int h)
+{
+    const int wh = w / 2, hh = h / 2;
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)wh * hh) return;
+    const int j = (int)(i / wh), x = (int)(i % wh);
+    const uint16_t *p = src + (long)(2 * j) * w + 2 * x;
+    unsigned sum = (unsigned)p[0] + p[1] + p[w] + p[w + 1];
+    dst[i] = (uint16_t)(sum / 4);
+}
+
+h2y_status launch_box_420(h2y_ctx_impl *c, const uint16_t *d_src, uint16_t *d_dst, int w, int h, cudaStream_t st)
+{
+    const long n = (long)(w / 2) * (h / 2);
+    k_box<<<(int)((n + 255) / 256), 256, 0, st>>>(d_src, d_dst, w, h);
+    c->launches++;
+    H2Y_CUDA(c, cudaGetLastError());
+    return H2Y_OK;
+}
+
+// ---- write_yuv compute stage (tiff.cpp:457-550) ---------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_out_clamp(uint16_t *p, size_t n, int shift, unsigned lo, unsigned hi)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint16_t)out_clamp(p[i], shift, lo, hi);
+}
+
+h2y_status launch_out_clamp(h2y_ctx_impl *c, uint16_t *d_plane, size_t n, int shift, unsigned lo, unsigned hi,
+                            cudaStream_t st)
+{
+    if (n == 0) return H2Y_OK;
+    k_out_clamp<<<(int)((n + 255) / 256), 256, 0, st>>>(d_plane, n, shift, lo, hi);
+    c->launches++;
+    H2Y_CUDA(c, cudaGetLastError());
+    return H2Y_OK;
+}
+
+// ---- Subsample420to444 (yuv2tiff.cpp:575-692), row-major ------------------------------------------
+__device__ __forceinline__ unsigned up_finish(float t, float lo, float hi)
+{
+    t = __fadd_rn(t, 0.5f);
+    if (t > hi) t = hi;
+    if (t < lo) t = lo;
+    return (unsigned)__float2int_rz(t);
+}
+
+// vertical 2-phase 6-tap: src wh x hh -> mid wh x h
+__global__ void __launch_bounds__(256)
+k_up_v(const uint16_t *__restrict__ src, uint16_t *__restrict__ mid, int wh, int hh, float lo, float hi)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)wh * hh) return;
+    const int j = (int)(i / wh), x = (int)(i % wh);
+    const float a3 = 3.0f / 256.0f, a16 = 16.0f / 256.0f, a67 = 67.0f / 256.0f, a227 = 227.0f / 256.0f,
+                a32 = 32.0f / 256.0f, a7 = 7.0f / 256.0f;
+    float m3 = (float)src[(long)clampi(j - 3, 0, hh - 1) * wh + x], m2 = (float)src[(long)clampi(j - 2, 0, hh - 1) * wh + x],
+          m1 = (float)src[(long)clampi(j - 1, 0, hh - 1) * wh + x], c0 = (float)src[(long)j * wh + x],
+          p1 = (float)src[(long)clampi(j + 1, 0, hh - 1) * wh + x], p2 = (float)src[(long)clampi(j + 2, 0, hh - 1) * wh + x],
+          p3 = (float)src[(long)clampi(j + 3, 0, hh - 1) * wh + x];
+    float t = __fmul_rn(a3, m3);
+    t = __fsub_rn(t, __fmul_rn(a16, m2));
+    t = __fadd_rn(t, __fmul_rn(a67, m1));
+    t = __fadd_rn(t, __fmul_rn(a227, c0));
+    t = __fsub_rn(t, __fmul_rn(a32, p1));
+    t = __fadd_rn(t, __fmul_rn(a7, p2));
+    mid[(long)(2 * j) * wh + x] = (uint16_t)up_finish(t, lo, hi);
+    t = __fmul_rn(a3, p3);
+    t = __fsub_rn(t, __fmul_rn(a16, p2));
+    t = __fadd_rn(t, __fmul_rn(a67, p1));
+    t = __fadd_rn(t, __fmul_rn(a227, c0));
+    t = __fsub_rn(t, __fmul_rn(a32, m1));
+    t = __fadd_rn(t, __fmul_rn(a7, m2));
+    mid[(long)(2 * j + 1) * wh + x] = (uint16_t)up_finish(t, lo, hi);
+}
+
+// horizontal: mid wh x h -> dst w x h
+__global__ void __launch_bounds__(256)
+k_up_h(const uint16_t *__restrict__ mid, uint16_t *__restrict__ dst, int wh, int h, float lo, float hi)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)wh * h) return;
+    const int y = (int)(i / wh), x = (int)(i % wh);
+    const uint16_t *r = mid + (long)y * wh;
+    const float b21 = 21.0f / 256.0f, b52 = 52.0f / 256.0f, b159 = 159.0f / 256.0f;
+    float l2 = (float)r[clampi(x - 2, 0, wh - 1)], l1 = (float)r[clampi(x - 1, 0, wh - 1)], c0 = (float)r[x],
+          r1 = (float)r[clampi(x + 1, 0, wh - 1)], r2 = (float)r[clampi(x + 2, 0, wh - 1)],
+          r3 = (float)r[clampi(x + 3, 0, wh - 1)];
+    float t = __fmul_rn(b21, __fadd_rn(l2, r3));
+    t = __fsub_rn(t, __fmul_rn(b52, __fadd_rn(l1, r2)));
+    t = __fadd_rn(t, __fmul_rn(b159, __fadd_rn(c0, r1)));
+    uint16_t *o = dst + (long)y * (2 * wh) + 2 * x;
+    o[0] = r[x];
+    o[1] = (uint16_t)up_finish(t, lo, hi);
+}
+
+__global__ void __launch_bounds__(256)
+k_up_box(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int wh, int hh)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)wh * hh) return;
+    const int j = (int)(i / wh), x = (int)(i % wh), w = 2 * wh;
+    const uint16_t v = src[i];
+    dst[(long)(2 * j) * w + 2 * x] = v;
+    dst[(long)(2 * j) * w + 2 * x + 1] = v;
+    dst[(long)(2 * j + 1) * w + 2 * x] = v;
+    dst[(long)(2 * j + 1) * w + 2 * x + 1] = v;
+}
+
+h2y_status launch_upsample(h2y_ctx_impl *c, const uint16_t *d_src, uint16_t *d_dst, uint16_t *d_mid, int w, int h,
+                           int fir, unsigned minCV, unsigned maxCV, cudaStream_t st)
+{
+    const int wh = w / 2, hh = h / 2;
+    const long n = (long)wh * hh;
+    if (!fir) {
+        k_up_box<<<(int)((n + 255) / 256), 256, 0, st>>>(d_src, d_dst, wh, hh);
+        c->launches++;
+    } else {
+        k_up_v<<<(int)((n + 255) / 256), 256, 0, st>>>(d_src, d_mid, wh, hh, (float)minCV, (float)maxCV);
+        const long n2 = (long)wh * h;
+        k_up_h<<<(int)((n2 + 255) / 256), 256, 0, st>>>(d_mid, d_dst, wh, h, (float)minCV, (float)maxCV);
+        c->launches += 2;
+    }
+    H2Y_CUDA(c, cudaGetLastError());
+    return H2Y_OK;
+}
+
+}   // namespace h2y

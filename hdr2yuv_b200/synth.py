@@ -1,0 +1,53 @@
+"""Synthetic frames for tests and bench.py: seeded, numpy only.
+
+There is no network and the reference ships no clips, so every workload is synthetic:
+  tiff16_frame  -- what a 16-bit X'Y'Z' PQ TIFF strip row looks like to read_tiff: interleaved
+                   R,G,B u16, uniform over the video range plus a 1 % sprinkle of out-of-range codes
+                   that exercise the on-read clip (tiff.cpp:296-304)
+  exr_half_frame -- linear-light half-float RGB(A) "in nits": log-uniform in [0.005, 4000], exact
+                   zeros present, all >= 0 and frame max >= 1 (else the reference divides by a zero
+                   range, common.cpp:135-136 / convert.cpp:939)
+"""
+import numpy as np
+
+
+def tiff16_frame(width, height, seed=1, channels=3, smooth=False):
+    rng = np.random.default_rng(seed)
+    if smooth:
+        y, x = np.mgrid[0:height, 0:width]
+        base = 4096 + (56064 * (0.5 + 0.5 * np.sin(x / 97.0) * np.cos(y / 61.0)))
+        px = np.stack([base, np.roll(base, 13, 1), np.roll(base, 29, 0)], -1)
+        px = px + rng.integers(-64, 65, px.shape)
+        px = np.clip(px, 0, 65535).astype(np.uint16)
+    else:
+        px = rng.integers(4096, 60161, (height, width, 3), dtype=np.uint16)
+    spr = rng.random((height, width, 3)) < 0.01
+    px[spr] = rng.choice(np.array([0, 4095, 60161, 65535], np.uint16), int(spr.sum()))
+    if channels == 4:
+        a = np.full((height, width, 1), 65535, np.uint16)
+        px = np.concatenate([px, a], -1)
+    return np.ascontiguousarray(px)
+
+
+def exr_half_frame(width, height, seed=0, channels=4, lo=0.005, hi=4000.0, correlated=False):
+    """Returns (H, W, channels) uint16 half bit patterns, r,g,b(,a) order."""
+    rng = np.random.default_rng(seed)
+    if correlated:
+        base = np.exp(rng.uniform(np.log(lo), np.log(hi), (height, width, 1)))
+        v = base * rng.uniform(0.7, 1.3, (height, width, 3))
+        v = np.clip(v, 0.0, hi)
+    else:
+        v = np.exp(rng.uniform(np.log(lo), np.log(hi), (height, width, 3)))
+    h = v.astype(np.float16)
+    flat = h.reshape(-1)
+    flat[rng.integers(0, flat.size, max(3, flat.size // 1000))] = np.float16(0.0)
+    flat[rng.integers(0, flat.size)] = np.float16(hi)       # pin the frame maximum
+    if channels == 4:
+        a = np.full((height, width, 1), np.float16(1.0))
+        h = np.concatenate([h, a], -1)
+    return np.ascontiguousarray(h).view(np.uint16)
+
+
+def planes_from_interleaved(px):
+    """(H,W,C) r,g,b(,a) -> (3,H,W) in the reference's G,B,R plane order (tiff.cpp:309-311)."""
+    return np.ascontiguousarray(np.stack([px[..., 1], px[..., 2], px[..., 0]], 0))

@@ -1,0 +1,201 @@
+"""-m gpu parity tests of the forward path (h2y_forward and the staged entry points) against the
+golden vectors generated from the compiled reference and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import gpu_util as G
+from hdr2yuv_b200 import _cabi as cabi
+from hdr2yuv_b200 import api, synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _uses_transfer(src, dst):
+    return src["transfer"] != dst["transfer"]
+
+
+@pytest.mark.parametrize("name,src,dst", cases.FORWARD_CASES, ids=[c[0] for c in cases.FORWARD_CASES])
+def test_fused_forward_matches_golden(ctx, golden_forward, name, src, dst):
+    px = golden_forward[name + "/in"]
+    got = G.gpu_forward(ctx, [px], src, dst)[0]
+    G.compare_codes(got, golden_forward[name + "/yuv"], _uses_transfer(src, dst), name)
+
+
+@pytest.mark.parametrize("name,src,dst", cases.FORWARD_CASES[::3], ids=[c[0] for c in cases.FORWARD_CASES[::3]])
+def test_exact_math_and_staged_routes_agree(ctx, golden_forward, name, src, dst):
+    # the reciprocal fast path, the reference-order FP64 path and the staged kernels give the same codes
+    px = golden_forward[name + "/in"]
+    fast = G.gpu_forward(ctx, [px], src, dst)[0]
+    os.environ["H2Y_EXACT_MATH"] = "1"
+    try:
+        exact = G.gpu_forward(ctx, [px], src, dst)[0]
+    finally:
+        del os.environ["H2Y_EXACT_MATH"]
+    os.environ["H2Y_FORCE_STAGED"] = "1"
+    try:
+        staged = G.gpu_forward(ctx, [px], src, dst)[0]
+    finally:
+        del os.environ["H2Y_FORCE_STAGED"]
+    assert np.array_equal(fast, exact)
+    G.compare_codes(staged, fast, _uses_transfer(src, dst), name + " staged-vs-fused")
+
+
+_TIFF = dict(kind="tiff16", bit_depth=16, full_range=0, transfer=16, primaries=10, matrix=0)
+_HALF = dict(kind="half", bit_depth=32, full_range=1, transfer=8, primaries=1, matrix=0)
+
+
+@pytest.mark.parametrize("w,h", [(8, 12), (240, 64), (248, 34), (488, 130), (1000, 96), (1920, 1080)])
+@pytest.mark.parametrize("matrix", [9, 11])
+def test_fused_forward_sizes_tiff(ctx, w, h, matrix):
+    # config 1 / 3 shape: 16-bit X'Y'Z' through read_tiff's clip, no transfer change -> bit exact
+    for chroma, res in ((1, 1), (1, 0), (3, 1), (2, 1)):
+        if res == 0 and (w % 4 or h % 4):
+            continue
+        if h > 500 and (chroma, res) != (1, 1):
+            continue
+        dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=matrix, chroma=chroma, resampler=res)
+        frames = [synth.tiff16_frame(w, h, seed=s, smooth=bool(s & 1)) for s in (1, 2)]
+        got = G.gpu_forward(ctx, frames, _TIFF, dst)
+        for f, g in zip(frames, got):
+            G.compare_codes(g, G.oracle_forward(f, _TIFF, dst), False, "tiff %dx%d c%d r%d" % (w, h, chroma, res))
+
+
+@pytest.mark.parametrize("w,h", [(16, 14), (240, 48), (496, 270), (1920, 1080)])
+def test_fused_forward_sizes_half_pq(ctx, w, h):
+    # config 2 / 5 shape: half RGBA linear light -> PQ; per-frame statistics differ inside one batch
+    for bd, ch in ((10, 4), (12, 3)):
+        dst = dict(bit_depth=bd, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+        frames = [synth.exr_half_frame(w, h, seed=0, channels=ch), synth.exr_half_frame(w, h, seed=1, channels=ch, hi=350.0),
+                  synth.exr_half_frame(w, h, seed=2, channels=ch, correlated=True)]
+        frames[1][..., 0] = np.minimum(frames[1][..., 0], np.float16(100.0).view(np.uint16))  # per-channel ranges differ
+        got = G.gpu_forward(ctx, frames, _HALF, dst)
+        for f, g in zip(frames, got):
+            G.compare_codes(g, G.oracle_forward(f, _HALF, dst), True, "half %dx%d b%d" % (w, h, bd))
+
+
+def test_full_4k_frame_half_pq(ctx):
+    # BASELINE config 2 at full size, one frame through the oracle (about 3 s of CPU)
+    w, h = 3840, 2160
+    dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+    f = synth.exr_half_frame(w, h, seed=0, channels=4)
+    got = G.gpu_forward(ctx, [f, f], _HALF, dst)
+    assert np.array_equal(got[0], got[1])                      # batch position does not matter
+    nbad = G.compare_codes(got[0], G.oracle_forward(f, _HALF, dst), True, "4K half PQ")
+    print("4K PQ frame: %d of %d samples deviate by one code" % (nbad, got[0].size))
+    st = ctx.forward_last_stats(0)
+    assert list(st.estimated_floor) == [0, 0, 0] and list(st.estimated_ceiling) == [4000, 4000, 4000]
+
+
+def test_odd_geometry_takes_general_route(ctx):
+    # widths that are not a multiple of 8 go through the staged kernels inside h2y_forward
+    for w, h in ((100, 50), (36, 20)):
+        dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+        f = synth.tiff16_frame(w, h, seed=3)
+        G.compare_codes(G.gpu_forward(ctx, [f], _TIFF, dst)[0], G.oracle_forward(f, _TIFF, dst), False, "odd tiff")
+        f = synth.exr_half_frame(w, h, seed=3, channels=4)
+        G.compare_codes(G.gpu_forward(ctx, [f], _HALF, dst)[0], G.oracle_forward(f, _HALF, dst), True, "odd half")
+
+
+def test_staged_entry_points_match_oracle_intermediates(ctx, golden_forward):
+    # pic_stats -> matrix_convert -> convert -> write_yuv clamp, one C-ABI call per reference function
+    for name, src, dst in [c for c in cases.FORWARD_CASES if c[0] in ("tiff_m9_c1_r1_b10", "half_pq_m9_b10_f0", "half_rho_m9")]:
+        px = golden_forward[name + "/in"]
+        h, w = px.shape[:2]
+        is_u16 = src["kind"] == "tiff16"
+        planes = O.load_rgb16(px, src["full_range"]) if is_u16 else O.load_half(px)
+        d_in = [torch.from_numpy(planes[c].copy()).cuda() for c in range(3)]
+        in_pic = api.pic_desc(w, h, cabi.CHROMA_444, src["transfer"], src["primaries"], src["matrix"], src["bit_depth"],
+                              src["full_range"], cabi.PIC_TYPE_U16 if is_u16 else cabi.PIC_TYPE_F32,
+                              cabi.LAYOUT_PLANAR_U16 if is_u16 else cabi.LAYOUT_PLANAR_F32)
+        st = ctx.pic_stats(in_pic, d_in)
+        want_stats = golden_forward[name + "/stats"]
+        assert list(st.estimated_floor) + list(st.estimated_ceiling) == list(want_stats)
+        tmp_depth = src["bit_depth"] if is_u16 else dst["bit_depth"]
+        tmp_pic = api.pic_desc(w, h, cabi.CHROMA_444, dst["transfer"], dst["primaries"], dst["matrix"], tmp_depth,
+                               dst["full_range"])
+        d_tmp = [torch.zeros(h * w, dtype=torch.int16, device="cuda") for _ in range(3)]
+        ctx.matrix_convert(tmp_pic, d_tmp, in_pic, d_in, st)
+        torch.cuda.synchronize()
+        tmp = np.stack([t.cpu().numpy().view(np.uint16).reshape(h, w) for t in d_tmp])
+        G.compare_codes(tmp, golden_forward[name + "/tmp444"], _uses_transfer(src, dst), name + " tmp444")
+        out_pic = api.pic_desc(w, h, dst["chroma"], dst["transfer"], dst["primaries"], dst["matrix"], dst["bit_depth"],
+                               dst["full_range"])
+        d_out = [torch.zeros(h * w, dtype=torch.int16, device="cuda") for _ in range(3)]
+        ctx.convert(out_pic, d_out, tmp_pic, d_tmp, dst["resampler"])
+        ctx.write_yuv_clamp(out_pic, d_out, tmp_depth)
+        torch.cuda.synchronize()
+        pw, ph = api.plane_dims(w, h, dst["chroma"])
+        got = np.concatenate([d_out[c].cpu().numpy().view(np.uint16)[: pw[c] * ph[c]] for c in range(3)])
+        G.compare_codes(got, golden_forward[name + "/yuv"], _uses_transfer(src, dst), name + " staged yuv")
+
+
+def test_matrix_convert_float_output_twin(ctx):
+    # F32-output branch (convert.cpp:1222-1304), reachable through the staged call
+    w, h = 64, 16
+    px = synth.exr_half_frame(w, h, seed=9, channels=4)
+    planes = O.load_half(px)
+    import ctypes as C
+    for m in (9, 11, 13, 0):
+        pic = O._Pic(w, h, 3, 8, 1, 0, 32, 1, O.PIC_F32)
+        outp = O._Pic(w, h, 3, 16, 9 if m else 1, m, 12, 0, O.PIC_F32)
+        want = np.zeros((3, h, w), np.float32)
+        for c in range(3):
+            pic.fbuf[c] = planes[c].ctypes.data
+            outp.fbuf[c] = want[c].ctypes.data
+        O.port_lib().orc_pic_stats(C.byref(pic), None, None)
+        assert O.port_lib().orc_matrix_convert(C.byref(outp), C.byref(pic)) == 0
+        in_pic = api.pic_desc(w, h, 3, 8, 1, 0, 32, 1, cabi.PIC_TYPE_F32, cabi.LAYOUT_PLANAR_F32)
+        out_pic = api.pic_desc(w, h, 3, 16, 9 if m else 1, m, 12, 0, cabi.PIC_TYPE_F32, cabi.LAYOUT_PLANAR_F32)
+        d_in = [torch.from_numpy(planes[c].copy()).cuda() for c in range(3)]
+        d_out = [torch.zeros(h * w, dtype=torch.float32, device="cuda") for _ in range(3)]
+        st = ctx.pic_stats(in_pic, d_in)
+        ctx.matrix_convert(out_pic, d_out, in_pic, d_in, st)
+        torch.cuda.synchronize()
+        got = np.stack([t.cpu().numpy().reshape(h, w) for t in d_out])
+        rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-6)
+        assert float(rel.max()) <= 1e-5, (m, float(rel.max()))   # north_star tolerance for float output
+
+
+def test_host_pipeline_equals_device_path(ctx):
+    w, h, n = 496, 270, 11
+    dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+    frames = [synth.exr_half_frame(w, h, seed=s, channels=4) for s in range(n)]
+    dev = G.gpu_forward(ctx, frames, _HALF, dst)
+    params = api.forward_params(w, h, cabi.LAYOUT_HALF_RGBA, _HALF, dst, resampler=1, clip_on_load=0)
+    src = np.ascontiguousarray(np.stack(frames, 0))
+    out = np.zeros((n, api.yuv_frame_bytes(w, h, 1) // 2), np.uint16)
+    ctx.forward_host(params, src, out, n)
+    for i in range(n):
+        assert np.array_equal(out[i], dev[i]), i
+    pin_in = api.PinnedBuffer(src.nbytes)
+    pin_out = api.PinnedBuffer(out.nbytes)
+    pin_in.array[:] = src.view(np.uint8).reshape(-1)
+    ctx.forward_host(params, pin_in.ptr, pin_out.ptr, n)
+    assert np.array_equal(pin_out.view(np.uint16).reshape(n, -1), out)
+    pin_in.free()
+    pin_out.free()
+
+
+def test_error_convention(ctx):
+    w, h = 64, 16
+    d_src = torch.zeros(w * h * 8, dtype=torch.uint8, device="cuda")
+    d_dst = torch.zeros(w * h * 6, dtype=torch.uint8, device="cuda")
+    good_dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+    p = api.forward_params(w, h, cabi.LAYOUT_HALF_RGBA, _HALF, good_dst)
+    p.src.chroma_format_idc = cabi.CHROMA_420            # matrix_convert's 4:4:4 precondition (convert.cpp:886-890)
+    with pytest.raises(cabi.H2YError) as e:
+        ctx.forward(p, d_src, d_dst, 1)
+    assert e.value.status == cabi.ERR_PRECONDITION
+    p = api.forward_params(w, h, cabi.LAYOUT_HALF_RGBA, _HALF, dict(good_dst, matrix=5))
+    with pytest.raises(cabi.H2YError) as e:              # "Can't determine color difference to use?" (1195-1198)
+        ctx.forward(p, d_src, d_dst, 1)
+    assert e.value.status == cabi.ERR_MATRIX
+    p = api.forward_params(w, h, cabi.LAYOUT_RGB16, dict(_TIFF, bit_depth=10), dict(good_dst, bit_depth=12))
+    with pytest.raises(cabi.H2YError) as e:              # write_yuv: dst bitdepth > src bitdepth (tiff.cpp:396-401)
+        ctx.forward(p, d_src, d_dst, 1)
+    assert e.value.status == cabi.ERR_BIT_DEPTH
