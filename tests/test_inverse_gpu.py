@@ -92,7 +92,8 @@ def test_round_trip_is_close(ctx):
     rgb, _ = gpu_inverse(ctx, [yuv], w, h, 12, O.INV_YDZDX, 1, 0, 0)
     want = np.clip(f.astype(np.int64), 4096, 60160)
     err = np.abs(rgb[0].astype(np.int64)[8:-8, 8:-8] - want[8:-8, 8:-8])
-    assert np.median(err) <= 64, float(np.median(err))     # luma channel is exact to the 12-bit truncation
+    assert int(err[..., 1].max()) <= 15                    # Y' = G' passes through: exact to the 12-bit truncation
+    assert np.median(err[..., 0]) <= 1024 and np.median(err[..., 2]) <= 1024   # chroma lost only the per-pixel noise
 
 
 def test_inverse_host_pipeline(ctx):
