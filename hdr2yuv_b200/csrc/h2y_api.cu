@@ -188,7 +188,7 @@ h2y_status h2y_ctx_destroy(h2y_ctx *c)
     for (int i = 0; i < 8; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->pipeline_ready) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_d2h); }
     if (c->h_framek) cudaFreeHost(c->h_framek);
-    if (c->ev[0]) for (int i = 0; i < 3; i++) cudaEventDestroy(c->ev[i]);
+    if (c->ev[0][0]) for (int r = 0; r < PROFILE_RING; r++) for (int i = 0; i < 3; i++) cudaEventDestroy(c->ev[r][i]);
     delete c;
     return H2Y_OK;
 }
@@ -197,21 +197,29 @@ h2y_status h2y_profile_enable(h2y_ctx *c, int on)
 {
     if (!c) return H2Y_ERR_ARG;
     H2Y_CUDA(c, cudaSetDevice(c->device));
-    if (on && !c->ev[0]) for (int i = 0; i < 3; i++) H2Y_CUDA(c, cudaEventCreate(&c->ev[i]));
+    if (on && !c->ev[0][0])
+        for (int r = 0; r < PROFILE_RING; r++) for (int i = 0; i < 3; i++) H2Y_CUDA(c, cudaEventCreate(&c->ev[r][i]));
     c->profile_on = on != 0;
-    c->profile_valid = 0;
+    c->profile_count = 0;
     return H2Y_OK;
 }
 
+// average over the (up to PROFILE_RING) most recent bracketed calls
 h2y_status h2y_profile_last_ms(h2y_ctx *c, float *main_ms, float *prologue_ms)
 {
-    if (!c || !c->profile_valid) return H2Y_ERR_ARG;
-    H2Y_CUDA(c, cudaEventSynchronize(c->ev[2]));
-    float a = 0, b = 0;
-    H2Y_CUDA(c, cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
-    H2Y_CUDA(c, cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
-    if (prologue_ms) *prologue_ms = a;
-    if (main_ms) *main_ms = b;
+    if (!c || c->profile_count <= 0) return H2Y_ERR_ARG;
+    const int n = c->profile_count < PROFILE_RING ? c->profile_count : PROFILE_RING;
+    double a = 0, b = 0;
+    for (int i = 0; i < n; i++) {
+        const int r = (c->profile_count - 1 - i) % PROFILE_RING;
+        float x = 0, y = 0;
+        H2Y_CUDA(c, cudaEventSynchronize(c->ev[r][2]));
+        H2Y_CUDA(c, cudaEventElapsedTime(&x, c->ev[r][0], c->ev[r][1]));
+        H2Y_CUDA(c, cudaEventElapsedTime(&y, c->ev[r][1], c->ev[r][2]));
+        a += x; b += y;
+    }
+    if (prologue_ms) *prologue_ms = (float)(a / n);
+    if (main_ms) *main_ms = (float)(b / n);
     return H2Y_OK;
 }
 
@@ -497,15 +505,16 @@ h2y_status h2y_forward(h2y_ctx *c, const h2y_forward_params *p, const void *d_sr
         uint8_t *dst = (uint8_t *)d_dst + (size_t)f0 * dst_stride;
         FrameK *dfk = nullptr;
         float *dl = nullptr;
-        if (c->profile_on) cudaEventRecord(c->ev[0], st);
+        cudaEvent_t *pev = c->ev[c->profile_count % PROFILE_RING];
+        if (c->profile_on) cudaEventRecord(pev[0], st);
         if (k.convert_transfer) {
             if ((s = launch_stats_and_luts(c, *p, k, src, src_stride, nf, &dfk, &dl, st)) != H2Y_OK) return s;
             c->last_nframes = nf;
             c->last_stream = st;
         }
-        if (c->profile_on) cudaEventRecord(c->ev[1], st);
+        if (c->profile_on) cudaEventRecord(pev[1], st);
         if ((s = launch_forward_fused(c, *p, k, src, src_stride, dst, dst_stride, nf, dfk, dl, st)) != H2Y_OK) return s;
-        if (c->profile_on) { cudaEventRecord(c->ev[2], st); c->profile_valid = 1; }
+        if (c->profile_on) { cudaEventRecord(pev[2], st); c->profile_count++; }
     }
     return H2Y_OK;
 }
@@ -630,9 +639,10 @@ h2y_status h2y_inverse(h2y_ctx *c, const h2y_inverse_params *p, const void *d_yu
     H2Y_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (d_invalid) H2Y_CUDA(c, cudaMemsetAsync(d_invalid, 0, sizeof(uint32_t) * nframes, st));
-    if (c->profile_on) { cudaEventRecord(c->ev[0], st); cudaEventRecord(c->ev[1], st); }
+    cudaEvent_t *pev = c->ev[c->profile_count % PROFILE_RING];
+    if (c->profile_on) { cudaEventRecord(pev[0], st); cudaEventRecord(pev[1], st); }
     s = launch_inverse(c, k, d_yuv, yuv_stride, d_rgb, rgb_stride, nframes, d_invalid, st);
-    if (c->profile_on && s == H2Y_OK) { cudaEventRecord(c->ev[2], st); c->profile_valid = 1; }
+    if (c->profile_on && s == H2Y_OK) { cudaEventRecord(pev[2], st); c->profile_count++; }
     return s;
 }
 

@@ -35,10 +35,11 @@ struct h2y_ctx_impl {
     int last_nframes;
     cudaStream_t last_stream;
     // profiling hooks
-    int profile_on, profile_valid;
-    cudaEvent_t ev[3];
+    int profile_on, profile_count;      // bracketed calls since h2y_profile_enable (ring of PROFILE_RING)
+    cudaEvent_t ev[16][3];
 };
 
+constexpr int PROFILE_RING = 16;
 enum ScratchSlot { SCR_STATS = 0, SCR_FRAMEK = 1, SCR_LUT = 2, SCR_TMP444 = 3, SCR_UNPACK = 4, SCR_OUT = 5,
                    SCR_RING_IN = 6, SCR_RING_OUT = 7 };
 
