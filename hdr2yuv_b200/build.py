@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhdr2yuv_b200.so")
 OBJDIR = os.path.join(HERE, "build")
-SOURCES = ["h2y_api.cu", "h2y_stats.cu", "h2y_staged.cu", "h2y_forward.cu", "h2y_inverse.cu"]
+SOURCES = ["h2y_api.cu", "h2y_stats.cu", "h2y_staged.cu", "h2y_forward.cu", "h2y_forward2.cu", "h2y_inverse.cu"]
 HEADERS = [os.path.join(CSRC, "h2y_device.cuh"), os.path.join(CSRC, "h2y_internal.h"),
            os.path.join(ROOT, "include", "hdr2yuv_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -187,6 +187,58 @@ __device__ __forceinline__ void px_matrix_exact(float G, float B, float R, const
     Cro = (unsigned long long)cr > (unsigned long long)k.maxCV ? k.maxCV : (unsigned)cr;
 }
 
+constexpr int FRAC_BITS = 14;
+
+// ---- colour-difference stage, fast form ------------------------------------------------------------
+// The reference computes  k = (int)( d / c + 0.5 )  in double.  Here q = RZ(d * RN(1/c) + 0.5 + M)
+// with M = 1.5*2^38 leaves floor(q * 2^14) in the low mantissa word; |q - exact| < 2^-36, so when the
+// 14 fraction bits are neither all 0 nor all 1 the truncated integer is certain.  Otherwise (and
+// for NaN, whose low word is 0) the pixel is redone by px_matrix_exact.  Returns true when safe.
+__device__ __forceinline__ bool trunc_from_magic(double q, int &k)
+{
+    const int lo = __double2loint(q);
+    k = (lo >> FRAC_BITS) + (int)((unsigned)lo >> 31);
+    return ((unsigned)(lo + 1) & ((1u << FRAC_BITS) - 1u)) > 1u;
+}
+
+template <int MK>
+__device__ __forceinline__ bool px_matrix_fast(float G, float B, float R, const PixK &k, unsigned &Y, unsigned &Cb,
+                                               unsigned &Cr)
+{
+    const double MAGIC = 412316860416.0 + 0.5;   // 1.5 * 2^38 + the reference's +0.5
+    bool ok = true;
+    int cb, cr;
+    if (MK == MK_PASS) {
+        Y = min(__float2uint_rz(G), k.maxCV);
+        Cb = min(__float2uint_rz(B), k.maxCV);
+        Cr = min(__float2uint_rz(R), k.maxCV);
+        return G >= 0.0f && B >= 0.0f && R >= 0.0f;
+    } else if (MK == MK_YCBCR) {
+        const double s = __dadd_rn(__dadd_rn(__dmul_rn(k.wr, (double)R), __dmul_rn(k.wg, (double)G)),
+                                   __dmul_rn(k.wb, (double)B));
+        const float tmpF = __double2float_rn(__dadd_rn(s, 0.5));
+        Y = min(__float2uint_rz(tmpF), k.maxCV);
+        ok = tmpF >= 0.0f;
+        ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(B, tmpF), k.rdb, MAGIC), cb);
+        ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(R, tmpF), k.rdr, MAGIC), cr);
+    } else if (MK == MK_YDZDX) {
+        Y = min(__float2uint_rz(G), k.maxCV);
+        ok = G >= 0.0f;
+        const double hg = __dmul_rn((double)G, -0.5);
+        ok &= trunc_from_magic(__dadd_rz(__dadd_rn(hg, __dmul_rn((double)B, 0.5)), MAGIC), cb);
+        ok &= trunc_from_magic(__dadd_rz(__dadd_rn(hg, __dmul_rn((double)R, 0.5)), MAGIC), cr);
+    } else {   // MK_Y100
+        Y = min(__float2uint_rz(G), k.maxCV);
+        ok = G >= 0.0f;
+        ok &= trunc_from_magic(__dadd_rz((double)__fadd_rn(__fmul_rn(k.P, G), __fmul_rn(k.Q, B)), MAGIC), cb);
+        ok &= trunc_from_magic(__dadd_rz((double)__fadd_rn(__fmul_rn(k.RR, R), __fmul_rn(k.S, G)), MAGIC), cr);
+    }
+    // negatives compare as huge unsigned and clamp to maxCV, like the reference's unsigned long compare
+    Cb = min((unsigned)(cb + k.half_m1), k.maxCV);
+    Cr = min((unsigned)(cr + k.half_m1), k.maxCV);
+    return ok;
+}
+
 // ---- write_yuv's shift + range clamp (tiff.cpp:457-550) --------------------------------------
 __device__ __forceinline__ unsigned out_clamp(unsigned v, int shift, unsigned lo, unsigned hi)
 {

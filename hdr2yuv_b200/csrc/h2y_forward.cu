@@ -32,7 +32,6 @@ namespace {
 constexpr int THREADS = 512, WARPS = THREADS / 32;
 constexpr int RING_ROWS = 48, RING_W = 128;          // 120 used columns per plane, padded
 constexpr int LUT_SMEM_CODES = 0x7C01;               // non-negative halfs up to +inf
-constexpr int FRAC_BITS = 14;
 }   // namespace
 
 struct FwdArgs {
@@ -44,6 +43,7 @@ struct FwdArgs {
     int layout;
     int use_lut;             // transfer changes: per-frame LUT gather
     int exact_math;          // force the reference-order FP64 path for every pixel (debug / tests)
+    int skip_clean;          // frames flagged clean were converted by the v2 kernel (h2y_forward2.cu)
     int strip_w, nstrips, seg_rows, nsegs, nitems;
     PixK k;
     const FrameK *framek;
@@ -114,56 +114,6 @@ __device__ __forceinline__ float lut_fetch(const LutView &lv, const float *g, un
     return __ldg(g + code);
 }
 
-// ---- colour-difference stage, fast form ------------------------------------------------------------
-// The reference computes  k = (int)( d / c + 0.5 )  in double.  Here q = RZ(d * RN(1/c) + 0.5 + M)
-// with M = 1.5*2^38 leaves floor(q * 2^14) in the low mantissa word; |q - exact| < 2^-36, so when the
-// 14 fraction bits are neither all 0 nor all 1 the truncated integer is certain.  Otherwise (and
-// for NaN, whose low word is 0) the pixel is redone by px_matrix_exact.  Returns true when safe.
-__device__ __forceinline__ bool trunc_from_magic(double q, int &k)
-{
-    const int lo = __double2loint(q);
-    k = (lo >> FRAC_BITS) + (int)((unsigned)lo >> 31);
-    return ((unsigned)(lo + 1) & ((1u << FRAC_BITS) - 1u)) > 1u;
-}
-
-template <int MK>
-__device__ __forceinline__ bool px_matrix_fast(float G, float B, float R, const PixK &k, unsigned &Y, unsigned &Cb,
-                                               unsigned &Cr)
-{
-    const double MAGIC = 412316860416.0 + 0.5;   // 1.5 * 2^38 + the reference's +0.5
-    bool ok = true;
-    int cb, cr;
-    if (MK == MK_PASS) {
-        Y = min(__float2uint_rz(G), k.maxCV);
-        Cb = min(__float2uint_rz(B), k.maxCV);
-        Cr = min(__float2uint_rz(R), k.maxCV);
-        return G >= 0.0f && B >= 0.0f && R >= 0.0f;
-    } else if (MK == MK_YCBCR) {
-        const double s = __dadd_rn(__dadd_rn(__dmul_rn(k.wr, (double)R), __dmul_rn(k.wg, (double)G)),
-                                   __dmul_rn(k.wb, (double)B));
-        const float tmpF = __double2float_rn(__dadd_rn(s, 0.5));
-        Y = min(__float2uint_rz(tmpF), k.maxCV);
-        ok = tmpF >= 0.0f;
-        ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(B, tmpF), k.rdb, MAGIC), cb);
-        ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(R, tmpF), k.rdr, MAGIC), cr);
-    } else if (MK == MK_YDZDX) {
-        Y = min(__float2uint_rz(G), k.maxCV);
-        ok = G >= 0.0f;
-        const double hg = __dmul_rn((double)G, -0.5);
-        ok &= trunc_from_magic(__dadd_rz(__dadd_rn(hg, __dmul_rn((double)B, 0.5)), MAGIC), cb);
-        ok &= trunc_from_magic(__dadd_rz(__dadd_rn(hg, __dmul_rn((double)R, 0.5)), MAGIC), cr);
-    } else {   // MK_Y100
-        Y = min(__float2uint_rz(G), k.maxCV);
-        ok = G >= 0.0f;
-        ok &= trunc_from_magic(__dadd_rz((double)__fadd_rn(__fmul_rn(k.P, G), __fmul_rn(k.Q, B)), MAGIC), cb);
-        ok &= trunc_from_magic(__dadd_rz((double)__fadd_rn(__fmul_rn(k.RR, R), __fmul_rn(k.S, G)), MAGIC), cr);
-    }
-    // negatives compare as huge unsigned and clamp to maxCV, like the reference's unsigned long compare
-    Cb = min((unsigned)(cb + k.half_m1), k.maxCV);
-    Cr = min((unsigned)(cr + k.half_m1), k.maxCV);
-    return ok;
-}
-
 template <int MK>
 __device__ __forceinline__ void pixel8(const FwdArgs &a, const LutView &lv, const Px8 &p, unsigned Y[8],
                                        unsigned Cb[8], unsigned Cr[8], unsigned &fallbacks)
@@ -226,6 +176,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_fused(const FwdArgs a)
         const int strip = item % a.nstrips;
         const int seg = (item / a.nstrips) % a.nsegs;
         const int frame = item / (a.nstrips * a.nsegs);
+        if (a.skip_clean && a.framek[frame].clean) continue;          // uniform per CTA
         const uint8_t *fsrc = a.src + (size_t)frame * a.src_stride;
         uint16_t *fY = reinterpret_cast<uint16_t *>(a.dst + (size_t)frame * a.dst_stride);
         uint16_t *fCb = fY + (size_t)w * h;
@@ -480,9 +431,10 @@ static h2y_status launch_mk(h2y_ctx_impl *c, const FwdArgs &a, int cm, int grid,
 
 h2y_status launch_forward_fused(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, const void *d_src,
                                 size_t src_stride, void *d_dst, size_t dst_stride, int nframes,
-                                const FrameK *d_framek, const float *d_luts, cudaStream_t st)
+                                const FrameK *d_framek, const float *d_luts, cudaStream_t st, int skip_clean)
 {
     FwdArgs a;
+    a.skip_clean = skip_clean;
     a.src = (const uint8_t *)d_src; a.src_stride = src_stride;
     a.dst = (uint8_t *)d_dst; a.dst_stride = dst_stride;
     a.w = p.src.width; a.h = p.src.height; a.nframes = nframes;

@@ -18,6 +18,10 @@ struct FrameK {
     float offset[3], range[3];  // convert.cpp:936-940
     int lut_slot[3];            // index (frame*3+channel) of the LUT this channel reads
     int same_lut;               // 1 when the three channels share one LUT
+    // half-float sources: every sample finite and non-negative (sign bit clear), normalisation range > 0 and one
+    // shared LUT -- the precondition of the v2 kernel (h2y_forward2.cu); code_lo..code_hi = raw code range
+    int clean;
+    unsigned code_lo, code_hi;
 };
 
 struct h2y_ctx_impl {
@@ -86,9 +90,13 @@ h2y_status launch_upsample(h2y_ctx_impl *c, const uint16_t *d_src, uint16_t *d_d
 
 // ---- launchers (h2y_forward.cu / h2y_inverse.cu) ---------------------------------------------
 bool fused_forward_supported(const h2y_forward_params &p);
+bool forward_exr420_supported(const h2y_forward_params &p, const PixK &k, int tmp_bit_depth);
+h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, int tmp_bit_depth,
+                                 const void *d_src, size_t src_stride, void *d_dst, size_t dst_stride, int nframes,
+                                 const FrameK *d_framek, const float *d_luts, cudaStream_t st);
 h2y_status launch_forward_fused(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, const void *d_src,
                                 size_t src_stride, void *d_dst, size_t dst_stride, int nframes,
-                                const FrameK *d_framek, const float *d_luts, cudaStream_t st);
+                                const FrameK *d_framek, const float *d_luts, cudaStream_t st, int skip_clean = 0);
 
 struct InvK {
     int w, h, bit_depth, matrix, fir, full_range, alpha;

@@ -8,6 +8,8 @@
 // afford per pixel, so a tiny FP64 kernel evaluates the function once per code (65 536 codes)
 // and the fused forward kernel gathers from it.  Bit-exact by construction up to CUDA-vs-glibc
 // pow() last-ulp differences before the rounding to float.
+#include <cstdlib>
+
 #include "h2y_internal.h"
 
 namespace h2y {
@@ -23,7 +25,8 @@ __device__ __forceinline__ float fkey_inv(unsigned k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// stats slots: [frame][channel][2] = {min key, max key}
+// stats slots: [frame][8] = {min key, max key} x 3 channels, then min and max RAW 16-bit code
+constexpr int SLOTS = 8;
 __global__ void k_stats_init(unsigned *slots, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -71,9 +74,228 @@ k_stats_codes(const uint16_t *__restrict__ src, size_t frame_stride_elems, int l
             mx[c] = max(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
         }
         if ((threadIdx.x & 31) == 0) {
-            atomicMin(&slots[(blockIdx.y * 3 + c) * 2 + 0], mn[c]);
-            atomicMax(&slots[(blockIdx.y * 3 + c) * 2 + 1], mx[c]);
+            atomicMin(&slots[blockIdx.y * SLOTS + c * 2 + 0], mn[c]);
+            atomicMax(&slots[blockIdx.y * SLOTS + c * 2 + 1], mx[c]);
         }
+    }
+    // this scalar route does not track the raw code range: the frame is never "clean"
+    if (threadIdx.x == 0 && blockIdx.x == 0) { slots[blockIdx.y * SLOTS + 6] = 0u; slots[blockIdx.y * SLOTS + 7] = 0xffffu; }
+}
+
+// ---- vectorised statistics for the fused path -----------------------------------------------------
+// 16-byte loads, packed 16-bit min/max (HMNMX2 for half bit patterns, VIMNMX.U16x2 for integer codes):
+// 3 instructions per pixel, so the pass runs at HBM speed.  Interleaved 3-channel data repeats every
+// 48 bytes with three word kinds (R,G) (B,R) (G,B); 4-channel data has two, (R,G) and (B,A).
+template <bool HALF> struct Pk;
+template <> struct Pk<true> {
+    static __device__ __forceinline__ unsigned mn(unsigned a, unsigned b)
+    {
+        __half2 r = __hmin2(*reinterpret_cast<__half2 *>(&a), *reinterpret_cast<__half2 *>(&b));
+        return *reinterpret_cast<unsigned *>(&r);
+    }
+    static __device__ __forceinline__ unsigned mx(unsigned a, unsigned b)
+    {
+        __half2 r = __hmax2(*reinterpret_cast<__half2 *>(&a), *reinterpret_cast<__half2 *>(&b));
+        return *reinterpret_cast<unsigned *>(&r);
+    }
+    static constexpr unsigned MIN_INIT = 0x7C007C00u, MAX_INIT = 0xFC00FC00u;   // +inf, -inf
+    // NaN never wins a '<' / '>' in the reference loop (common.cpp:121-133); minNum/maxNum drop it too
+    static __device__ __forceinline__ bool key(unsigned h, unsigned &k)
+    {
+        if ((h & 0x7FFFu) > 0x7C00u) return false;
+        k = fkey(half_bits_to_float(h));
+        return true;
+    }
+};
+template <> struct Pk<false> {
+    static __device__ __forceinline__ unsigned mn(unsigned a, unsigned b)
+    {
+        unsigned r;
+        asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+        return r;
+    }
+    static __device__ __forceinline__ unsigned mx(unsigned a, unsigned b)
+    {
+        unsigned r;
+        asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+        return r;
+    }
+    static constexpr unsigned MIN_INIT = 0xFFFFFFFFu, MAX_INIT = 0u;
+    static __device__ __forceinline__ bool key(unsigned c, unsigned &k) { k = c; return true; }
+};
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
+{
+    uint4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// grid = (blocks, nframes); npix % 8 == 0, frames 16-byte aligned.  NCH = 3 or 4 interleaved, 0 = planar.
+template <bool HALF, int NCH>
+__global__ void __launch_bounds__(256, 4)
+k_stats_vec(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int clip_on, unsigned lo, unsigned hi,
+            unsigned *slots)
+{
+    typedef Pk<HALF> P;
+    const uint8_t *f = src + (size_t)blockIdx.y * frame_stride;
+    unsigned mnv[3], mxv[3];        // per word kind (interleaved) or per plane (planar), two lanes each
+    unsigned umn = 0xFFFFFFFFu, umx = 0u;   // half input: extrema of the RAW codes of the colour channels (packed)
+#pragma unroll
+    for (int i = 0; i < 3; i++) { mnv[i] = P::MIN_INIT; mxv[i] = P::MAX_INIT; }
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long)gridDim.x * blockDim.x;
+    if (NCH == 3) {
+        // Warp-contiguous 16-byte loads (whole sectors per instruction).  Vector n holds words of kind
+        // (n + w) mod 3 at position w, kinds 0 = (R,G), 1 = (B,R), 2 = (G,B); the grid stride is a multiple of
+        // 3 vectors, so a thread's phase n mod 3 never changes and it can accumulate per word POSITION.
+        const long nvec = npix * 6 / 16;
+        unsigned pmn[4], pmx[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { pmn[i] = P::MIN_INIT; pmx[i] = P::MAX_INIT; }
+        const uint4 *p = reinterpret_cast<const uint4 *>(f);
+        long n = tid;
+        for (; n + 3 * nthr < nvec; n += 4 * nthr) {
+            uint4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = ldg_stream(p + n + j * nthr);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                // stepping by nthr (a multiple of 3) keeps the phase
+                pmn[0] = P::mn(pmn[0], v[j].x); pmx[0] = P::mx(pmx[0], v[j].x);
+                pmn[1] = P::mn(pmn[1], v[j].y); pmx[1] = P::mx(pmx[1], v[j].y);
+                pmn[2] = P::mn(pmn[2], v[j].z); pmx[2] = P::mx(pmx[2], v[j].z);
+                pmn[3] = P::mn(pmn[3], v[j].w); pmx[3] = P::mx(pmx[3], v[j].w);
+                if (HALF) {
+                    typedef Pk<false> U;
+                    umx = U::mx(umx, U::mx(U::mx(v[j].x, v[j].y), U::mx(v[j].z, v[j].w)));
+                    umn = U::mn(umn, U::mn(U::mn(v[j].x, v[j].y), U::mn(v[j].z, v[j].w)));
+                }
+            }
+        }
+        for (; n < nvec; n += nthr) {
+            const uint4 v = ldg_stream(p + n);
+            pmn[0] = P::mn(pmn[0], v.x); pmx[0] = P::mx(pmx[0], v.x);
+            pmn[1] = P::mn(pmn[1], v.y); pmx[1] = P::mx(pmx[1], v.y);
+            pmn[2] = P::mn(pmn[2], v.z); pmx[2] = P::mx(pmx[2], v.z);
+            pmn[3] = P::mn(pmn[3], v.w); pmx[3] = P::mx(pmx[3], v.w);
+            if (HALF) {
+                typedef Pk<false> U;
+                umx = U::mx(umx, U::mx(U::mx(v.x, v.y), U::mx(v.z, v.w)));
+                umn = U::mn(umn, U::mn(U::mn(v.x, v.y), U::mn(v.z, v.w)));
+            }
+        }
+        const int ph = (int)(tid % 3);                        // kind of word w is (ph + w) % 3
+#pragma unroll
+        for (int wd = 0; wd < 4; wd++) {
+            const int kind = (ph + wd) % 3;
+#pragma unroll
+            for (int kk = 0; kk < 3; kk++)
+                if (kind == kk) { mnv[kk] = P::mn(mnv[kk], pmn[wd]); mxv[kk] = P::mx(mxv[kk], pmx[wd]); }
+        }
+    } else if (NCH == 4) {
+        const long nvec = npix / 2;                           // 2 pixels per uint4: (R,G)(B,A)(R,G)(B,A)
+        for (long g = tid; g < nvec; g += nthr) {
+            const uint4 a = ldg_stream(reinterpret_cast<const uint4 *>(f) + g);
+            mnv[0] = P::mn(mnv[0], P::mn(a.x, a.z));
+            mxv[0] = P::mx(mxv[0], P::mx(a.x, a.z));
+            mnv[1] = P::mn(mnv[1], P::mn(a.y, a.w));
+            mxv[1] = P::mx(mxv[1], P::mx(a.y, a.w));
+            if (HALF) {                     // alpha (high half of .y/.w) is not a colour sample: mask it to the B code
+                typedef Pk<false> U;
+                const unsigned by = __byte_perm(a.y, 0, 0x1010), bw = __byte_perm(a.w, 0, 0x1010);
+                umx = U::mx(U::mx(umx, U::mx(a.x, a.z)), U::mx(by, bw));
+                umn = U::mn(U::mn(umn, U::mn(a.x, a.z)), U::mn(by, bw));
+            }
+        }
+    } else {
+        const long nvec = npix / 8;
+#pragma unroll
+        for (int pl = 0; pl < 3; pl++) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(f + (size_t)pl * npix * 2);
+            for (long g = tid; g < nvec; g += nthr) {
+                const uint4 a = ldg_stream(p + g);
+                mnv[pl] = P::mn(P::mn(mnv[pl], a.x), P::mn(a.y, P::mn(a.z, a.w)));
+                mxv[pl] = P::mx(P::mx(mxv[pl], a.x), P::mx(a.y, P::mx(a.z, a.w)));
+            }
+        }
+    }
+    // warp reduce, then one warp reduces the CTA's 8 warps through shared memory: 8 atomics per CTA
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        for (int o = 16; o > 0; o >>= 1) {
+            mnv[i] = P::mn(mnv[i], __shfl_xor_sync(0xffffffffu, mnv[i], o));
+            mxv[i] = P::mx(mxv[i], __shfl_xor_sync(0xffffffffu, mxv[i], o));
+        }
+    if (HALF) {
+        typedef Pk<false> U;
+        for (int o = 16; o > 0; o >>= 1) {
+            umn = U::mn(umn, __shfl_xor_sync(0xffffffffu, umn, o));
+            umx = U::mx(umx, __shfl_xor_sync(0xffffffffu, umx, o));
+        }
+    }
+    __shared__ unsigned red[8][8];
+    if ((threadIdx.x & 31) == 0) {
+        unsigned *r = red[threadIdx.x >> 5];
+        r[0] = mnv[0]; r[1] = mnv[1]; r[2] = mnv[2]; r[3] = mxv[0]; r[4] = mxv[1]; r[5] = mxv[2]; r[6] = umn; r[7] = umx;
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    {
+        typedef Pk<false> U;
+        const int wsrc = threadIdx.x & 7;
+        unsigned a0 = red[wsrc][0], a1 = red[wsrc][1], a2 = red[wsrc][2], b0 = red[wsrc][3], b1 = red[wsrc][4], b2 = red[wsrc][5],
+                 c0 = red[wsrc][6], c1 = red[wsrc][7];
+        for (int o = 4; o > 0; o >>= 1) {
+            a0 = P::mn(a0, __shfl_xor_sync(0xffffffffu, a0, o)); a1 = P::mn(a1, __shfl_xor_sync(0xffffffffu, a1, o));
+            a2 = P::mn(a2, __shfl_xor_sync(0xffffffffu, a2, o)); b0 = P::mx(b0, __shfl_xor_sync(0xffffffffu, b0, o));
+            b1 = P::mx(b1, __shfl_xor_sync(0xffffffffu, b1, o)); b2 = P::mx(b2, __shfl_xor_sync(0xffffffffu, b2, o));
+            c0 = U::mn(c0, __shfl_xor_sync(0xffffffffu, c0, o)); c1 = U::mx(c1, __shfl_xor_sync(0xffffffffu, c1, o));
+        }
+        mnv[0] = a0; mnv[1] = a1; mnv[2] = a2; mxv[0] = b0; mxv[1] = b1; mxv[2] = b2; umn = c0; umx = c1;
+    }
+    if (HALF) {
+        if (threadIdx.x == 0) {
+            atomicMin(&slots[blockIdx.y * SLOTS + 6], min(umn & 0xffffu, umn >> 16));
+            atomicMax(&slots[blockIdx.y * SLOTS + 7], max(umx & 0xffffu, umx >> 16));
+        }
+    } else if (threadIdx.x == 0 && blockIdx.x == 0) {
+        slots[blockIdx.y * SLOTS + 6] = 0u; slots[blockIdx.y * SLOTS + 7] = 0xffffu;     // integer codes: not the v2 route
+    }
+    if (threadIdx.x == 0) {
+        // (word kind, half) pairs that hold each of G, B, R (slot order 0/1/2 = G/B/R)
+        unsigned cmn[3][2], cmx[3][2];
+#define LO16(x) ((x) & 0xffffu)
+#define HI16(x) ((x) >> 16)
+        if (NCH == 3) {
+            cmn[0][0] = HI16(mnv[0]); cmn[0][1] = LO16(mnv[2]);   cmx[0][0] = HI16(mxv[0]); cmx[0][1] = LO16(mxv[2]);   // G
+            cmn[1][0] = LO16(mnv[1]); cmn[1][1] = HI16(mnv[2]);   cmx[1][0] = LO16(mxv[1]); cmx[1][1] = HI16(mxv[2]);   // B
+            cmn[2][0] = LO16(mnv[0]); cmn[2][1] = HI16(mnv[1]);   cmx[2][0] = LO16(mxv[0]); cmx[2][1] = HI16(mxv[1]);   // R
+        } else if (NCH == 4) {
+            cmn[0][0] = cmn[0][1] = HI16(mnv[0]);  cmx[0][0] = cmx[0][1] = HI16(mxv[0]);
+            cmn[1][0] = cmn[1][1] = LO16(mnv[1]);  cmx[1][0] = cmx[1][1] = LO16(mxv[1]);
+            cmn[2][0] = cmn[2][1] = LO16(mnv[0]);  cmx[2][0] = cmx[2][1] = LO16(mxv[0]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                cmn[c][0] = LO16(mnv[c]); cmn[c][1] = HI16(mnv[c]);
+                cmx[c][0] = LO16(mxv[c]); cmx[c][1] = HI16(mxv[c]);
+            }
+        }
+#undef LO16
+#undef HI16
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                unsigned a = cmn[c][j], b = cmx[c][j], k;
+                if (!HALF && clip_on) {     // the clip is monotone: clip(min) = min(clip)
+                    a = a < lo ? lo : (a > hi ? hi : a);
+                    b = b < lo ? lo : (b > hi ? hi : b);
+                }
+                if (P::key(a, k)) atomicMin(&slots[blockIdx.y * SLOTS + c * 2 + 0], k);
+                if (P::key(b, k)) atomicMax(&slots[blockIdx.y * SLOTS + c * 2 + 1], k);
+            }
     }
 }
 
@@ -134,7 +356,7 @@ __global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_fl
     for (int p = threadIdx.x; p < n; p += blockDim.x) {
         FrameK &f = fk[p / 3];
         const int c = p % 3;
-        unsigned kmin = slots[p * 2], kmax = slots[p * 2 + 1];
+        unsigned kmin = slots[(p / 3) * SLOTS + c * 2], kmax = slots[(p / 3) * SLOTS + c * 2 + 1];
         int fl, ce;
         if (is_float) {
             // seeds FLT_MAX / FLT_MIN(smallest positive) of common.cpp:118-119, then (int) truncation 135-136
@@ -172,8 +394,16 @@ __global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_fl
         f.lut_slot[c] = slot;
     }
     __syncthreads();
-    for (int fi = threadIdx.x; fi < nframes; fi += blockDim.x)
-        fk[fi].same_lut = fk[fi].lut_slot[0] == fk[fi].lut_slot[1] && fk[fi].lut_slot[0] == fk[fi].lut_slot[2];
+    for (int fi = threadIdx.x; fi < nframes; fi += blockDim.x) {
+        FrameK &f = fk[fi];
+        f.same_lut = f.lut_slot[0] == f.lut_slot[1] && f.lut_slot[0] == f.lut_slot[2];
+        // "clean": half source whose raw codes are all below +inf's (finite, sign bit clear, so code order is
+        // value order), every normalisation range positive, one LUT for the three channels
+        const unsigned ulo = slots[fi * SLOTS + 6], uhi = slots[fi * SLOTS + 7];
+        f.code_lo = ulo; f.code_hi = uhi;
+        f.clean = is_float && f.same_lut && ulo <= uhi && uhi < 0x7C00u && f.range[0] > 0.0f && f.range[1] > 0.0f &&
+                  f.range[2] > 0.0f;
+    }
 }
 
 // grid = (256, nframes*3): LUT p is built only by its owner (lut_slot == p).
@@ -203,16 +433,34 @@ h2y_status launch_stats_and_luts(h2y_ctx_impl *c, const h2y_forward_params &p, c
 {
     void *slots, *fk, *luts;
     h2y_status s;
-    if ((s = scratch_reserve(c, SCR_STATS, (size_t)nframes * 6 * sizeof(unsigned), &slots)) != H2Y_OK) return s;
+    if ((s = scratch_reserve(c, SCR_STATS, (size_t)nframes * SLOTS * sizeof(unsigned), &slots)) != H2Y_OK) return s;
     if ((s = scratch_reserve(c, SCR_FRAMEK, (size_t)nframes * sizeof(FrameK), &fk)) != H2Y_OK) return s;
     if ((s = scratch_reserve(c, SCR_LUT, (size_t)nframes * 3 * 65536 * sizeof(float), &luts)) != H2Y_OK) return s;
     const long npix = (long)p.src.width * p.src.height;
-    const int nslots = nframes * 6;
+    const int nslots = nframes * SLOTS;
     k_stats_init<<<(nslots + 255) / 256, 256, 0, st>>>((unsigned *)slots, nslots);
     const int blocks = (int)(((npix + 2047) / 2048) < 4L * c->sm_count ? ((npix + 2047) / 2048) : 4L * c->sm_count);
     dim3 grid(blocks, nframes);
     const bool half = layout_is_half(p.src.layout);
-    if (half)
+    const int nch = layout_is_planar(p.src.layout) ? 0 : layout_channels(p.src.layout);
+    const bool vec = (npix % 8) == 0 && (((uintptr_t)d_src | src_stride) & 15) == 0;
+    const uint8_t *sb = (const uint8_t *)d_src;
+    unsigned *sl = (unsigned *)slots;
+    if (vec) {
+        // 2 CTAs of 256 threads per SM per frame row keeps ~16 KB in flight per SM
+        // grid.x * 256 threads must be a multiple of 3 (see k_stats_vec, 3-channel case)
+        const char *egx = getenv("H2Y_STATS_GX");
+        const int gx = (egx ? atoi(egx) : (nframes >= 8 ? 2 * c->sm_count : 6 * c->sm_count)) / 3 * 3;
+        dim3 vgrid(gx, nframes);
+        if (half) {
+            if (nch == 3) k_stats_vec<true, 3><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, 0, 0, 0, sl);
+            else k_stats_vec<true, 4><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, 0, 0, 0, sl);
+        } else {
+            if (nch == 3) k_stats_vec<false, 3><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl);
+            else if (nch == 4) k_stats_vec<false, 4><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl);
+            else k_stats_vec<false, 0><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl);
+        }
+    } else if (half)
         k_stats_codes<true><<<grid, 256, 0, st>>>((const uint16_t *)d_src, src_stride / 2, p.src.layout, npix, 0, 0, 0,
                                                   (unsigned *)slots);
     else
@@ -233,12 +481,12 @@ h2y_status launch_stats_planar(h2y_ctx_impl *c, const h2y_pic_desc &pic, const v
 {
     void *slots, *fk;
     h2y_status s;
-    if ((s = scratch_reserve(c, SCR_STATS, 6 * sizeof(unsigned), &slots)) != H2Y_OK) return s;
+    if ((s = scratch_reserve(c, SCR_STATS, SLOTS * sizeof(unsigned), &slots)) != H2Y_OK) return s;
     if ((s = scratch_reserve(c, SCR_FRAMEK, sizeof(FrameK), &fk)) != H2Y_OK) return s;
     int pw[3], ph[3];
     h2y_plane_dims(pic.width, pic.height, pic.chroma_format_idc, pw, ph);
     const long n0 = (long)pw[0] * ph[0], n12 = (long)pw[1] * ph[1];
-    k_stats_init<<<1, 256, 0, st>>>((unsigned *)slots, 6);
+    k_stats_init<<<1, 256, 0, st>>>((unsigned *)slots, SLOTS);
     const int blocks = (int)(((n0 + 2047) / 2048) < 4L * c->sm_count ? ((n0 + 2047) / 2048) : 4L * c->sm_count);
     const bool isf = pic.pic_buffer_type == H2Y_PIC_TYPE_F32;
     if (isf)
