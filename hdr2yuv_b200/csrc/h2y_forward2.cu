@@ -45,12 +45,15 @@ typedef unsigned long long u64;
 
 __device__ __forceinline__ u64 pk(float lo, float hi)
 {
-    return ((u64)__float_as_uint(hi) << 32) | (u64)__float_as_uint(lo);
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
 }
-__device__ __forceinline__ float plo(u64 v) { return __uint_as_float((unsigned)v); }
-__device__ __forceinline__ float phi(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
-__device__ __forceinline__ int ilo(u64 v) { return (int)(unsigned)v; }
-__device__ __forceinline__ int ihi(u64 v) { return (int)(unsigned)(v >> 32); }
+__device__ __forceinline__ void unpk(u64 v, int &lo, int &hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ float plo(u64 v) { int a, b; unpk(v, a, b); return __int_as_float(a); }
+__device__ __forceinline__ float phi(u64 v) { int a, b; unpk(v, a, b); return __int_as_float(b); }
+__device__ __forceinline__ int ilo(u64 v) { int a, b; unpk(v, a, b); return a; }
+__device__ __forceinline__ int ihi(u64 v) { int a, b; unpk(v, a, b); return b; }
 __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c)
 {
     u64 r;
@@ -179,31 +182,44 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, const float *lut, con
         const u64 cbl = ffma2(fadd2(B2, nbase), rdb2, cbc2), crl = ffma2(fadd2(R2, nbase), rdr2, crc2);
         const u64 cb1 = fadd2_rm(cbl, magic2), cb2 = fadd2_rm(fadd2(cbl, twoG2), magic2);
         const u64 cr1 = fadd2_rm(crl, magic2), cr2 = fadd2_rm(fadd2(crl, twoG2), magic2);
+        int Y1[2], Y2[2], B1[2], Bq[2], R1[2], Rq[2], xb[2], xr[2];
+        unpk(y1, Y1[0], Y1[1]); unpk(y2, Y2[0], Y2[1]);
+        unpk(cb1, B1[0], B1[1]); unpk(cb2, Bq[0], Bq[1]);
+        unpk(cr1, R1[0], R1[1]); unpk(cr2, Rq[0], Rq[1]);
+        unpk(cbl, xb[0], xb[1]); unpk(crl, xr[0], xr[1]);
+        int ybits[2];
+        unsigned cbi[2], cri[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const int Y1 = e ? ihi(y1) : ilo(y1), Y2 = e ? ihi(y2) : ilo(y2);
-            const int B1 = e ? ihi(cb1) : ilo(cb1), Bq = e ? ihi(cb2) : ilo(cb2);
-            const int R1 = e ? ihi(cr1) : ilo(cr1), Rq = e ? ihi(cr2) : ilo(cr2);
-            const unsigned xb = (unsigned)(e ? ihi(cbl) : ilo(cbl)), xr = (unsigned)(e ? ihi(crl) : ilo(crl));
-            int ybits = Y1;
+            ybits[e] = Y1[e];
             // trunc toward zero = floor + 1 for negative non-integers (integers are never "safe")
-            unsigned cbi = (unsigned)(B1 + cbias + (int)(xb >> 31));
-            unsigned cri = (unsigned)(R1 + cbias + (int)(xr >> 31));
-            if (((Y1 ^ Y2) | (B1 ^ Bq) | (R1 ^ Rq)) != 0) {
-                // within the guard band of an integer: take the reference-exact route for this pixel
-                const float Gs = e ? phi(G2) : plo(G2), Bs = e ? phi(B2) : plo(B2), Rs = e ? phi(R2) : plo(R2);
-                unsigned Ye, Cbe, Cre;
-                pixel_exact<MK>(Gs, Bs, Rs, k, Ye, Cbe, Cre);
-                ybits = (int)Ye + MAGIC_BITS;
-                cbi = Cbe; cri = Cre;
-                fallbacks++;
-            }
+            cbi[e] = (unsigned)(B1[e] + cbias + (int)((unsigned)xb[e] >> 31));
+            cri[e] = (unsigned)(R1[e] + cbias + (int)((unsigned)xr[e] >> 31));
+        }
+        const int f0 = (Y1[0] ^ Y2[0]) | (B1[0] ^ Bq[0]) | (R1[0] ^ Rq[0]), f1 = (Y1[1] ^ Y2[1]) | (B1[1] ^ Bq[1]) | (R1[1] ^ Rq[1]);
+        if ((f0 | f1) != 0) {
+            // within the guard band of an integer: take the reference-exact route for that pixel (one branch per pair)
+            float Gs[2], Bs[2], Rs[2];
+            int t0, t1;
+            unpk(G2, t0, t1); Gs[0] = __int_as_float(t0); Gs[1] = __int_as_float(t1);
+            unpk(B2, t0, t1); Bs[0] = __int_as_float(t0); Bs[1] = __int_as_float(t1);
+            unpk(R2, t0, t1); Rs[0] = __int_as_float(t0); Rs[1] = __int_as_float(t1);
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+                if ((e ? f1 : f0) != 0) {
+                    unsigned Ye, Cbe, Cre;
+                    pixel_exact<MK>(Gs[e], Bs[e], Rs[e], k, Ye, Cbe, Cre);
+                    ybits[e] = (int)Ye + MAGIC_BITS;
+                    cbi[e] = Cbe; cri[e] = Cre;
+                    fallbacks++;
+                }
+        }
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
             // write_yuv: >> shift, range clamp; the low 16 bits of the result are the code
-            yv[q + e] = (unsigned)clamp3(ybits >> shift, ylo, yhi);
+            yv[q + e] = (unsigned)clamp3(ybits[e] >> shift, ylo, yhi);
             // matrix_convert's clamp through unsigned long: negatives land on maxCV (convert.cpp:1210-1213)
-            cbi = min(cbi, k.maxCV);
-            cri = min(cri, k.maxCV);
-            chroma[q + e] = pk((float)(int)cbi, (float)(int)cri);
+            chroma[q + e] = pk((float)(int)min(cbi[e], k.maxCV), (float)(int)min(cri[e], k.maxCV));
         }
     }
     ypack = make_uint4(__byte_perm(yv[0], yv[1], 0x5410), __byte_perm(yv[2], yv[3], 0x5410),
@@ -383,6 +399,159 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
     if (a.fallback_count && fallbacks) atomicAdd(a.fallback_count, (unsigned long long)fallbacks);
 }
 
+// =================================================================================================
+// v3: warp-autonomous variant for large batches.  A warp owns a column strip and a long run of rows and
+// keeps the vertical filter in REGISTERS: the 12-tap filter at even rows is evaluated as six running
+// {Cb,Cr} accumulators per chroma column (an output row starts every second input row and lives for
+// twelve).  Each new horizontally filtered row is folded into the six accumulators with FFMA2s whose
+// destination is the neighbouring accumulator on odd rows, so the rotation costs no moves.  There is no
+// shared-memory ring, no CTA barrier inside a frame and no vertical-filter phase; shared memory holds
+// only the LUT.  Rows are split statically: worker k gets rows [k*R/K, (k+1)*R/K) of the batch's R rows,
+// so every warp does the same amount of work and the 11 halo rows are paid once per ~900 rows.
+struct Fwd3Args {
+    Fwd2Args b;
+    int sub;                 // row workers per CTA (16 / strips when a picture has fewer than 16 strips)
+    int wps;                 // warps per row worker = strips handled side by side
+    long total_rows;         // nframes * h
+};
+
+template <int MK, int NCH>
+__global__ void __launch_bounds__(THREADS, 1) k_forward_exr420_rows(const Fwd3Args A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *lut_s = reinterpret_cast<float *>(smem_raw);
+    const Fwd2Args &a = A.b;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PixK &k = a.k;
+    const int w = a.w, h = a.h, wh = w >> 1;
+    const int hi_bits = MAGIC_BITS + (int)k.maxCV;
+    const int shift = k.down_shift;
+    const int clo = (int)k.loC + (MAGIC_BITS >> shift), chi = (int)k.hiC + (MAGIC_BITS >> shift);
+    unsigned fallbacks = 0;
+
+    // this warp's worker and strip set
+    const int wk = warp / A.wps;                         // worker within the CTA
+    const int sfirst = warp - wk * A.wps;                // first strip; further strips every wps
+    const long K = (long)gridDim.x * A.sub;
+    const long kid = (long)blockIdx.x * A.sub + (wk < A.sub ? wk : 0);
+    const bool active = wk < A.sub;
+    // row ranges (even boundaries); the CTA's union range decides which frames it walks
+    const long g0 = ((kid * A.total_rows) / K) & ~1L, g1 = kid + 1 == K ? A.total_rows : (((kid + 1) * A.total_rows) / K) & ~1L;
+    const long c0 = ((((long)blockIdx.x * A.sub) * A.total_rows) / K) & ~1L;
+    const long c1 = (long)(blockIdx.x + 1) * A.sub == K ? A.total_rows : (((((long)blockIdx.x + 1) * A.sub) * A.total_rows) / K) & ~1L;
+    if (c1 <= c0) return;
+    const int f_first = (int)(c0 / h), f_last = (int)((c1 - 1) / h);
+    int cur_slot = -1;
+    unsigned cur_lo = 1, cur_hi = 0;
+
+    const u64 kv[12] = {pk(5.0f / 512.0f, 5.0f / 512.0f), pk(11.0f / 512.0f, 11.0f / 512.0f),
+                        pk(-21.0f / 512.0f, -21.0f / 512.0f), pk(-37.0f / 512.0f, -37.0f / 512.0f),
+                        pk(70.0f / 512.0f, 70.0f / 512.0f), pk(228.0f / 512.0f, 228.0f / 512.0f),
+                        pk(228.0f / 512.0f, 228.0f / 512.0f), pk(70.0f / 512.0f, 70.0f / 512.0f),
+                        pk(-37.0f / 512.0f, -37.0f / 512.0f), pk(-21.0f / 512.0f, -21.0f / 512.0f),
+                        pk(11.0f / 512.0f, 11.0f / 512.0f), pk(5.0f / 512.0f, 5.0f / 512.0f)};
+
+    for (int frame = f_first; frame <= f_last; frame++) {
+        const FrameK &fk = a.framek[frame];
+        if (!fk.clean) continue;                         // uniform per CTA: v1 converts this frame
+        // ---- LUT for this frame (CTA-wide) ----
+        {
+            const unsigned lo = fk.code_lo, hi = fk.code_hi;
+            if (fk.lut_slot[0] != cur_slot || lo < cur_lo || hi > cur_hi) {
+                __syncthreads();                         // every warp is done with the previous LUT
+                const float *gl = a.luts + (size_t)fk.lut_slot[0] * 65536;
+                for (unsigned c = lo + threadIdx.x; c <= hi; c += THREADS) lut_s[c] = __ldg(gl + c);
+                cur_slot = fk.lut_slot[0]; cur_lo = lo; cur_hi = hi;
+                __syncthreads();
+            }
+        }
+        if (!active) continue;
+        const long fbase = (long)frame * h;
+        const int ys = (int)(max(g0, fbase) - fbase), ye = (int)(min(g1, fbase + h) - fbase);
+        if (ys >= ye) continue;
+        const uint8_t *fsrc = a.src + (size_t)frame * a.src_stride;
+        uint16_t *fY = reinterpret_cast<uint16_t *>(a.dst + (size_t)frame * a.dst_stride);
+        uint16_t *fCb = fY + (size_t)w * h;
+        uint16_t *fCr = fCb + (size_t)wh * (h >> 1);
+
+        for (int strip = sfirst; strip < a.nstrips; strip += A.wps) {
+            const int x0 = strip * a.strip_w;
+            const int xl = x0 + 8 * (lane - 1);
+            const bool lane_in_pic = xl >= 0 && xl < w;
+            const bool lane_interior = lane >= 1 && lane < 31 && xl < min(x0 + a.strip_w, w);
+            const int xload = lane_in_pic ? xl : (xl < 0 ? 0 : w - 8);          // halo lanes outside the picture read a valid
+                                                                                 // address; their values are replaced below
+            u64 acc[6][4];
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[i][c] = 0ull;
+
+            const int rfirst = ys - 6, rlast = ye + 4;                          // rows feeding outputs ys/2 .. ye/2-1
+            RawPx<NCH> raw;
+            load_px8<NCH>(raw, fsrc, w, min(max(rfirst, 0), h - 1), xload);
+            for (int r = rfirst; r <= rlast; r++) {
+                // ---- 8 pixels of (replicated) row r ----
+                unsigned g[8], b[8], rr[8];
+                split_codes<NCH>(raw, g, b, rr);
+                if (r < rlast) load_px8<NCH>(raw, fsrc, w, min(max(r + 1, 0), h - 1), xload);    // prefetch
+                uint4 ypack;
+                u64 ch[8];
+                pixels8<MK>(a, lut_s, g, b, rr, ypack, ch, fallbacks);
+                if (lane_interior && r >= ys && r < ye) *reinterpret_cast<uint4 *>(fY + (size_t)r * w + xl) = ypack;
+                // ---- horizontal 7-tap: neighbours through shuffles ----
+                float l3x = __shfl_up_sync(0xffffffffu, plo(ch[3]), 1), l3y = __shfl_up_sync(0xffffffffu, phi(ch[3]), 1);
+                float l5x = __shfl_up_sync(0xffffffffu, plo(ch[5]), 1), l5y = __shfl_up_sync(0xffffffffu, phi(ch[5]), 1);
+                float l7x = __shfl_up_sync(0xffffffffu, plo(ch[7]), 1), l7y = __shfl_up_sync(0xffffffffu, phi(ch[7]), 1);
+                float n1x = __shfl_down_sync(0xffffffffu, plo(ch[1]), 1), n1y = __shfl_down_sync(0xffffffffu, phi(ch[1]), 1);
+                float n3x = __shfl_down_sync(0xffffffffu, plo(ch[3]), 1), n3y = __shfl_down_sync(0xffffffffu, phi(ch[3]), 1);
+                u64 l3 = pk(l3x, l3y), l5 = pk(l5x, l5y), l7 = pk(l7x, l7y), n1 = pk(n1x, n1y), n3 = pk(n3x, n3y);
+                if (xl == 0) l3 = l5 = l7 = ch[0];                  // replicate s[0]     (convert.cpp:295-300)
+                if (xl + 8 >= w) n1 = n3 = ch[7];                   // replicate s[W-1]
+                u64 o[4];
+                o[0] = fir_h7_pair(l3, l5, l7, ch[0], ch[1], ch[3], ch[5], hi_bits);
+                o[1] = fir_h7_pair(l5, l7, ch[1], ch[2], ch[3], ch[5], ch[7], hi_bits);
+                o[2] = fir_h7_pair(l7, ch[1], ch[3], ch[4], ch[5], ch[7], n1, hi_bits);
+                o[3] = fir_h7_pair(ch[1], ch[3], ch[5], ch[6], ch[7], n1, n3, hi_bits);
+                // ---- vertical 12-tap, running (convert.cpp:333-377): output row j takes rows 2j-5 .. 2j+6 ----
+                if ((r & 1) == 0) {
+                    // even row r = 2m: acc[i] is output j = m-3+i and receives tap 11-2i; acc[0] completes
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+#pragma unroll
+                        for (int i = 0; i < 6; i++) acc[i][c] = ffma2(kv[11 - 2 * i], o[c], acc[i][c]);
+                    }
+                    const int j = (r >> 1) - 3;
+                    if (lane_interior && j >= (ys >> 1) && j < (ye >> 1)) {
+                        unsigned cbv[4], crv[4];
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            // clamp [0,maxCV] + truncation + write_yuv's shift and range clamp: one integer clamp of the floor
+                            int lo_, hi_;
+                            unpk(fadd2_rm(acc[0][c], pk(MAGIC, MAGIC)), lo_, hi_);
+                            cbv[c] = (unsigned)clamp3(lo_ >> shift, clo, chi);
+                            crv[c] = (unsigned)clamp3(hi_ >> shift, clo, chi);
+                        }
+                        const size_t off = (size_t)j * wh + (xl >> 1);
+                        *reinterpret_cast<uint2 *>(fCb + off) = make_uint2(__byte_perm(cbv[0], cbv[1], 0x5410), __byte_perm(cbv[2], cbv[3], 0x5410));
+                        *reinterpret_cast<uint2 *>(fCr + off) = make_uint2(__byte_perm(crv[0], crv[1], 0x5410), __byte_perm(crv[2], crv[3], 0x5410));
+                    }
+                } else {
+                    // odd row r = 2m+1: the accumulators shift down by one output (the FFMA2 writes the neighbour),
+                    // old acc[i+1] receives tap 10-2i; a new output starts in acc[5] with tap 0
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+#pragma unroll
+                        for (int i = 0; i < 5; i++) acc[i][c] = ffma2(kv[10 - 2 * i], o[c], acc[i + 1][c]);
+                        acc[5][c] = ffma2(kv[0], o[c], pk(0.5f, 0.5f));
+                    }
+                }
+            }
+        }
+    }
+    if (a.fallback_count && fallbacks) atomicAdd(a.fallback_count, (unsigned long long)fallbacks);
+}
+
 // ---- host side -----------------------------------------------------------------------------------------
 
 bool forward_exr420_supported(const h2y_forward_params &p, const PixK &k, int tmp_bit_depth)
@@ -437,9 +606,36 @@ h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, c
     a.seg_rows = seg_rows;
     a.nsegs = (a.h + seg_rows - 1) / seg_rows;
     a.nitems = nframes * a.nsegs * a.nstrips;
+    const int nch = layout_channels(p.src.layout);
+    // large batches: the warp-autonomous kernel (rows split evenly over all warps of the GPU)
+    {
+        Fwd3Args A3;
+        A3.b = a;
+        A3.wps = a.nstrips < WARPS ? a.nstrips : WARPS;
+        A3.sub = WARPS / A3.wps;
+        A3.total_rows = (long)nframes * a.h;
+        const long rows_per_worker = A3.total_rows / ((long)grid_max * A3.sub);
+        const char *force = getenv("H2Y_FORWARD_KERNEL");             // "ring" / "rows": tests and experiments
+        const bool want_rows = force ? force[0] == 'r' && force[1] == 'o' : rows_per_worker >= 128;
+        if (want_rows && A3.total_rows >= 2) {
+            const size_t smem3 = (size_t)LUT_MAX_CODES * sizeof(float);
+            int g3 = grid_max;
+            while (g3 > 1 && A3.total_rows / ((long)g3 * A3.sub) < 16) g3 >>= 1;   // forced on a tiny batch
+#define L3(MKV, NC)                                                                                                        \
+    do {                                                                                                                   \
+        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MKV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
+        k_forward_exr420_rows<MKV, NC><<<g3, THREADS, smem3, st>>>(A3);                                                  \
+    } while (0)
+            if (k.mat_kind == MK_YCBCR) { if (nch == 3) L3(MK_YCBCR, 3); else L3(MK_YCBCR, 4); }
+            else { if (nch == 3) L3(MK_YDZDX, 3); else L3(MK_YDZDX, 4); }
+#undef L3
+            c->launches++;
+            H2Y_CUDA(c, cudaGetLastError());
+            return H2Y_OK;
+        }
+    }
     const size_t smem = (size_t)RING_ROWS * RING_PITCH * sizeof(float) + (size_t)LUT_MAX_CODES * sizeof(float);
     const int grid = a.nitems < grid_max ? a.nitems : grid_max;
-    const int nch = layout_channels(p.src.layout);
     if (k.mat_kind == MK_YCBCR)
         return nch == 3 ? launch_v2<MK_YCBCR, 3>(c, a, grid, smem, st) : launch_v2<MK_YCBCR, 4>(c, a, grid, smem, st);
     return nch == 3 ? launch_v2<MK_YDZDX, 3>(c, a, grid, smem, st) : launch_v2<MK_YDZDX, 4>(c, a, grid, smem, st);
