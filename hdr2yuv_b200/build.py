@@ -62,5 +62,34 @@ def build(verbose=False, force=False):
     return LIB
 
 
+CLI_DIR = os.path.join(HERE, "cli")
+CLI_BIN = os.path.join(CLI_DIR, "bin")
+CXX = os.environ.get("CXX", "g++")
+
+
+def build_cli(force=False):
+    """The C++ command-line hosts (hdr2yuv, yuv2tiff) and the reader test tool, linked against the in-tree
+    libhdr2yuv_b200.so (rpath $ORIGIN/../.. so they run from the tree on the GPU box)."""
+    build()
+    os.makedirs(CLI_BIN, exist_ok=True)
+    io_src = [os.path.join(CLI_DIR, "h2y_io.cpp"), os.path.join(CLI_DIR, "h2y_io.h")]
+    common = [CXX, "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + CLI_DIR]
+    gpu_link = ["-L" + HERE, "-lhdr2yuv_b200", "-Wl,-rpath,$ORIGIN/../..", "-lz", "-lpthread"]
+    targets = {"hdr2yuv": (["hdr2yuv_main.cpp"], gpu_link), "yuv2tiff": (["yuv2tiff_main.cpp"], gpu_link),
+               "h2y_iotool": (["h2y_iotool.cpp"], ["-lz"])}
+    out = {}
+    for name, (srcs, link) in targets.items():
+        exe = os.path.join(CLI_BIN, name)
+        deps = [os.path.join(CLI_DIR, s) for s in srcs] + io_src + [os.path.join(ROOT, "include", "hdr2yuv_b200.h"), LIB]
+        if force or _stale(exe, deps):
+            cmd = common + [os.path.join(CLI_DIR, s) for s in srcs] + [io_src[0], "-o", exe] + link
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+            if r.returncode != 0:
+                raise RuntimeError("build of %s failed:\n%s" % (name, r.stdout.decode(errors="replace")))
+        out[name] = exe
+    return out
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    print(build_cli(force="-f" in sys.argv))

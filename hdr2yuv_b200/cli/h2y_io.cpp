@@ -1,0 +1,533 @@
+// h2y_io.cpp -- see h2y_io.h.  Host-side file decoding only; no pixel arithmetic of the hot path lives here.
+#include "h2y_io.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+namespace h2yio {
+
+namespace {
+
+struct File {
+    FILE *f = nullptr;
+    explicit File(const std::string &p, const char *mode) { f = fopen(p.c_str(), mode); }
+    ~File() { if (f) fclose(f); }
+    bool read_at(void *dst, size_t n, uint64_t off)
+    {
+        if (fseeko(f, (off_t)off, SEEK_SET) != 0) return false;
+        return fread(dst, 1, n, f) == n;
+    }
+};
+
+bool fail(std::string *err, const std::string &msg)
+{
+    if (err) *err = msg;
+    return false;
+}
+
+inline uint16_t bswap16(uint16_t v) { return (uint16_t)((v >> 8) | (v << 8)); }
+inline uint32_t bswap32(uint32_t v) { return __builtin_bswap32(v); }
+
+// ---- TIFF --------------------------------------------------------------------------------------------
+struct TiffDir {
+    bool big_endian = false;
+    uint32_t width = 0, height = 0, bits = 0, compression = 1, photometric = 2, spp = 1, rows_per_strip = 0xffffffffu,
+             planar = 1;
+    std::vector<uint32_t> offsets, counts;
+};
+
+struct TiffReader {
+    File file;
+    TiffDir d;
+    explicit TiffReader(const std::string &p) : file(p, "rb") {}
+    uint16_t u16(const uint8_t *p) const { uint16_t v; memcpy(&v, p, 2); return d.big_endian ? bswap16(v) : v; }
+    uint32_t u32(const uint8_t *p) const { uint32_t v; memcpy(&v, p, 4); return d.big_endian ? bswap32(v) : v; }
+
+    bool values(uint16_t type, uint32_t count, const uint8_t *field, std::vector<uint32_t> *out)
+    {
+        const size_t esz = type == 3 ? 2 : (type == 4 ? 4 : (type == 1 ? 1 : 0));
+        if (!esz) return false;
+        std::vector<uint8_t> buf(esz * count);
+        if (esz * count <= 4) memcpy(buf.data(), field, esz * count);
+        else if (!file.read_at(buf.data(), buf.size(), u32(field))) return false;
+        out->resize(count);
+        for (uint32_t i = 0; i < count; i++)
+            (*out)[i] = type == 3 ? u16(&buf[2 * i]) : (type == 4 ? u32(&buf[4 * i]) : buf[i]);
+        return true;
+    }
+
+    bool parse(std::string *err)
+    {
+        if (!file.f) return fail(err, "unable to open file");
+        uint8_t hdr[8];
+        if (!file.read_at(hdr, 8, 0)) return fail(err, "short TIFF header");
+        if (hdr[0] == 'I' && hdr[1] == 'I') d.big_endian = false;
+        else if (hdr[0] == 'M' && hdr[1] == 'M') d.big_endian = true;
+        else return fail(err, "not a TIFF file");
+        if (u16(hdr + 2) != 42) return fail(err, "not a classic TIFF (BigTIFF is not supported)");
+        const uint32_t ifd = u32(hdr + 4);
+        uint8_t nb[2];
+        if (!file.read_at(nb, 2, ifd)) return fail(err, "bad IFD offset");
+        const int n = u16(nb);
+        std::vector<uint8_t> ent((size_t)n * 12);
+        if (!file.read_at(ent.data(), ent.size(), ifd + 2)) return fail(err, "short IFD");
+        for (int i = 0; i < n; i++) {
+            const uint8_t *e = &ent[(size_t)i * 12];
+            const uint16_t tag = u16(e), type = u16(e + 2);
+            const uint32_t count = u32(e + 4);
+            std::vector<uint32_t> v;
+            if (tag != 273 && tag != 279 && count > 8) continue;
+            if (!values(type, count, e + 8, &v) || v.empty()) continue;
+            switch (tag) {
+            case 256: d.width = v[0]; break;
+            case 257: d.height = v[0]; break;
+            case 258: d.bits = v[0]; break;
+            case 259: d.compression = v[0]; break;
+            case 262: d.photometric = v[0]; break;
+            case 273: d.offsets = v; break;
+            case 277: d.spp = v[0]; break;
+            case 278: d.rows_per_strip = v[0]; break;
+            case 279: d.counts = v; break;
+            case 284: d.planar = v[0]; break;
+            default: break;
+            }
+        }
+        if (!d.width || !d.height) return fail(err, "TIFF without dimensions");
+        if (d.compression != 1) return fail(err, "compressed TIFF is not supported (baseline raw strips only)");
+        if (d.bits != 16) return fail(err, "TIFF BitsPerSample must be 16");
+        if (d.spp != 3 && d.spp != 4) return fail(err, "TIFF SamplesPerPixel must be 3 or 4");
+        if (d.planar != 1) return fail(err, "planar TIFF is not supported");
+        if (d.offsets.empty()) return fail(err, "TIFF without strips");
+        if (d.rows_per_strip > d.height) d.rows_per_strip = d.height;
+        return true;
+    }
+};
+
+// ---- EXR ---------------------------------------------------------------------------------------------
+struct ExrChannel { std::string name; int type = 1; int xs = 1, ys = 1; };
+struct ExrHeader {
+    std::vector<ExrChannel> ch;      // file order (alphabetical)
+    int compression = 0;
+    int xmin = 0, ymin = 0, xmax = -1, ymax = -1;
+    int line_order = 0;
+    uint64_t table_offset = 0;
+    int width() const { return xmax - xmin + 1; }
+    int height() const { return ymax - ymin + 1; }
+    int lines_per_block() const { return compression == 3 ? 16 : 1; }
+};
+
+bool exr_parse(File &f, ExrHeader *h, std::string *err)
+{
+    if (!f.f) return fail(err, "unable to open file");
+    fseeko(f.f, 0, SEEK_END);
+    const uint64_t size = (uint64_t)ftello(f.f);
+    const size_t hmax = (size_t)std::min<uint64_t>(size, 1u << 20);
+    std::vector<uint8_t> b(hmax);
+    if (!f.read_at(b.data(), hmax, 0) || hmax < 8) return fail(err, "short EXR file");
+    uint32_t magic, ver;
+    memcpy(&magic, &b[0], 4);
+    memcpy(&ver, &b[4], 4);
+    if (magic != 20000630u) return fail(err, "not an OpenEXR file");
+    if (ver & 0x200) return fail(err, "tiled EXR is not supported");
+    if (ver & 0x1800) return fail(err, "deep / multi-part EXR is not supported");
+    size_t p = 8;
+    auto cstr = [&](std::string *s) {
+        size_t e = p;
+        while (e < hmax && b[e]) e++;
+        if (e >= hmax) return false;
+        s->assign((const char *)&b[p], e - p);
+        p = e + 1;
+        return true;
+    };
+    for (;;) {
+        std::string name, type;
+        if (p >= hmax) return fail(err, "EXR header too large");
+        if (b[p] == 0) { p++; break; }
+        if (!cstr(&name) || !cstr(&type) || p + 4 > hmax) return fail(err, "bad EXR attribute");
+        int32_t asz;
+        memcpy(&asz, &b[p], 4);
+        p += 4;
+        if (asz < 0 || p + (size_t)asz > hmax) return fail(err, "bad EXR attribute size");
+        const uint8_t *v = &b[p];
+        if (name == "channels") {
+            size_t q = 0;
+            while (q < (size_t)asz && v[q]) {
+                ExrChannel c;
+                while (q < (size_t)asz && v[q]) c.name.push_back((char)v[q++]);
+                q++;
+                if (q + 16 > (size_t)asz) return fail(err, "bad EXR channel list");
+                int32_t t, xs, ys;
+                memcpy(&t, v + q, 4); memcpy(&xs, v + q + 8, 4); memcpy(&ys, v + q + 12, 4);
+                c.type = t; c.xs = xs; c.ys = ys;
+                q += 16;
+                h->ch.push_back(c);
+            }
+        } else if (name == "compression" && asz >= 1) h->compression = v[0];
+        else if (name == "dataWindow" && asz >= 16) {
+            int32_t w[4];
+            memcpy(w, v, 16);
+            h->xmin = w[0]; h->ymin = w[1]; h->xmax = w[2]; h->ymax = w[3];
+        } else if (name == "lineOrder" && asz >= 1) h->line_order = v[0];
+        p += (size_t)asz;
+    }
+    h->table_offset = p;
+    if (h->width() < 1 || h->height() < 1) return fail(err, "EXR without a data window");
+    if (h->compression != 0 && h->compression != 2 && h->compression != 3)
+        return fail(err, "EXR compression must be NONE, ZIPS or ZIP");
+    for (const auto &c : h->ch) {
+        if (c.xs != 1 || c.ys != 1) return fail(err, "subsampled EXR channels are not supported");
+        if (c.type != 1 && c.type != 2) return fail(err, "EXR channels must be HALF or FLOAT");
+    }
+    return true;
+}
+
+// ZIP post-processing of OpenEXR: undo the byte-delta predictor, then re-interleave the two byte halves
+void exr_unfilter(std::vector<uint8_t> &raw, std::vector<uint8_t> &out)
+{
+    const size_t n = raw.size();
+    for (size_t i = 1; i < n; i++) raw[i] = (uint8_t)(raw[i - 1] + raw[i] - 128);
+    out.resize(n);
+    const size_t half = (n + 1) / 2;
+    for (size_t i = 0, a = 0, b2 = half; i < n;) {
+        out[i++] = raw[a++];
+        if (i < n) out[i++] = raw[b2++];
+    }
+}
+
+void exr_filter(const std::vector<uint8_t> &in, std::vector<uint8_t> &out)
+{
+    const size_t n = in.size();
+    out.resize(n);
+    const size_t half = (n + 1) / 2;
+    for (size_t i = 0, a = 0, b2 = half; i < n;) {
+        out[a++] = in[i++];
+        if (i < n) out[b2++] = in[i++];
+    }
+    uint8_t prev = out.empty() ? 0 : out[0];
+    for (size_t i = 1; i < n; i++) {
+        const uint8_t cur = out[i];
+        out[i] = (uint8_t)(cur - prev + 128);
+        prev = cur;
+    }
+}
+
+}   // namespace
+
+uint16_t float_to_half(float f)
+{
+    // round to nearest even, as Imath's half(float)
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    const int32_t exp = (int32_t)((x >> 23) & 0xff) - 127 + 15;
+    uint32_t man = x & 0x7fffffu;
+    if (((x >> 23) & 0xff) == 0xff) return (uint16_t)(sign | 0x7c00u | (man ? 0x200u | (man >> 13) : 0));
+    if (exp >= 31) return (uint16_t)(sign | 0x7c00u);
+    if (exp <= 0) {
+        if (exp < -10) return (uint16_t)sign;
+        man |= 0x800000u;
+        const int shift = 14 - exp;
+        uint32_t h = man >> shift;
+        const uint32_t rem = man & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+        if (rem > halfway || (rem == halfway && (h & 1))) h++;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((uint32_t)exp << 10) | (man >> 13);
+    const uint32_t rem = man & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) h++;
+    return (uint16_t)(sign | h);
+}
+
+// ---- TIFF API ----------------------------------------------------------------------------------------
+bool tiff_probe(const std::string &path, ImageInfo *info, std::string *err)
+{
+    TiffReader r(path);
+    if (!r.parse(err)) return false;
+    info->width = (int)r.d.width; info->height = (int)r.d.height; info->channels = (int)r.d.spp; info->bits = 16;
+    info->is_half = false;
+    return true;
+}
+
+bool tiff_read(const std::string &path, uint16_t *dst, int crop_w, int crop_h, ImageInfo *info, std::string *err)
+{
+    TiffReader r(path);
+    if (!r.parse(err)) return false;
+    const TiffDir &d = r.d;
+    const int w = (int)d.width, h = (int)d.height, ch = (int)d.spp;
+    const int ow = crop_w > 0 && crop_w < w ? crop_w : w, oh = crop_h > 0 && crop_h < h ? crop_h : h;
+    const int x0 = (w - ow) / 2, y0 = (h - oh) / 2;                     // centred cut-out (tiff.cpp:191-220)
+    const size_t row_bytes = (size_t)w * ch * 2;
+    std::vector<uint8_t> strip;
+    const uint32_t rps = d.rows_per_strip;
+    for (size_t s = 0; s < d.offsets.size(); s++) {
+        const int first_row = (int)(s * rps), nrows = std::min<int>((int)rps, h - first_row);
+        if (nrows <= 0) break;
+        if (first_row + nrows <= y0 || first_row >= y0 + oh) continue;
+        strip.resize(row_bytes * nrows);
+        if (!r.file.read_at(strip.data(), strip.size(), d.offsets[s])) return fail(err, "short TIFF strip");
+        for (int rr = 0; rr < nrows; rr++) {
+            const int y = first_row + rr - y0;
+            if (y < 0 || y >= oh) continue;
+            const uint16_t *src = reinterpret_cast<const uint16_t *>(&strip[row_bytes * rr]) + (size_t)x0 * ch;
+            uint16_t *o = dst + (size_t)y * ow * ch;
+            if (d.big_endian) for (int i = 0; i < ow * ch; i++) o[i] = bswap16(src[i]);
+            else memcpy(o, src, (size_t)ow * ch * 2);
+        }
+    }
+    info->width = ow; info->height = oh; info->channels = ch; info->bits = 16; info->is_half = false;
+    return true;
+}
+
+bool tiff_write_rgb16(const std::string &path, const uint16_t *src, int width, int height, int channels, std::string *err)
+{
+    File f(path, "wb");
+    if (!f.f) return fail(err, "unable to create " + path);
+    const uint32_t row_bytes = (uint32_t)width * channels * 2;
+    const uint32_t data_off = 8;
+    const uint32_t ntags = 10;
+    // layout: header | pixel rows | bits array | strip offsets | strip counts | IFD
+    const uint32_t bits_off = data_off + row_bytes * (uint32_t)height;
+    const uint32_t offs_off = bits_off + 2 * (uint32_t)channels + (channels & 1 ? 2 : 0);
+    const uint32_t cnts_off = offs_off + 4 * (uint32_t)height;
+    const uint32_t ifd_off = cnts_off + 4 * (uint32_t)height;
+    uint8_t hdr[8] = {'I', 'I', 42, 0, 0, 0, 0, 0};
+    memcpy(hdr + 4, &ifd_off, 4);
+    fwrite(hdr, 1, 8, f.f);
+    fwrite(src, 1, (size_t)row_bytes * height, f.f);
+    std::vector<uint16_t> bits(channels + (channels & 1), 16);
+    fwrite(bits.data(), 2, bits.size(), f.f);
+    std::vector<uint32_t> offs(height), cnts(height, row_bytes);
+    for (int y = 0; y < height; y++) offs[y] = data_off + row_bytes * (uint32_t)y;
+    fwrite(offs.data(), 4, height, f.f);
+    fwrite(cnts.data(), 4, height, f.f);
+    struct Ent { uint16_t tag, type; uint32_t count, value; };
+    const Ent ents[ntags] = {
+        {256, 4, 1, (uint32_t)width}, {257, 4, 1, (uint32_t)height}, {258, 3, (uint32_t)channels, bits_off},
+        {259, 3, 1, 1}, {262, 3, 1, 2}, {273, 4, (uint32_t)height, offs_off}, {277, 3, 1, (uint32_t)channels},
+        {278, 4, 1, 1}, {279, 4, (uint32_t)height, cnts_off}, {284, 3, 1, 1}};
+    uint16_t n = ntags;
+    fwrite(&n, 2, 1, f.f);
+    for (const Ent &e : ents) {
+        uint8_t b[12];
+        memcpy(b, &e.tag, 2); memcpy(b + 2, &e.type, 2); memcpy(b + 4, &e.count, 4);
+        uint32_t v = e.value;
+        if (e.type == 3 && e.count == 1) v &= 0xffffu;
+        memcpy(b + 8, &v, 4);
+        fwrite(b, 1, 12, f.f);
+    }
+    uint32_t next = 0;
+    fwrite(&next, 4, 1, f.f);
+    return ferror(f.f) ? fail(err, "write error on " + path) : true;
+}
+
+// ---- EXR API -----------------------------------------------------------------------------------------
+bool exr_probe(const std::string &path, ImageInfo *info, std::string *err)
+{
+    File f(path, "rb");
+    ExrHeader h;
+    if (!exr_parse(f, &h, err)) return false;
+    bool has_a = false;
+    for (const auto &c : h.ch) has_a |= c.name == "A";
+    info->width = h.width(); info->height = h.height(); info->channels = has_a ? 4 : 3; info->bits = 16; info->is_half = true;
+    return true;
+}
+
+bool exr_read_half(const std::string &path, uint16_t *dst, int out_channels, ImageInfo *info, std::string *err)
+{
+    File f(path, "rb");
+    ExrHeader h;
+    if (!exr_parse(f, &h, err)) return false;
+    const int w = h.width(), ht = h.height();
+    // where each file channel goes in the interleaved output (r,g,b,a = 0,1,2,3); others are skipped
+    std::vector<int> dest(h.ch.size(), -1);
+    bool have[4] = {false, false, false, false};
+    size_t line_bytes = 0;
+    for (size_t i = 0; i < h.ch.size(); i++) {
+        const std::string &n = h.ch[i].name;
+        const int k = n == "R" ? 0 : (n == "G" ? 1 : (n == "B" ? 2 : (n == "A" ? 3 : -1)));
+        if (k >= 0 && k < out_channels) { dest[i] = k; have[k] = true; }
+        line_bytes += (size_t)w * (h.ch[i].type == 1 ? 2 : 4);
+    }
+    if (!have[0] || !have[1] || !have[2]) return fail(err, "EXR file needs R, G and B channels");
+    if (out_channels == 4 && !have[3])
+        for (size_t i = 0; i < (size_t)w * ht; i++) dst[i * 4 + 3] = 0x3C00;     // RgbaInputFile fills A with 1
+    const int lpb = h.lines_per_block();
+    const int nblocks = (ht + lpb - 1) / lpb;
+    std::vector<uint64_t> table(nblocks);
+    if (!f.read_at(table.data(), (size_t)nblocks * 8, h.table_offset)) return fail(err, "short EXR offset table");
+    std::vector<uint8_t> packed, raw, lines;
+    for (int b = 0; b < nblocks; b++) {
+        int32_t hdr2[2];
+        if (!f.read_at(hdr2, 8, table[b])) return fail(err, "bad EXR chunk offset");
+        const int y0 = hdr2[0] - h.ymin, psize = hdr2[1];
+        const int nl = std::min(lpb, ht - y0);
+        if (y0 < 0 || nl <= 0 || psize < 0) return fail(err, "bad EXR chunk");
+        const size_t want = line_bytes * nl;
+        packed.resize((size_t)psize);
+        if (!f.read_at(packed.data(), packed.size(), table[b] + 8)) return fail(err, "short EXR chunk");
+        const uint8_t *data;
+        if (h.compression == 0 || (size_t)psize == want) data = packed.data();      // stored raw when not smaller
+        else {
+            raw.resize(want);
+            uLongf got = (uLongf)want;
+            if (uncompress(raw.data(), &got, packed.data(), (uLong)psize) != Z_OK || got != want)
+                return fail(err, "EXR zlib stream is corrupt");
+            exr_unfilter(raw, lines);
+            data = lines.data();
+        }
+        for (int l = 0; l < nl; l++) {
+            const uint8_t *p = data + line_bytes * l;
+            uint16_t *o = dst + (size_t)(y0 + l) * w * out_channels;
+            for (size_t c = 0; c < h.ch.size(); c++) {
+                const bool is_half = h.ch[c].type == 1;
+                if (dest[c] >= 0) {
+                    uint16_t *oc = o + dest[c];
+                    if (is_half) {
+                        const uint16_t *s = reinterpret_cast<const uint16_t *>(p);
+                        for (int x = 0; x < w; x++) oc[(size_t)x * out_channels] = s[x];
+                    } else {
+                        for (int x = 0; x < w; x++) {
+                            float v;
+                            memcpy(&v, p + 4 * (size_t)x, 4);
+                            oc[(size_t)x * out_channels] = float_to_half(v);
+                        }
+                    }
+                }
+                p += (size_t)w * (is_half ? 2 : 4);
+            }
+        }
+    }
+    info->width = w; info->height = ht; info->channels = out_channels; info->bits = 16; info->is_half = true;
+    return true;
+}
+
+bool exr_write_half(const std::string &path, const uint16_t *src, int width, int height, int channels, int compression,
+                    std::string *err)
+{
+    if (compression != 0 && compression != 2 && compression != 3) return fail(err, "compression must be 0, 2 or 3");
+    File f(path, "wb");
+    if (!f.f) return fail(err, "unable to create " + path);
+    std::vector<uint8_t> hb;
+    auto put = [&](const void *p, size_t n) { hb.insert(hb.end(), (const uint8_t *)p, (const uint8_t *)p + n); };
+    auto puts0 = [&](const char *s) { put(s, strlen(s) + 1); };
+    auto attr = [&](const char *name, const char *type, const void *v, int32_t n) { puts0(name); puts0(type); put(&n, 4); put(v, (size_t)n); };
+    const uint32_t magic = 20000630u, ver = 2;
+    put(&magic, 4); put(&ver, 4);
+    const char *names = channels == 4 ? "ABGR" : "BGR";        // alphabetical, as the format requires
+    std::vector<uint8_t> cl;
+    for (const char *c = names; *c; c++) {
+        cl.push_back((uint8_t)*c); cl.push_back(0);
+        const int32_t t = 1, z = 0, one = 1;
+        cl.insert(cl.end(), (const uint8_t *)&t, (const uint8_t *)&t + 4);
+        cl.insert(cl.end(), (const uint8_t *)&z, (const uint8_t *)&z + 4);
+        cl.insert(cl.end(), (const uint8_t *)&one, (const uint8_t *)&one + 4);
+        cl.insert(cl.end(), (const uint8_t *)&one, (const uint8_t *)&one + 4);
+    }
+    cl.push_back(0);
+    attr("channels", "chlist", cl.data(), (int32_t)cl.size());
+    const uint8_t comp = (uint8_t)compression, lo = 0;
+    attr("compression", "compression", &comp, 1);
+    const int32_t win[4] = {0, 0, width - 1, height - 1};
+    attr("dataWindow", "box2i", win, 16);
+    attr("displayWindow", "box2i", win, 16);
+    attr("lineOrder", "lineOrder", &lo, 1);
+    const float par = 1.0f, swc[2] = {0.0f, 0.0f}, sww = 1.0f;
+    attr("pixelAspectRatio", "float", &par, 4);
+    attr("screenWindowCenter", "v2f", swc, 8);
+    attr("screenWindowWidth", "float", &sww, 4);
+    hb.push_back(0);
+    const int lpb = compression == 3 ? 16 : 1, nblocks = (height + lpb - 1) / lpb;
+    const size_t line_bytes = (size_t)width * channels * 2;
+    std::vector<uint64_t> table(nblocks);
+    std::vector<std::vector<uint8_t>> chunks(nblocks);
+    uint64_t off = hb.size() + (uint64_t)nblocks * 8;
+    const int order3[3] = {2, 1, 0}, order4[4] = {3, 2, 1, 0};           // file channel -> r,g,b,a index
+    for (int b = 0; b < nblocks; b++) {
+        const int y0 = b * lpb, nl = std::min(lpb, height - y0);
+        std::vector<uint8_t> plain(line_bytes * nl);
+        for (int l = 0; l < nl; l++)
+            for (int c = 0; c < channels; c++) {
+                const int k = channels == 4 ? order4[c] : order3[c];
+                uint16_t *o = reinterpret_cast<uint16_t *>(&plain[line_bytes * l + (size_t)c * width * 2]);
+                const uint16_t *s = src + (size_t)(y0 + l) * width * channels + k;
+                for (int x = 0; x < width; x++) o[x] = s[(size_t)x * channels];
+            }
+        std::vector<uint8_t> &ck = chunks[b];
+        std::vector<uint8_t> body;
+        if (compression == 0) body = plain;
+        else {
+            std::vector<uint8_t> filt;
+            exr_filter(plain, filt);
+            uLongf cap = compressBound((uLong)filt.size());
+            body.resize(cap);
+            if (compress2(body.data(), &cap, filt.data(), (uLong)filt.size(), 6) != Z_OK) return fail(err, "zlib compress failed");
+            body.resize(cap);
+            if (body.size() >= plain.size()) body = plain;
+        }
+        const int32_t y = y0, sz = (int32_t)body.size();
+        ck.resize(8 + body.size());
+        memcpy(&ck[0], &y, 4); memcpy(&ck[4], &sz, 4); memcpy(&ck[8], body.data(), body.size());
+        table[b] = off;
+        off += ck.size();
+    }
+    fwrite(hb.data(), 1, hb.size(), f.f);
+    fwrite(table.data(), 8, nblocks, f.f);
+    for (auto &ck : chunks) fwrite(ck.data(), 1, ck.size(), f.f);
+    return ferror(f.f) ? fail(err, "write error on " + path) : true;
+}
+
+// ---- raw ---------------------------------------------------------------------------------------------
+uint64_t file_size(const std::string &path)
+{
+    File f(path, "rb");
+    if (!f.f) return 0;
+    fseeko(f.f, 0, SEEK_END);
+    return (uint64_t)ftello(f.f);
+}
+
+bool file_read_at(const std::string &path, void *dst, size_t bytes, uint64_t offset, std::string *err)
+{
+    File f(path, "rb");
+    if (!f.f) return fail(err, "unable to open file " + path);
+    if (!f.read_at(dst, bytes, offset)) return fail(err, "short read from " + path);
+    return true;
+}
+
+bool rgb_planar_read(const std::string &path, uint16_t *dst, int width, int height, long frame, std::string *err)
+{
+    const size_t n = (size_t)width * height;
+    std::vector<uint16_t> planes(n * 3);
+    if (!file_read_at(path, planes.data(), n * 6, (uint64_t)frame * n * 6, err)) return false;
+    const uint16_t *r = planes.data(), *g = r + n, *b = g + n;          // file order R,G,B (hdr2yuv.cpp:633-638)
+    for (size_t i = 0; i < n; i++) { dst[3 * i] = r[i]; dst[3 * i + 1] = g[i]; dst[3 * i + 2] = b[i]; }
+    return true;
+}
+
+std::string sequence_name(const std::string &first, int index)
+{
+    if (first.find('%') != std::string::npos) {
+        char buf[4096];
+        snprintf(buf, sizeof(buf), first.c_str(), index);
+        return buf;
+    }
+    if (index == 0) return first;
+    const size_t slash = first.find_last_of('/');
+    const size_t base = slash == std::string::npos ? 0 : slash + 1;
+    size_t dot = first.find_last_of('.');
+    if (dot == std::string::npos || dot < base) dot = first.size();
+    size_t e = dot;
+    while (e > base && !(first[e - 1] >= '0' && first[e - 1] <= '9')) e--;
+    size_t s = e;
+    while (s > base && first[s - 1] >= '0' && first[s - 1] <= '9') s--;
+    if (s == e) return first;                                       // no digits: a single file
+    const std::string digits = first.substr(s, e - s);
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%0*lld", (int)digits.size(), atoll(digits.c_str()) + index);
+    return first.substr(0, s) + buf + first.substr(e);
+}
+
+}   // namespace h2yio

@@ -1,0 +1,154 @@
+"""CPU tests of the C++ command-line hosts' host side: the native TIFF / EXR / raw readers and writers
+(checked against OpenCV's libtiff / OpenEXR codecs where available), frame-sequence naming and the
+reference's option handling.  No GPU: hdr2yuv --dump_input stops before any CUDA call."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from hdr2yuv_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def cli():
+    from hdr2yuv_b200 import build
+    return build.build_cli()
+
+
+def run(cmd, cwd=None, check=True):
+    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    text = r.stdout.decode(errors="replace")
+    if check:
+        assert r.returncode == 0, text
+    return r.returncode, text
+
+
+def _halfs(rng, h, w, c):
+    v = np.exp(rng.uniform(np.log(1e-3), np.log(4000.0), (h, w, c))).astype(np.float16)
+    v.reshape(-1)[::17] = 0
+    return v.view(np.uint16)
+
+
+@pytest.mark.parametrize("comp", [0, 2, 3])
+@pytest.mark.parametrize("channels", [3, 4])
+def test_exr_round_trip(cli, tmp_path, comp, channels):
+    rng = np.random.default_rng(comp * 10 + channels)
+    w, h = 37, 35                       # 35 rows: two full 16-line ZIP blocks and a partial one
+    px = _halfs(rng, h, w, channels)
+    raw, exr, back = tmp_path / "in.raw", tmp_path / "a.exr", tmp_path / "out.raw"
+    px.tofile(raw)
+    run([cli["h2y_iotool"], "write-exr", str(exr), str(w), str(h), str(channels), str(comp), str(raw)])
+    run([cli["h2y_iotool"], "read-exr", str(exr), str(back), str(channels)])
+    assert np.array_equal(np.fromfile(back, np.uint16).reshape(h, w, channels), px)
+    if channels == 4:                   # reading 3 of 4 channels drops alpha; reading 4 of 3 fills alpha with 1.0
+        run([cli["h2y_iotool"], "read-exr", str(exr), str(back), "3"])
+        assert np.array_equal(np.fromfile(back, np.uint16).reshape(h, w, 3), px[..., :3])
+    else:
+        run([cli["h2y_iotool"], "read-exr", str(exr), str(back), "4"])
+        got = np.fromfile(back, np.uint16).reshape(h, w, 4)
+        assert np.array_equal(got[..., :3], px) and (got[..., 3] == 0x3C00).all()
+
+
+def test_readers_against_opencv_codecs(cli, tmp_path):
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    w, h = 53, 41
+    f = np.exp(rng.uniform(np.log(1e-3), np.log(4000.0), (h, w, 3))).astype(np.float32)
+    for name, comp in (("none", cv2.IMWRITE_EXR_COMPRESSION_NO), ("zip", cv2.IMWRITE_EXR_COMPRESSION_ZIP),
+                       ("zips", cv2.IMWRITE_EXR_COMPRESSION_ZIPS)):
+        p = str(tmp_path / ("cv_%s.exr" % name))
+        try:
+            ok = cv2.imwrite(p, f, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION, comp])
+        except cv2.error:
+            pytest.skip("this OpenCV build has no OpenEXR codec")
+        assert ok
+        run([cli["h2y_iotool"], "read-exr", p, str(tmp_path / "o.raw")])
+        got = np.fromfile(tmp_path / "o.raw", np.uint16).reshape(h, w, 3).view(np.float16)
+        assert np.array_equal(got, f[..., ::-1].astype(np.float16))          # OpenCV is B,G,R
+    # a FLOAT-channel file is narrowed to half like Imf::RgbaInputFile does
+    p = str(tmp_path / "cv_f32.exr")
+    assert cv2.imwrite(p, f, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_FLOAT])
+    run([cli["h2y_iotool"], "read-exr", p, str(tmp_path / "o.raw")])
+    got = np.fromfile(tmp_path / "o.raw", np.uint16).reshape(h, w, 3).view(np.float16)
+    assert np.array_equal(got, f[..., ::-1].astype(np.float16))
+    # TIFF: libtiff-written, and our writer read back by libtiff
+    t = rng.integers(0, 65536, (h, w, 3), dtype=np.uint16)
+    p = str(tmp_path / "cv.tiff")
+    assert cv2.imwrite(p, t, [cv2.IMWRITE_TIFF_COMPRESSION, 1])
+    run([cli["h2y_iotool"], "read-tiff", p, str(tmp_path / "o.raw")])
+    assert np.array_equal(np.fromfile(tmp_path / "o.raw", np.uint16).reshape(h, w, 3), t[..., ::-1])
+    t.tofile(tmp_path / "t.raw")
+    p2 = str(tmp_path / "ours.tiff")
+    run([cli["h2y_iotool"], "write-tiff", p2, str(w), str(h), "3", str(tmp_path / "t.raw")])
+    back = cv2.imread(p2, cv2.IMREAD_UNCHANGED)
+    assert back is not None and back.dtype == np.uint16 and np.array_equal(back[..., ::-1], t)
+
+
+def test_tiff_round_trip_and_centre_cutout(cli, tmp_path):
+    rng = np.random.default_rng(9)
+    for channels in (3, 4):
+        w, h = 100, 60
+        t = rng.integers(0, 65536, (h, w, channels), dtype=np.uint16)
+        t.tofile(tmp_path / "t.raw")
+        p = str(tmp_path / "a.tiff")
+        run([cli["h2y_iotool"], "write-tiff", p, str(w), str(h), str(channels), str(tmp_path / "t.raw")])
+        run([cli["h2y_iotool"], "read-tiff", p, str(tmp_path / "o.raw")])
+        assert np.array_equal(np.fromfile(tmp_path / "o.raw", np.uint16).reshape(h, w, channels), t)
+        run([cli["h2y_iotool"], "read-tiff", p, str(tmp_path / "o.raw"), "40", "20"])      # tiff.cpp:191-220
+        assert np.array_equal(np.fromfile(tmp_path / "o.raw", np.uint16).reshape(20, 40, channels), t[20:40, 30:70])
+
+
+BASE = ["--src_chroma_format_idc", "3", "--dst_chroma_format_idc", "1", "--dst_bit_depth", "10",
+        "--src_matrix_coeffs", "0", "--dst_matrix_coeffs", "9", "--src_colour_primaries", "1", "--dst_colour_primaries", "9"]
+
+
+def test_dump_input_layouts_and_sequences(cli, tmp_path):
+    w, h = 64, 48
+    # numbered EXR sequence: frame i = seed i
+    frames = [synth.exr_half_frame(w, h, seed=i, channels=3) for i in range(3)]
+    for i, f in enumerate(frames):
+        f.tofile(tmp_path / "f.raw")
+        run([cli["h2y_iotool"], "write-exr", str(tmp_path / ("clip_%05d.exr" % (7 + i))), str(w), str(h), "3", "3", str(tmp_path / "f.raw")])
+    dump = tmp_path / "dump.raw"
+    _, text = run([cli["hdr2yuv"], "--src_filename", str(tmp_path / "clip_00007.exr"), "--dst_filename", str(tmp_path / "o.yuv"),
+                   "--src_pic_width", str(w), "--src_pic_height", str(h), "--src_bit_depth", "16", "--n_frames", "3",
+                   "--src_transfer_characteristics", "8", "--dst_transfer_characteristics", "PQ", "--dump_input", str(dump)] + BASE)
+    got = np.fromfile(dump, np.uint16).reshape(3, h, w, 3)
+    assert all(np.array_equal(got[i], frames[i]) for i in range(3)), text
+    assert "dst_transfer_characteristics: 16 (type: PQ)" in text          # names resolve like the reference's table
+    # printf-style pattern with a start frame
+    _, _ = run([cli["hdr2yuv"], "--src_filename", str(tmp_path / "clip_%05d.exr"), "--dst_filename", str(tmp_path / "o.yuv"),
+                "--src_pic_width", str(w), "--src_pic_height", str(h), "--src_bit_depth", "16", "--n_frames", "2",
+                "--src_start_frame", "8", "--src_transfer_characteristics", "8", "--dst_transfer_characteristics", "16",
+                "--dump_input", str(dump)] + BASE)
+    got = np.fromfile(dump, np.uint16).reshape(2, h, w, 3)
+    assert np.array_equal(got[0], frames[1]) and np.array_equal(got[1], frames[2])
+    # planar .rgb, second frame of the file: R,G,B planes -> interleaved R,G,B
+    rgb = np.stack([synth.tiff16_frame(w, h, seed=s) for s in (1, 2)], 0)
+    np.ascontiguousarray(rgb.transpose(0, 3, 1, 2)).tofile(tmp_path / "clip.rgb")
+    run([cli["hdr2yuv"], "--src_filename", str(tmp_path / "clip.rgb"), "--dst_filename", str(tmp_path / "o.yuv"),
+         "--src_pic_width", str(w), "--src_pic_height", str(h), "--src_bit_depth", "16", "--src_start_frame", "1",
+         "--src_transfer_characteristics", "16", "--dump_input", str(dump)] + BASE)
+    assert np.array_equal(np.fromfile(dump, np.uint16).reshape(h, w, 3), rgb[1])
+
+
+def test_option_errors_follow_the_reference(cli, tmp_path):
+    # 4:2:0 input is refused with the reference's message and exit(0) (hdr2yuv.cpp:536-574)
+    rc, text = run([cli["hdr2yuv"], "--src_filename", "a.yuv", "--dst_filename", "b.yuv", "--src_pic_width", "64",
+                    "--src_pic_height", "48", "--src_bit_depth", "10", "--src_chroma_format_idc", "1"], check=False)
+    assert rc == 0 and "Only 4:4:4 input supported" in text and "TOO MANY ARGUMENT ERRORS" in text
+    # unknown extension
+    rc, text = run([cli["hdr2yuv"], "--src_filename", "a.png", "--dst_filename", "b.yuv", "--src_pic_width", "64",
+                    "--src_pic_height", "48", "--src_bit_depth", "10", "--src_chroma_format_idc", "3"], check=False)
+    assert rc == 0 and "not recongized or not supported" in text
+    # unknown flags only warn
+    rc, text = run([cli["hdr2yuv"], "--bogus", "1", "--help"], check=False)
+    assert "WARNING: argument (--bogus) unrecongized" in text and "Transfer chracteristics options" in text
+    # a short raw file is reported, not read past its end
+    np.zeros(10, np.uint16).tofile(tmp_path / "short.rgb")
+    rc, text = run([cli["hdr2yuv"], "--src_filename", str(tmp_path / "short.rgb"), "--dst_filename", str(tmp_path / "o.yuv"),
+                    "--src_pic_width", "64", "--src_pic_height", "48", "--src_bit_depth", "16", "--src_chroma_format_idc", "3",
+                    "--dst_chroma_format_idc", "1", "--dst_bit_depth", "10"], check=False)
+    assert rc == 1 and "holds 0 frames" in text
