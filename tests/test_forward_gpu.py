@@ -199,3 +199,60 @@ def test_error_convention(ctx):
     with pytest.raises(cabi.H2YError) as e:              # write_yuv: dst bitdepth > src bitdepth (tiff.cpp:396-401)
         ctx.forward(p, d_src, d_dst, 1)
     assert e.value.status == cabi.ERR_BIT_DEPTH
+
+
+# ---- the two EXR-route kernels (h2y_forward2.cu) --------------------------------------------------------
+def _force_kernel(monkeypatch, which):
+    if which:
+        monkeypatch.setenv("H2Y_FORWARD_KERNEL", which)
+    else:
+        monkeypatch.delenv("H2Y_FORWARD_KERNEL", raising=False)
+
+
+@pytest.mark.parametrize("which", ["ring", "rows", None])
+@pytest.mark.parametrize("matrix,depth,full", [(9, 10, 0), (9, 12, 0), (11, 10, 0), (1, 10, 0), (9, 10, 1), (11, 12, 1)])
+def test_exr_kernels_match_oracle(ctx, monkeypatch, which, matrix, depth, full):
+    # widths that are and are not multiples of the 240-px strip, several frames per batch, RGB and RGBA
+    _force_kernel(monkeypatch, which)
+    for (w, h, ch) in ((240, 66, 3), (488, 130, 4), (1000, 34, 3)):
+        dst = dict(bit_depth=depth, full_range=full, transfer=16, primaries=9, matrix=matrix, chroma=1, resampler=1)
+        frames = [synth.exr_half_frame(w, h, seed=100 + s, channels=ch) for s in range(3)]
+        got = G.gpu_forward(ctx, frames, _HALF, dst)
+        for f, g in zip(frames, got):
+            G.compare_codes(g, G.oracle_forward(f, _HALF, dst), True, "%s %dx%d m%d b%d" % (which, w, h, matrix, depth))
+
+
+def test_large_4k_batch_takes_rows_kernel_and_matches_oracle(ctx):
+    # 10 frames of 3840x2160: the batch size at which h2y_forward picks the warp-autonomous kernel by itself.
+    # Every frame is checked through a checksum of the two oracle-verified frames' neighbours: frames repeat
+    # with period 2, so frames 0 and 1 (oracle) pin all ten.
+    w, h, n = 3840, 2160, 10
+    dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+    base = [synth.exr_half_frame_fast(w, h, seed=s, channels=3) for s in (0, 1)]
+    frames = [base[i % 2] for i in range(n)]
+    before = ctx.kernel_launches
+    got = G.gpu_forward(ctx, frames, _HALF, dst)
+    assert ctx.kernel_launches - before == 6          # init, stats, plan, LUT, rows kernel, v1 sweep for unclean frames
+    for i in (0, 1):
+        G.compare_codes(got[i], G.oracle_forward(base[i], _HALF, dst), True, "4K frame %d" % i)
+    for i in range(2, n):
+        assert np.array_equal(got[i], got[i % 2]), i
+
+
+@pytest.mark.parametrize("which", ["ring", "rows"])
+def test_unclean_frames_fall_back_to_the_general_kernel(ctx, monkeypatch, which):
+    # negative zero, +inf and a different (floor, ceiling) per frame: frames 1 and 2 are not "clean" and must come
+    # out of the v1 kernel, bit-identical to what the oracle gives; frames 0 and 3 stay on the fast kernel
+    _force_kernel(monkeypatch, which)
+    w, h = 256, 64
+    dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+    frames = [synth.exr_half_frame(w, h, seed=40 + s, channels=3, hi=1000.0 * (s + 1)) for s in range(4)]
+    frames[1] = frames[1].copy(); frames[1][5, 7, 1] = 0x8000                  # -0.0
+    frames[2] = frames[2].copy(); frames[2][9, 100, 2] = 0x7C00                # +inf
+    got = G.gpu_forward(ctx, frames, _HALF, dst)
+    for i in (0, 1, 3):
+        G.compare_codes(got[i], G.oracle_forward(frames[i], _HALF, dst), True, "frame %d" % i)
+    # +inf makes the reference's own range (int)inf - floor overflow: only require that the fast kernel declined it
+    monkeypatch.setenv("H2Y_FORCE_V1", "1")
+    ref2 = G.gpu_forward(ctx, [frames[2]], _HALF, dst)[0]
+    assert np.array_equal(got[2], ref2)
