@@ -497,8 +497,8 @@ h2y_status h2y_forward(h2y_ctx *c, const h2y_forward_params *p, const void *d_sr
                                     (uint8_t *)d_dst + (size_t)f * dst_stride, st)) != H2Y_OK) return s;
         return H2Y_OK;
     }
-    // bounded groups keep the LUT scratch (768 KiB per frame) small
-    const int GROUP = 64;
+    // bounded groups keep the LUT scratch (768 KiB per frame) bounded
+    const int GROUP = 256;
     for (int f0 = 0; f0 < nframes; f0 += GROUP) {
         const int nf = nframes - f0 < GROUP ? nframes - f0 : GROUP;
         const uint8_t *src = (const uint8_t *)d_src + (size_t)f0 * src_stride;

@@ -111,7 +111,7 @@ uint64_t h2y_kernel_launches(const h2y_ctx *ctx);         /* kernels this contex
  * CUDA events on the caller's stream.  h2y_profile_last_ms waits for the bracketed calls made since
  * h2y_profile_enable (the 16 most recent) and returns the AVERAGE duration of their dominant kernel
  * (the fused forward / inverse kernel) and of the kernels before it (statistics + LUT build; 0 when
- * there are none).  A forward call of more than 64 frames brackets each 64-frame group. */
+ * there are none).  A forward call of more than 256 frames brackets each 256-frame group. */
 h2y_status h2y_profile_enable(h2y_ctx *ctx, int on);
 h2y_status h2y_profile_last_ms(h2y_ctx *ctx, float *main_kernel_ms, float *prologue_ms);
 
