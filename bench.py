@@ -325,6 +325,7 @@ def bench_config(wl, name, frames_per_step):
            "l2": "inputs larger than L2 (batch >> 126 MB); no flush needed"}
     if wl["kind"] == "forward":
         cfg["layout"] = wl["layout"] + " (%d B/px in)" % LAYOUT_BPP[wl["layout"]]
+        cfg["content"] = "iid log-uniform samples (SURVEY.md 8d config 2)" if wl["src_kind"] == "half" else "iid uniform codes"
     return cfg
 
 
@@ -383,7 +384,12 @@ def run_gpu(args, wl, name):
         h_in = api.PinnedBuffer(in_bytes * nf)
         fb = api.src_frame_bytes(fparams.src)
         tmp_h = np.empty((8, h, w, 3), np.uint16)
-        fill_frames(fwl, first, 8, tmp_h)
+        if args.content == "iid":
+            fill_frames(fwl, first, 8, tmp_h)
+        else:
+            from hdr2yuv_b200 import synth
+            for i in range(8):
+                tmp_h[i] = synth.exr_half_frame_smooth_fast(w, h, seed=first + i)
         d_tmp = torch.from_numpy(tmp_h.view(np.uint8).reshape(-1)).to(dev)
         d_y = torch.empty(in_bytes * 8, dtype=torch.uint8, device=dev)
         ctx.forward(fparams, d_tmp, d_y, 8)
@@ -499,6 +505,8 @@ def run_gpu(args, wl, name):
         line["parity"] = {"frames": n, "samples": total, "differ": differ, "max_abs_codes": max_abs,
                           "tolerance_codes": 1 if wl["kind"] == "forward" and wl["src"]["transfer"] != wl["dst"]["transfer"] else 0,
                           "against": kind}
+    if d_invalid is not None:
+        line["config"]["invalid_pixels_per_frame_mean"] = float(d_invalid.float().mean().item())
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -519,6 +527,8 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the workload's)")
     ap.add_argument("--layout", choices=sorted(LAYOUT_BPP), default=None, help="override the source layout")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
+    ap.add_argument("--content", choices=["smooth", "iid"], default="smooth",
+                    help="inverse workload only: the .yuv frames come from spatially correlated (default) or iid-random sources")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3                                     # timing rule: W >= 3

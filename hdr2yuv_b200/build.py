@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhdr2yuv_b200.so")
 OBJDIR = os.path.join(HERE, "build")
 SOURCES = ["h2y_api.cu", "h2y_stats.cu", "h2y_staged.cu", "h2y_forward.cu", "h2y_forward2.cu", "h2y_inverse.cu"]
-HEADERS = [os.path.join(CSRC, "h2y_device.cuh"), os.path.join(CSRC, "h2y_internal.h"),
+HEADERS = [os.path.join(CSRC, "h2y_device.cuh"), os.path.join(CSRC, "h2y_internal.h"), os.path.join(CSRC, "h2y_f32x2.cuh"),
            os.path.join(ROOT, "include", "hdr2yuv_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

@@ -29,6 +29,7 @@
 #include <cmath>
 #include <cstdlib>
 
+#include "h2y_f32x2.cuh"
 #include "h2y_internal.h"
 
 namespace h2y {
@@ -38,46 +39,6 @@ constexpr int THREADS = 512, WARPS = THREADS / 32;
 constexpr int RING_ROWS = 64, RING_COLS = 120;            // float2 per column
 constexpr int RING_PITCH = RING_COLS * 2;                 // floats per ring row
 constexpr int LUT_MAX_CODES = 0x7C00;                     // clean frames: codes 0 .. 0x7BFF
-constexpr float MAGIC = 12582912.0f;                      // 1.5 * 2^23: integer part lands in the mantissa
-constexpr int MAGIC_BITS = 0x4B400000;
-
-typedef unsigned long long u64;
-
-__device__ __forceinline__ u64 pk(float lo, float hi)
-{
-    u64 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpk(u64 v, int &lo, int &hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
-__device__ __forceinline__ float plo(u64 v) { int a, b; unpk(v, a, b); return __int_as_float(a); }
-__device__ __forceinline__ float phi(u64 v) { int a, b; unpk(v, a, b); return __int_as_float(b); }
-__device__ __forceinline__ int ilo(u64 v) { int a, b; unpk(v, a, b); return a; }
-__device__ __forceinline__ int ihi(u64 v) { int a, b; unpk(v, a, b); return b; }
-__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c)
-{
-    u64 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ u64 fadd2(u64 a, u64 b)
-{
-    u64 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-// {a.lo*m, a.hi*m}, each product rounded on its own.  NOT mul.rn.f32x2: ptxas 12.9 contracts mul.rn.f32x2 +
-// add.rn.f32x2 into one FFMA2 even with explicit .rn and -fmad=false (checked in the SASS), which would drop
-// the reference's separate rounding of x*maxVR before +minVR (convert.cpp:1141).  Scalar FMULs are left alone.
-__device__ __forceinline__ u64 fmul2s(float lo, float hi, float m) { return pk(__fmul_rn(lo, m), __fmul_rn(hi, m)); }
-
-__device__ __forceinline__ u64 fadd2_rm(u64 a, u64 b)      // round toward -inf
-{
-    u64 r;
-    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ int clamp3(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 // position of chroma column c (0..119) inside a ring row, in float2 units: the horizontal stage stores
 // outputs {0,1} and {2,3} of a lane with two conflict-free 16-byte stores, so columns 4l, 4l+1 live in

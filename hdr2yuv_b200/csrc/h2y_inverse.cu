@@ -9,6 +9,9 @@
 // every thread then finishes 8 consecutive pixels of one row: 16-byte luma load, three
 // 16-byte interleaved stores.  4:4:4 chroma never touches HBM.
 // Algorithmic traffic: 3 B/px in (4:2:0 u16) + 6 B/px out (RGB16) = 9 B/px.
+#include <cstdlib>
+
+#include "h2y_f32x2.cuh"
 #include "h2y_internal.h"
 
 namespace h2y {
@@ -31,17 +34,20 @@ __device__ __forceinline__ float up_fin(float t, float hi)
 }
 
 // per-pixel inverse colour difference (yuv2tiff.cpp:399-430, 478-544); returns invalid count
+// MKIND: -1 = decide at run time from k.matrix; H2Y_INV_* = compiled for that family only (smaller code)
+template <int MKIND = -1>
 __device__ __forceinline__ int inv_pixel(const InvK &k, int Y, float fcb, float fcr, unsigned &Ro, unsigned &Go,
                                          unsigned &Bo)
 {
+    const int matrix = MKIND < 0 ? k.matrix : MKIND;
     int Yav = Y, Rp, Bp;
     const int Ysave = Y;
     const double top = (double)k.Full - 1.0;
     const double halfm = (double)k.Half - 0.5;
-    if (k.matrix == H2Y_INV_YDzDx) {
+    if (matrix == H2Y_INV_YDzDx) {
         Rp = 2 * (int)fcr - (int)(k.Full - 1) + Yav;
         Bp = 2 * (int)fcb - (int)(k.Full - 1) + Yav;
-    } else if (k.matrix == H2Y_INV_2020 || k.matrix == H2Y_INV_709) {
+    } else if (matrix == H2Y_INV_2020 || matrix == H2Y_INV_709) {
         float t = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn((double)fcb, -halfm), k.kb), (double)Yav));
         if ((double)t > top) t = (float)top;
         Bp = f2i_x86(t);
@@ -191,6 +197,240 @@ k_inverse_fused(InvK k, const uint16_t *__restrict__ yuv, size_t yuv_stride_elem
     }
 }
 
+// =================================================================================================
+// Large-batch variant: warp-autonomous rows, same idea as k_forward_exr420_rows (h2y_forward2.cu).
+// A warp owns a 240-pixel column strip (lane = 8 luma pixels = 4 chroma columns, lanes 0/31 are halo lanes of
+// the horizontal interpolation) and a long run of chroma rows.  The 7-row vertical window lives in a private
+// 8-slot shared-memory ring that only its own lanes touch (no barrier of any kind); both upsampling stages are
+// FFMA2 chains on {Cb,Cr} pairs (all terms are integers/256 below 2^23, so the order is free) with the
+// reference's clamp + truncation taken as a round-down add and an integer clamp.  The Y'CbCr inverse is
+// evaluated in fp32 with a guard band: each truncation is taken at x-G and x+G and the reference-exact
+// inv_pixel() (double arithmetic, true division) runs only for the rare pixel where the two disagree or a
+// component is negative (which also carries the invalidPixels bookkeeping).
+struct Inv2Args {
+    InvK k;
+    const uint8_t *yuv;
+    size_t yuv_stride;
+    uint8_t *rgb;
+    size_t rgb_stride;
+    uint32_t *invalid;
+    int nstrips, sub, wps;
+    long total_crows;        // nframes * (h / 2)
+    float hm, kb, kr, nwb, nwr, rwg, guard;   // Half-0.5, chroma gains, -wb, -wr, 1/wg as fp32
+};
+
+namespace {
+constexpr int RTHREADS = 512, RWARPS = RTHREADS / 32, RSLOTS = 8;
+constexpr float TWO23 = 8388608.0f;
+}
+
+// mode: 0 = every pixel through inv_pixel (Y100 / Y500), 1 = guarded fp32 (709 / 2020), 2 = integer Y'DzDx
+template <int MODE, bool FIR, bool ALPHA>
+__global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const InvK &k = A.k;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 *ring = reinterpret_cast<float4 *>(smem_raw) + (size_t)warp * RSLOTS * 2 * 32;      // [slot][half][lane]
+    const int w = k.w, h = k.h, wh = w >> 1, hh = h >> 1;
+    constexpr int nch = ALPHA ? 4 : 3;
+    const int hi_bits = MAGIC_BITS + (int)k.maxCV;
+    const int wk = warp / A.wps, sfirst = warp - wk * A.wps;
+    if (wk >= A.sub) return;
+    const long K = (long)gridDim.x * A.sub, kid = (long)blockIdx.x * A.sub + wk;
+    const long g0 = (kid * A.total_crows) / K, g1 = ((kid + 1) * A.total_crows) / K;
+    if (g1 <= g0) return;
+    const float G = A.guard;
+    int invalid_frame = -1;
+    unsigned invalid = 0;
+
+    for (int frame = (int)(g0 / hh); frame <= (int)((g1 - 1) / hh); frame++) {
+        const long fbase = (long)frame * hh;
+        const int cs = (int)(max(g0, fbase) - fbase), ce = (int)(min(g1, fbase + hh) - fbase);
+        const uint16_t *fy = reinterpret_cast<const uint16_t *>(A.yuv + (size_t)frame * A.yuv_stride);
+        const uint16_t *fcb = fy + (size_t)w * h, *fcr = fcb + (size_t)wh * hh;
+        uint16_t *frgb = reinterpret_cast<uint16_t *>(A.rgb + (size_t)frame * A.rgb_stride);
+        if (A.invalid && invalid_frame != frame) {
+            if (invalid && invalid_frame >= 0) atomicAdd(&A.invalid[invalid_frame], invalid);
+            invalid = 0; invalid_frame = frame;
+        }
+        for (int strip = sfirst; strip < A.nstrips; strip += A.wps) {
+            const int x0 = strip * 240, xl = x0 + 8 * (lane - 1);
+            const bool lane_in_pic = xl >= 0 && xl < w;
+            const bool lane_interior = lane >= 1 && lane < 31 && xl < min(x0 + 240, w);
+            const int cl = (lane_in_pic ? xl : (xl < 0 ? 0 : w - 8)) >> 1;       // first of this lane's 4 chroma columns
+
+            // chroma row r (picture row, already clamped) -> two float4 {cb0,cr0,cb1,cr1},{cb2,cr2,cb3,cr3}
+            auto fetch = [&](int r, uint2 &vb, uint2 &vr) {
+                vb = __ldg(reinterpret_cast<const uint2 *>(fcb + (size_t)r * wh + cl));
+                vr = __ldg(reinterpret_cast<const uint2 *>(fcr + (size_t)r * wh + cl));
+            };
+            auto stash = [&](int r, uint2 vb, uint2 vr) {
+                unsigned wb[2] = {vb.x, vb.y}, wr[2] = {vr.x, vr.y};
+                if (!k.full_range) {                                              // read clamp, yuv2tiff.cpp:297-320
+                    const unsigned lo2 = k.minVRC * 0x10001u, hi2 = k.maxVRC * 0x10001u;
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        asm("max.u16x2 %0, %0, %1;" : "+r"(wb[i]) : "r"(lo2)); asm("min.u16x2 %0, %0, %1;" : "+r"(wb[i]) : "r"(hi2));
+                        asm("max.u16x2 %0, %0, %1;" : "+r"(wr[i]) : "r"(lo2)); asm("min.u16x2 %0, %0, %1;" : "+r"(wr[i]) : "r"(hi2));
+                    }
+                }
+                const u64 m2 = pk(-TWO23, -TWO23);
+                u64 p[4];
+#pragma unroll
+                for (int i = 0; i < 2; i++) {        // 0x4B000000 | v is the float 2^23 + v
+                    p[2 * i] = fadd2(pk(__uint_as_float(__byte_perm(wb[i], 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(wr[i], 0x4B000000u, 0x7610))), m2);
+                    p[2 * i + 1] = fadd2(pk(__uint_as_float(__byte_perm(wb[i], 0x4B000000u, 0x7632)), __uint_as_float(__byte_perm(wr[i], 0x4B000000u, 0x7632))), m2);
+                }
+                float4 *slot = ring + (size_t)(r & (RSLOTS - 1)) * 64 + lane;
+                slot[0] = make_float4(plo(p[0]), phi(p[0]), plo(p[1]), phi(p[1]));
+                slot[32] = make_float4(plo(p[2]), phi(p[2]), plo(p[3]), phi(p[3]));
+            };
+            // prime the ring with rows clamp(cs-3) .. clamp(cs+3)
+            for (int r = max(cs - 3, 0); r <= min(cs + 3, hh - 1); r++) {
+                uint2 vb, vr;
+                fetch(r, vb, vr);
+                stash(r, vb, vr);
+            }
+            uint2 nb = make_uint2(0, 0), nr = make_uint2(0, 0);
+            if (cs + 4 <= hh - 1) fetch(cs + 4, nb, nr);
+
+            for (int c = cs; c < ce; c++) {
+                // luma rows 2c, 2c+1 (issued early)
+                uint4 yrow[2];
+                yrow[0] = __ldg(reinterpret_cast<const uint4 *>(fy + (size_t)(2 * c) * w + (cl << 1)));
+                yrow[1] = __ldg(reinterpret_cast<const uint4 *>(fy + (size_t)(2 * c + 1) * w + (cl << 1)));
+                __syncwarp();
+                // ---- vertical 2-phase 6-tap (yuv2tiff.cpp:615-650) on the 7-row window ----
+                u64 win[7][4];
+#pragma unroll
+                for (int t = 0; t < 7; t++) {
+                    const int r = min(max(c - 3 + t, 0), hh - 1);
+                    const float4 *slot = ring + (size_t)(r & (RSLOTS - 1)) * 64 + lane;
+                    const float4 a = slot[0], b = slot[32];
+                    win[t][0] = pk(a.x, a.y); win[t][1] = pk(a.z, a.w); win[t][2] = pk(b.x, b.y); win[t][3] = pk(b.z, b.w);
+                }
+                u64 dv[2][4];          // the reference's dst422 rows 2c and 2c+1, this lane's 4 columns
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (FIR) {
+                        const u64 a3 = pk(3.0f / 256.0f, 3.0f / 256.0f), a16n = pk(-16.0f / 256.0f, -16.0f / 256.0f),
+                                  a67 = pk(67.0f / 256.0f, 67.0f / 256.0f), a227 = pk(227.0f / 256.0f, 227.0f / 256.0f),
+                                  a32n = pk(-32.0f / 256.0f, -32.0f / 256.0f), a7 = pk(7.0f / 256.0f, 7.0f / 256.0f), hf = pk(0.5f, 0.5f);
+                        u64 e = ffma2(a3, win[0][i], hf);
+                        e = ffma2(a16n, win[1][i], e); e = ffma2(a67, win[2][i], e); e = ffma2(a227, win[3][i], e);
+                        e = ffma2(a32n, win[4][i], e); e = ffma2(a7, win[5][i], e);
+                        u64 o = ffma2(a3, win[6][i], hf);
+                        o = ffma2(a16n, win[5][i], o); o = ffma2(a67, win[4][i], o); o = ffma2(a227, win[3][i], o);
+                        o = ffma2(a32n, win[2][i], o); o = ffma2(a7, win[1][i], o);
+                        int e0, e1, o0, o1;
+                        unpk(fadd2_rm(e, pk(MAGIC, MAGIC)), e0, e1);
+                        unpk(fadd2_rm(o, pk(MAGIC, MAGIC)), o0, o1);
+                        dv[0][i] = fadd2(pk(__int_as_float(clamp3(e0, MAGIC_BITS, hi_bits)), __int_as_float(clamp3(e1, MAGIC_BITS, hi_bits))), pk(-MAGIC, -MAGIC));
+                        dv[1][i] = fadd2(pk(__int_as_float(clamp3(o0, MAGIC_BITS, hi_bits)), __int_as_float(clamp3(o1, MAGIC_BITS, hi_bits))), pk(-MAGIC, -MAGIC));
+                    } else {
+                        dv[0][i] = dv[1][i] = win[3][i];        // box: replicate (yuv2tiff.cpp:577-588)
+                    }
+                }
+                // the next row enters the ring while the pixels are finished; then prefetch the one after
+                if (c + 4 <= hh - 1) stash(c + 4, nb, nr);
+                if (c + 5 <= hh - 1 && c + 1 < ce) fetch(c + 5, nb, nr);
+
+#pragma unroll 1
+                for (int half = 0; half < 2; half++) {                  // not unrolled: the instruction cache is the limit
+                    u64 d[4];                                           // selects, not a run-time array index (no local memory)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) d[i] = half ? dv[1][i] : dv[0][i];
+                    // ---- horizontal: even x copies, odd x 6-tap over columns i-2 .. i+3 (yuv2tiff.cpp:655-683) ----
+                    u64 cpx[8];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) cpx[2 * i] = d[i];
+                    if (FIR) {
+                        u64 L2 = pk(__shfl_up_sync(0xffffffffu, plo(d[2]), 1), __shfl_up_sync(0xffffffffu, phi(d[2]), 1));
+                        u64 L3 = pk(__shfl_up_sync(0xffffffffu, plo(d[3]), 1), __shfl_up_sync(0xffffffffu, phi(d[3]), 1));
+                        u64 R0 = pk(__shfl_down_sync(0xffffffffu, plo(d[0]), 1), __shfl_down_sync(0xffffffffu, phi(d[0]), 1));
+                        u64 R1 = pk(__shfl_down_sync(0xffffffffu, plo(d[1]), 1), __shfl_down_sync(0xffffffffu, phi(d[1]), 1));
+                        u64 R2 = pk(__shfl_down_sync(0xffffffffu, plo(d[2]), 1), __shfl_down_sync(0xffffffffu, phi(d[2]), 1));
+                        if (xl == 0) L2 = L3 = d[0];                    // columns clamp to [0, w/2-1]
+                        if (xl + 8 >= w) R0 = R1 = R2 = d[3];
+                        const u64 nb8[9] = {L2, L3, d[0], d[1], d[2], d[3], R0, R1, R2};
+                        const u64 b21 = pk(21.0f / 256.0f, 21.0f / 256.0f), b52n = pk(-52.0f / 256.0f, -52.0f / 256.0f),
+                                  b159 = pk(159.0f / 256.0f, 159.0f / 256.0f), hf = pk(0.5f, 0.5f);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            u64 t = ffma2(b21, nb8[i], hf);
+                            t = ffma2(b21, nb8[i + 5], t); t = ffma2(b52n, nb8[i + 1], t); t = ffma2(b52n, nb8[i + 4], t);
+                            t = ffma2(b159, nb8[i + 2], t); t = ffma2(b159, nb8[i + 3], t);
+                            int t0, t1;
+                            unpk(fadd2_rm(t, pk(MAGIC, MAGIC)), t0, t1);
+                            cpx[2 * i + 1] = fadd2(pk(__int_as_float(clamp3(t0, MAGIC_BITS, hi_bits)), __int_as_float(clamp3(t1, MAGIC_BITS, hi_bits))), pk(-MAGIC, -MAGIC));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) cpx[2 * i + 1] = d[i];
+                    }
+                    if (!lane_interior) continue;
+                    // ---- eight pixels of luma row 2c + half ----
+                    const uint4 yr = half ? yrow[1] : yrow[0];
+                    const unsigned yw[4] = {yr.x, yr.y, yr.z, yr.w};
+                    unsigned smp[8][3];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        unsigned Y = (q & 1) ? (yw[q >> 1] >> 16) : (yw[q >> 1] & 0xffffu);
+                        if (!k.full_range) Y = min(max(Y, k.minVR), k.maxVR);                 // yuv2tiff.cpp:283-294
+                        const float cbf = plo(cpx[q]), crf = phi(cpx[q]);
+                        bool slow = MODE == 0;
+                        int Rp = 0, Gp = 0, Bp = 0;
+                        if (MODE == 1) {
+                            const float Yf = __uint_as_float(0x4B000000u | Y) - TWO23;
+                            const float Yg = Yf - G;
+                            const u64 tlo = ffma2(fadd2(cpx[q], pk(-A.hm, -A.hm)), pk(A.kb, A.kr), pk(Yg, Yg));
+                            int B1, R1, B2, R2;
+                            unpk(fadd2_rm(tlo, pk(MAGIC, MAGIC)), B1, R1);
+                            unpk(fadd2_rm(fadd2(tlo, pk(2.0f * G, 2.0f * G)), pk(MAGIC, MAGIC)), B2, R2);
+                            const int Bc = min(B1, hi_bits), Rc = min(R1, hi_bits);          // t > Full-1 -> Full-1 (406-412)
+                            const u64 brf = fadd2(pk(__int_as_float(Bc), __int_as_float(Rc)), pk(-MAGIC, -MAGIC));
+                            const float g = __fmaf_rn(A.nwr, phi(brf), __fmaf_rn(A.nwb, plo(brf), Yf));
+                            const float glo = __fmaf_rn(g, A.rwg, 0.5f - G);
+                            const int G1 = __float_as_int(__fadd_rd(glo, MAGIC)), G2 = __float_as_int(__fadd_rd(glo + 2.0f * G, MAGIC));
+                            slow = (((B1 ^ B2) | (R1 ^ R2) | (G1 ^ G2)) != 0) | (min(min(B1, R1), G1) < MAGIC_BITS);
+                            Bp = Bc - MAGIC_BITS; Rp = Rc - MAGIC_BITS; Gp = min(G1, hi_bits) - MAGIC_BITS;
+                        } else if (MODE == 2) {                                              // yuv2tiff.cpp:401-402
+                            const int off = (int)Y - (int)(k.Full - 1);
+                            Rp = 2 * (int)crf + off; Bp = 2 * (int)cbf + off; Gp = (int)Y;
+                            slow = (Rp | Bp) < 0;
+                        }
+                        unsigned R, Gv, B;
+                        if (slow) {
+                            invalid += (unsigned)inv_pixel<MODE == 1 ? H2Y_INV_2020 : (MODE == 2 ? H2Y_INV_YDzDx : -1)>(k, (int)Y, cbf, crf, R, Gv, B);
+                        } else {
+                            if (!k.full_range) {                                              // yuv2tiff.cpp:515-524
+                                Rp = clamp3(Rp, (int)k.minVR, (int)k.maxVR); Gp = clamp3(Gp, (int)k.minVR, (int)k.maxVR);
+                                Bp = clamp3(Bp, (int)k.minVR, (int)k.maxVR);
+                            }
+                            R = ((unsigned)Rp << k.SR) & 0xffffu; Gv = ((unsigned)Gp << k.SR) & 0xffffu; B = ((unsigned)Bp << k.SR) & 0xffffu;
+                        }
+                        smp[q][0] = R; smp[q][1] = Gv; smp[q][2] = B;
+                    }
+                    unsigned ow[16];
+                    if (!ALPHA) {
+#pragma unroll
+                        for (int i = 0; i < 12; i++) ow[i] = smp[(2 * i) / 3][(2 * i) % 3] | (smp[(2 * i + 1) / 3][(2 * i + 1) % 3] << 16);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) { ow[2 * q] = smp[q][0] | (smp[q][1] << 16); ow[2 * q + 1] = smp[q][2] | 0xffff0000u; }
+                    }
+                    uint4 *o = reinterpret_cast<uint4 *>(frgb + ((size_t)(2 * c + half) * w + xl) * nch);
+#pragma unroll
+                    for (int i = 0; i < nch; i++) o[i] = make_uint4(ow[4 * i], ow[4 * i + 1], ow[4 * i + 2], ow[4 * i + 3]);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (A.invalid && invalid && invalid_frame >= 0) atomicAdd(&A.invalid[invalid_frame], invalid);
+}
+
 h2y_status make_invk(const h2y_inverse_params &p, InvK *k)
 {
     if (p.width < 8 || p.height < 2 || (p.width & 7) || (p.height & 1)) return H2Y_ERR_ARG;
@@ -217,6 +457,47 @@ h2y_status make_invk(const h2y_inverse_params &p, InvK *k)
 h2y_status launch_inverse(h2y_ctx_impl *c, const InvK &k, const void *d_yuv, size_t yuv_stride, void *d_rgb,
                           size_t rgb_stride, int nframes, uint32_t *d_invalid, cudaStream_t st)
 {
+    // large batches: warp-autonomous rows kernel
+    {
+        Inv2Args A;
+        A.k = k; A.yuv = (const uint8_t *)d_yuv; A.yuv_stride = yuv_stride; A.rgb = (uint8_t *)d_rgb; A.rgb_stride = rgb_stride;
+        A.invalid = d_invalid;
+        A.nstrips = (k.w + 239) / 240;
+        A.wps = 1;
+        for (int d = 1; d <= RWARPS; d++) if (RWARPS % d == 0 && A.nstrips % d == 0) A.wps = d;
+        A.sub = RWARPS / A.wps;
+        A.total_crows = (long)nframes * (k.h / 2);
+        A.hm = (float)k.Half - 0.5f; A.kb = (float)k.kb; A.kr = (float)k.kr;
+        A.nwb = -(float)k.wb; A.nwr = -(float)k.wr; A.rwg = (float)(1.0 / k.wg);
+        A.guard = 1.0f / (float)(1 << (21 - k.bit_depth));          // same bound as the forward kernel
+        const long rows_per_worker = A.total_crows / ((long)c->sm_count * A.sub);
+        const char *force = getenv("H2Y_INVERSE_KERNEL");           // "tile" / "rows": tests and experiments
+        const bool want_rows = force ? force[0] == 'r' : rows_per_worker >= 48;
+        if (want_rows) {
+            int grid = c->sm_count;
+            while (grid > 1 && A.total_crows / ((long)grid * A.sub) < 4) grid >>= 1;
+            const size_t smem = (size_t)RWARPS * RSLOTS * 64 * sizeof(float4);
+            const int mode = (k.matrix == H2Y_INV_2020 || k.matrix == H2Y_INV_709) ? 1 : (k.matrix == H2Y_INV_YDzDx ? 2 : 0);
+#define LR(M, F, AL)                                                                                                       \
+    do {                                                                                                                   \
+        H2Y_CUDA(c, cudaFuncSetAttribute(k_inverse_rows<M, F, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_inverse_rows<M, F, AL><<<grid, RTHREADS, smem, st>>>(A);                                                        \
+    } while (0)
+#define LRM(M)                                                                                                             \
+    do {                                                                                                                   \
+        if (k.fir && k.alpha) LR(M, true, true);                                                                           \
+        else if (k.fir) LR(M, true, false);                                                                                \
+        else if (k.alpha) LR(M, false, true);                                                                              \
+        else LR(M, false, false);                                                                                          \
+    } while (0)
+            if (mode == 1) LRM(1); else if (mode == 2) LRM(2); else LRM(0);
+#undef LRM
+#undef LR
+            c->launches++;
+            H2Y_CUDA(c, cudaGetLastError());
+            return H2Y_OK;
+        }
+    }
     dim3 grid((k.w + TILE_W - 1) / TILE_W, (k.h + TILE_H - 1) / TILE_H, nframes);
 #define INV(F, A) k_inverse_fused<F, A><<<grid, 256, 0, st>>>(k, (const uint16_t *)d_yuv, yuv_stride / 2, \
                                                               (uint16_t *)d_rgb, rgb_stride / 2, d_invalid)

@@ -78,3 +78,24 @@ def exr_half_frame_fast(width, height, seed=0, channels=3):
         out[..., 3] = 0x3C00                    # alpha = 1.0
         return out
     return px
+
+
+def exr_half_frame_smooth_fast(width, height, seed=0, block=16):
+    """Spatially correlated linear-light frame (what decoded video looks like to the inverse path): a log-uniform
+    luminance field at 1/block resolution, bilinearly smooth through a separable box blur, with a mild colour cast
+    per channel and 2 % pixel noise.  (H, W, 3) uint16 half bit patterns, all >= 0, max pinned to 4000."""
+    rng = np.random.default_rng(seed)
+    bh, bw = height // block + 2, width // block + 2
+    low = np.exp(rng.uniform(np.log(0.05), np.log(2000.0), (bh, bw))).astype(np.float32)
+    lum = np.repeat(np.repeat(low, block, 0), block, 1)
+    k = block
+    c = np.cumsum(lum, 0); lum = (c[k:] - c[:-k]) / k
+    c = np.cumsum(lum, 1); lum = (c[:, k:] - c[:, :-k]) / k
+    lum = lum[:height, :width]
+    cast = rng.uniform(0.6, 1.4, (bh, bw, 3)).astype(np.float32)
+    cast = np.repeat(np.repeat(cast, block, 0), block, 1)[:height, :width]
+    noise = rng.uniform(0.98, 1.02, (height, width, 1)).astype(np.float32)
+    v = (lum[..., None] * cast * noise).astype(np.float16)
+    flat = v.reshape(-1)
+    flat[int(rng.integers(0, flat.size))] = np.float16(4000.0)
+    return np.ascontiguousarray(v).view(np.uint16)
