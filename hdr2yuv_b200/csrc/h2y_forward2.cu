@@ -442,39 +442,55 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
             const bool lane_interior = lane >= 1 && lane < 31 && xl < min(x0 + a.strip_w, w);
             const int xload = lane_in_pic ? xl : (xl < 0 ? 0 : w - 8);          // halo lanes outside the picture read a valid
                                                                                  // address; their values are replaced below
+            const bool left_edge = xl == 0, right_edge = xl + 8 >= w;
             u64 acc[6][4];
 #pragma unroll
             for (int i = 0; i < 6; i++)
 #pragma unroll
                 for (int c = 0; c < 4; c++) acc[i][c] = 0ull;
 
-            const int rfirst = ys - 6, rlast = ye + 4;                          // rows feeding outputs ys/2 .. ye/2-1
-            RawPx<NCH> raw;
-            load_px8<NCH>(raw, fsrc, w, min(max(rfirst, 0), h - 1), xload);
-            for (int r = rfirst; r <= rlast; r++) {
-                // ---- 8 pixels of (replicated) row r ----
+            const int rfirst = ys - 6, rlast = ye + 4;                          // rows feeding outputs ys/2 .. ye/2-1 (both even)
+            // running pointers: source row (clamped = edge replicate), Y row, chroma output row
+            const size_t spitch = (size_t)w * (2 * NCH);
+            const uint8_t *sp = fsrc + (size_t)min(max(rfirst, 0), h - 1) * spitch + (size_t)xload * (2 * NCH);
+            uint16_t *yp = fY + (ptrdiff_t)rfirst * w + xl;
+            uint16_t *cbp = fCb + ((ptrdiff_t)(rfirst >> 1) - 3) * wh + (xl >> 1);
+            const ptrdiff_t crd = fCr - fCb;
+
+            // one row: 8 pixels -> Y store, chroma, horizontal 7-tap -> o[4]
+            auto row_front = [&](const RawPx<NCH> &raw, int r, u64 o[4]) {
                 unsigned g[8], b[8], rr[8];
                 split_codes<NCH>(raw, g, b, rr);
-                if (r < rlast) load_px8<NCH>(raw, fsrc, w, min(max(r + 1, 0), h - 1), xload);    // prefetch
                 uint4 ypack;
                 u64 ch[8];
                 pixels8<MK>(a, lut_s, g, b, rr, ypack, ch, fallbacks);
-                if (lane_interior && r >= ys && r < ye) *reinterpret_cast<uint4 *>(fY + (size_t)r * w + xl) = ypack;
-                // ---- horizontal 7-tap: neighbours through shuffles ----
+                if (lane_interior && r >= ys && r < ye) *reinterpret_cast<uint4 *>(yp) = ypack;
                 float l3x = __shfl_up_sync(0xffffffffu, plo(ch[3]), 1), l3y = __shfl_up_sync(0xffffffffu, phi(ch[3]), 1);
                 float l5x = __shfl_up_sync(0xffffffffu, plo(ch[5]), 1), l5y = __shfl_up_sync(0xffffffffu, phi(ch[5]), 1);
                 float l7x = __shfl_up_sync(0xffffffffu, plo(ch[7]), 1), l7y = __shfl_up_sync(0xffffffffu, phi(ch[7]), 1);
                 float n1x = __shfl_down_sync(0xffffffffu, plo(ch[1]), 1), n1y = __shfl_down_sync(0xffffffffu, phi(ch[1]), 1);
                 float n3x = __shfl_down_sync(0xffffffffu, plo(ch[3]), 1), n3y = __shfl_down_sync(0xffffffffu, phi(ch[3]), 1);
                 u64 l3 = pk(l3x, l3y), l5 = pk(l5x, l5y), l7 = pk(l7x, l7y), n1 = pk(n1x, n1y), n3 = pk(n3x, n3y);
-                if (xl == 0) l3 = l5 = l7 = ch[0];                  // replicate s[0]     (convert.cpp:295-300)
-                if (xl + 8 >= w) n1 = n3 = ch[7];                   // replicate s[W-1]
-                u64 o[4];
+                if (left_edge) l3 = l5 = l7 = ch[0];                // replicate s[0]     (convert.cpp:295-300)
+                if (right_edge) n1 = n3 = ch[7];                    // replicate s[W-1]
                 o[0] = fir_h7_pair(l3, l5, l7, ch[0], ch[1], ch[3], ch[5], hi_bits);
                 o[1] = fir_h7_pair(l5, l7, ch[1], ch[2], ch[3], ch[5], ch[7], hi_bits);
                 o[2] = fir_h7_pair(l7, ch[1], ch[3], ch[4], ch[5], ch[7], n1, hi_bits);
                 o[3] = fir_h7_pair(ch[1], ch[3], ch[5], ch[6], ch[7], n1, n3, hi_bits);
-                // ---- vertical 12-tap, running (convert.cpp:333-377): output row j takes rows 2j-5 .. 2j+6 ----
+            };
+            // advance the source pointer from (clamped) row r to (clamped) row r+1
+            auto next_src = [&](int r) { sp += ((unsigned)r < (unsigned)(h - 1)) ? spitch : 0; };
+
+            RawPx<NCH> raw, cur;
+            load_px8<NCH>(raw, sp, 0, 0, 0);
+#pragma unroll 1
+            for (int r = rfirst; r <= rlast; r++) {          // one row body for both parities: the instruction cache is a limit
+                cur = raw;
+                next_src(r);
+                if (r < rlast) load_px8<NCH>(raw, sp, 0, 0, 0);                 // prefetch the next row
+                u64 o[4];
+                row_front(cur, r, o);
+                yp += w;
                 if ((r & 1) == 0) {
                     // even row r = 2m: acc[i] is output j = m-3+i and receives tap 11-2i; acc[0] completes
 #pragma unroll
@@ -493,13 +509,13 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                             cbv[c] = (unsigned)clamp3(lo_ >> shift, clo, chi);
                             crv[c] = (unsigned)clamp3(hi_ >> shift, clo, chi);
                         }
-                        const size_t off = (size_t)j * wh + (xl >> 1);
-                        *reinterpret_cast<uint2 *>(fCb + off) = make_uint2(__byte_perm(cbv[0], cbv[1], 0x5410), __byte_perm(cbv[2], cbv[3], 0x5410));
-                        *reinterpret_cast<uint2 *>(fCr + off) = make_uint2(__byte_perm(crv[0], crv[1], 0x5410), __byte_perm(crv[2], crv[3], 0x5410));
+                        *reinterpret_cast<uint2 *>(cbp) = make_uint2(__byte_perm(cbv[0], cbv[1], 0x5410), __byte_perm(cbv[2], cbv[3], 0x5410));
+                        *reinterpret_cast<uint2 *>(cbp + crd) = make_uint2(__byte_perm(crv[0], crv[1], 0x5410), __byte_perm(crv[2], crv[3], 0x5410));
                     }
+                    cbp += wh;
                 } else {
-                    // odd row r = 2m+1: the accumulators shift down by one output (the FFMA2 writes the neighbour),
-                    // old acc[i+1] receives tap 10-2i; a new output starts in acc[5] with tap 0
+                    // odd row r = 2m+1: the accumulators shift down by one output (the FFMA2 writes the neighbour);
+                    // old acc[i+1] receives tap 10-2i and a new output starts in acc[5] with tap 0
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
 #pragma unroll
