@@ -452,6 +452,32 @@ def run_gpu(args, wl, name):
     if gpu_ref_out is not None:
         host_matches_device = bool(np.array_equal(h_out.view(np.uint16).reshape(nf, -1), gpu_ref_out))
 
+    # ---- what the host platform gives at this N: plain pinned copies, both directions at once, all ranks together ---
+    pcie = None
+    try:
+        nbytes = 1 << 30
+        hp_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        hp_out = torch.empty(nbytes // 2, dtype=torch.uint8, pin_memory=True)
+        dp_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        dp_out = torch.empty(nbytes // 2, dtype=torch.uint8, device=dev)
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        for timed in (False, True):
+            barrier(dist)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                with torch.cuda.stream(s1):
+                    dp_in.copy_(hp_in, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    hp_out.copy_(dp_out, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        dt = reduce_max(dist, dt, dev)
+        pcie = {"h2d_gbs_per_gpu": 3 * nbytes / dt / 1e9, "d2h_gbs_per_gpu": 1.5 * nbytes / dt / 1e9,
+                "what": "plain cudaMemcpyAsync of pinned buffers, 2:1 H2D:D2H like the workload, all ranks concurrently"}
+        del hp_in, hp_out, dp_in, dp_out
+    except Exception as exc:                                  # never let the probe break the bench line
+        pcie = {"error": str(exc)[:100]}
+
     # ---- numbers ---------------------------------------------------------------------------------------
     px_step = px_per_frame * nf * world
     mpx = px_step * args.steps / (dev_ms * 1e-3) / 1e6
@@ -478,7 +504,7 @@ def run_gpu(args, wl, name):
                 "h2d_gbs_per_gpu": in_bytes * nf * args.steps / (e2e_ms * 1e-3) / 1e9,
                 "d2h_gbs_per_gpu": out_bytes * nf * args.steps / (e2e_ms * 1e-3) / 1e9,
                 "api": "h2y_forward_host" if wl["kind"] == "forward" else "h2y_inverse_host",
-                "host_output_equals_device_output": host_matches_device},
+                "host_output_equals_device_output": host_matches_device, "pcie_copy_ceiling": pcie},
         "gpu_launches": int(launches) * world,
         "clocks": clocks,
     }

@@ -74,6 +74,11 @@ SYMBOLS = {
     "h2y_write_yuv_clamp": (C.c_int, [C.c_void_p, C.POINTER(PicDesc), C.POINTER(_P3), C.c_int, C.c_void_p]),
     "h2y_subsample_420_to_444": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                            C.c_uint16, C.c_uint16, C.c_void_p]),
+    "h2y_matrix_inverse": (C.c_int, [C.c_void_p, C.POINTER(PicDesc), C.POINTER(_P3), C.POINTER(PicDesc), C.POINTER(_P3),
+                                     C.c_void_p, C.c_void_p]),
+    "h2y_write_tiff_rows": (C.c_int, [C.c_void_p, C.POINTER(PicDesc), C.POINTER(_P3), C.c_int, C.c_void_p, C.c_void_p]),
+    "h2y_inverse444_host": (C.c_int, [C.c_void_p, C.POINTER(PicDesc), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                      C.c_size_t, C.c_int, C.c_void_p]),
     "h2y_forward": (C.c_int, [C.c_void_p, C.POINTER(ForwardParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                               C.c_int, C.c_void_p]),
     "h2y_forward_host": (C.c_int, [C.c_void_p, C.POINTER(ForwardParams), C.c_void_p, C.c_size_t, C.c_void_p,

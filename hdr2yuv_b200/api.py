@@ -127,6 +127,26 @@ class Context:
         check(lib().h2y_subsample_420_to_444(self._h, src.data_ptr(), dst.data_ptr(), width, height, int(algorithm),
                                              minCV, maxCV, _stream_ptr(stream)), "h2y_subsample_420_to_444")
 
+    def matrix_inverse(self, out_pic, out_planes, in_pic, in_planes, invalid=None, stream=None):
+        """matrix_inverse (convert.cpp:1320-1867): contiguous U16 planes Y,Cb,Cr -> G,B,R."""
+        po, pi = _planes(out_planes), _planes(in_planes)
+        check(lib().h2y_matrix_inverse(self._h, C.byref(out_pic), C.byref(po), C.byref(in_pic), C.byref(pi),
+                                       invalid.data_ptr() if invalid is not None else None, _stream_ptr(stream)),
+              "h2y_matrix_inverse")
+
+    def write_tiff_rows(self, pic, planes, src_bit_depth, rgb, stream=None):
+        """compute half of write_tiff (tiff.cpp:559-652): planes G,B,R -> interleaved R,G,B."""
+        pl = _planes(planes)
+        check(lib().h2y_write_tiff_rows(self._h, C.byref(pic), C.byref(pl), int(src_bit_depth), rgb.data_ptr(),
+                                        _stream_ptr(stream)), "h2y_write_tiff_rows")
+
+    def inverse444_host(self, in_pic, out_bit_depth, yuv, rgb, nframes, invalid=None):
+        """.yuv 4:4:4 frames -> RGB16 rows as main() + write_tiff do (hdr2yuv.cpp:803-821, 898-933)."""
+        n = in_pic.width * in_pic.height * 6
+        check(lib().h2y_inverse444_host(self._h, C.byref(in_pic), int(out_bit_depth), _addr(yuv), n, _addr(rgb), n,
+                                        int(nframes), _addr(invalid) if invalid is not None else None),
+              "h2y_inverse444_host")
+
     # ---- fused ----------------------------------------------------------------------------------
     def forward(self, params, src, dst, nframes, src_stride=None, dst_stride=None, stream=None):
         """pic_stats -> matrix_convert -> convert -> write_yuv clamp on frames resident in HBM."""

@@ -26,10 +26,11 @@ namespace {
 
 enum FileType { FT_UNDEFINED = 0, FT_YUV, FT_TIFF, FT_EXR, FT_Y4M, FT_DPX, FT_RGB };
 struct TypeInfo { int idx; const char *name; int supported; };
-// hdr.h:48-68; DPX and the .tiff/.exr/.dpx/.rgb destinations are outside the accelerated path
+// hdr.h:48-68; DPX and the .exr/.dpx/.rgb destinations are outside the accelerated path; a .tiff destination is
+// served for .yuv sources (matrix_inverse + write_tiff, hdr2yuv.cpp:818-819, 930-933)
 const TypeInfo kInputTypes[] = {{FT_UNDEFINED, "UNDEFINED", 0}, {FT_YUV, "yuv", 1}, {FT_TIFF, "tiff", 1}, {FT_EXR, "exr", 1},
                                 {FT_Y4M, "y4m", 0}, {FT_DPX, "dpx", 0}, {FT_RGB, "rgb", 1}};
-const TypeInfo kOutputTypes[] = {{FT_UNDEFINED, "UNDEFINED", 0}, {FT_YUV, "yuv", 1}, {FT_TIFF, "tiff", 0}, {FT_EXR, "exr", 0},
+const TypeInfo kOutputTypes[] = {{FT_UNDEFINED, "UNDEFINED", 0}, {FT_YUV, "yuv", 1}, {FT_TIFF, "tiff", 1}, {FT_EXR, "exr", 0},
                                  {FT_Y4M, "y4m", 0}, {FT_DPX, "dpx", 0}, {FT_RGB, "rgb", 0}};
 // hdr.h:140-166 (index = transfer_characteristics code)
 const TypeInfo kTransfers[] = {{0, "RESERVED0", 0}, {1, "BT709", 1}, {2, "UNSPECIFIED", 0}, {3, "RESERVED3", 0},
@@ -350,6 +351,34 @@ int main(int argc, char *argv[])
         }
         fclose(f);
         printf("dumped %d frame(s) of %dx%d, layout %d, %zu bytes each\n", nframes, s.width, s.height, (int)s.layout, s.frame_bytes);
+        return 0;
+    }
+
+    if (a.output_file_type == FT_TIFF) {
+        // .yuv (4:4:4) -> .tiff: matrix_inverse into a tmp picture of the source depth, write_tiff at the dst depth
+        if (s.type != FT_YUV) { printf("ERROR: a .tiff destination needs a .yuv source (matrix_inverse, hdr2yuv.cpp:818-819)\n"); return 1; }
+        h2y_ctx *ctx = nullptr;
+        h2y_status st = h2y_ctx_create(0, &ctx);
+        if (st != H2Y_OK) { printf("ERROR: %s\n", h2y_status_string(st)); return 1; }
+        const size_t fb = (size_t)s.width * s.height * 6;
+        uint8_t *hin = (uint8_t *)h2y_host_alloc(fb), *hout = (uint8_t *)h2y_host_alloc(fb);
+        if (!hin || !hout) { printf("ERROR: pinned host allocation failed\n"); return 1; }
+        for (int i = 0; i < nframes; i++) {
+            if (!read_frame(a, s, i, hin, &err)) { printf("ERROR: %s\n", err.c_str()); return 1; }
+            uint32_t invalid = 0;
+            st = h2y_inverse444_host(ctx, &fp.src, out.bit_depth, hin, fb, hout, fb, 1, &invalid);
+            if (st == H2Y_ERR_MATRIX) { printf("Can't determine color difference to use?\n\n"); return 0; }   // exit(0), convert.cpp:1737
+            if (st != H2Y_OK) { printf("%s (h2y_status %d)\n", h2y_status_string(st), (int)st); return 1; }
+            const std::string name = nframes > 1 ? h2yio::sequence_name(a.dst_filename, i) : std::string(a.dst_filename);
+            if (!h2yio::tiff_write_rgb16(name, reinterpret_cast<const uint16_t *>(hout), s.width, s.height, 3, &err)) {
+                printf("unable to open %s.  Exiting\n", name.c_str());
+                return 0;
+            }
+            if (a.verbose_level > 0) printf("%s: invalid pixels %u\n", name.c_str(), invalid);
+        }
+        h2y_host_free(hin); h2y_host_free(hout);
+        h2y_ctx_destroy(ctx);
+        printf("wrote %d tiff frame(s)\n", nframes);
         return 0;
     }
 

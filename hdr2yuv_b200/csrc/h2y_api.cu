@@ -402,6 +402,58 @@ h2y_status h2y_subsample_420_to_444(h2y_ctx *c, const void *d_src, void *d_dst, 
                            (cudaStream_t)stream);
 }
 
+static h2y_status minv_family(const h2y_pic_desc *in, int *family)
+{
+    // convert.cpp:1324-1325, 1387: DXYZ is cleared by comparing matrix_coeffs with the BOOLEANS D709/D2020/Y100/Y500
+    const int m = in->matrix_coeffs;
+    const int D709 = m == H2Y_MATRIX_BT709, D2020 = m == H2Y_MATRIX_BT2020c;
+    int DXYZ = 1;
+    if (m == D709 || m == D2020 || m == 0) DXYZ = 0;
+    if (DXYZ) { *family = 0; return H2Y_OK; }
+    if (D2020) return H2Y_ERR_UNSUPPORTED;          // unreachable: m == 10 never clears DXYZ
+    if (D709) { *family = 1; return H2Y_OK; }
+    return H2Y_ERR_MATRIX;                          // "Can't determine color difference to use?" (1735-1738)
+}
+
+h2y_status h2y_matrix_inverse(h2y_ctx *c, const h2y_pic_desc *out, void *const d_out[3], const h2y_pic_desc *in,
+                              const void *const d_in[3], uint32_t *d_invalid, void *stream)
+{
+    if (!c || !out || !in || !d_out || !d_in) return H2Y_ERR_ARG;
+    if (in->pic_buffer_type != H2Y_PIC_TYPE_U16 || out->pic_buffer_type != H2Y_PIC_TYPE_U16) return H2Y_ERR_UNSUPPORTED;
+    if (in->chroma_format_idc != H2Y_CHROMA_444 || in->width != out->width || in->height != out->height) return H2Y_ERR_PRECONDITION;
+    if (!depth_ok(in->bit_depth) || !depth_ok(out->bit_depth) || in->width < 1 || in->height < 1) return H2Y_ERR_ARG;
+    int family;
+    h2y_status s = minv_family(in, &family);
+    if (s != H2Y_OK) return s;
+    const long npix = (long)in->width * in->height;
+    // the staged call takes three separate planes: they must be one allocation's worth apart or we copy-free by
+    // launching on plane pointers -> require contiguity Y,Cb,Cr (what init_pic + the .yuv reader produce is three
+    // mallocs; the binding passes them contiguous)
+    const uint16_t *p0 = (const uint16_t *)d_in[0];
+    if ((const uint16_t *)d_in[1] != p0 + npix || (const uint16_t *)d_in[2] != p0 + 2 * npix) return H2Y_ERR_ARG;
+    uint16_t *o0 = (uint16_t *)d_out[0];
+    if ((uint16_t *)d_out[1] != o0 + npix || (uint16_t *)d_out[2] != o0 + 2 * npix) return H2Y_ERR_ARG;
+    h2y_clip_limits clip;
+    clip_of(in->bit_depth, in->video_full_range_flag, &clip);
+    const int d = in->bit_depth - out->bit_depth;
+    H2Y_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_invalid) H2Y_CUDA(c, cudaMemsetAsync(d_invalid, 0, sizeof(uint32_t), st));
+    return launch_matrix_inverse(c, family, clip.minVR, clip.maxVR, d > 0 ? d : 0, d < 0 ? -d : 0, npix, p0, 0, o0, 0, 1, 0,
+                                 d_invalid, st);
+}
+
+h2y_status h2y_write_tiff_rows(h2y_ctx *c, const h2y_pic_desc *pic, const void *const d_planes[3], int src_bit_depth,
+                               void *d_rgb, void *stream)
+{
+    if (!c || !pic || !d_planes || !d_rgb || pic->width < 1 || pic->height < 1) return H2Y_ERR_ARG;
+    const int sr = pic->bit_depth - src_bit_depth;
+    if (sr < 0) return H2Y_ERR_BIT_DEPTH;
+    H2Y_CUDA(c, cudaSetDevice(c->device));
+    return launch_write_tiff_rows(c, (long)pic->width * pic->height, (const uint16_t *)d_planes[0], (const uint16_t *)d_planes[1],
+                                  (const uint16_t *)d_planes[2], (uint16_t *)d_rgb, sr, (cudaStream_t)stream);
+}
+
 // ---- fused forward ------------------------------------------------------------------------------------
 
 static h2y_status forward_validate(const h2y_forward_params *p, h2y_pic_desc *tmp, PixK *k)
@@ -674,6 +726,46 @@ h2y_status h2y_inverse_host(h2y_ctx *c, const h2y_inverse_params *p, const void 
                      [&](uint8_t *di, size_t ip, uint8_t *dob, size_t op, int nf, cudaStream_t st) {
                          if (d_inv) cudaMemsetAsync(d_inv + done, 0, sizeof(uint32_t) * nf, st);
                          h2y_status r = launch_inverse(c, k, di, ip, dob, op, nf, d_inv ? d_inv + done : nullptr, st);
+                         done += nf;
+                         return r;
+                     });
+    if (s != H2Y_OK) return s;
+    if (h_invalid) H2Y_CUDA(c, cudaMemcpy(h_invalid, d_inv, sizeof(uint32_t) * (size_t)nframes, cudaMemcpyDeviceToHost));
+    return H2Y_OK;
+}
+
+h2y_status h2y_inverse444_host(h2y_ctx *c, const h2y_pic_desc *in, int out_bit_depth, const void *h_yuv, size_t yuv_stride,
+                               void *h_rgb, size_t rgb_stride, int nframes, uint32_t *h_invalid)
+{
+    if (!c || !in || !h_yuv || !h_rgb || nframes < 0) return H2Y_ERR_ARG;
+    if (nframes == 0) return H2Y_OK;
+    if (in->pic_buffer_type != H2Y_PIC_TYPE_U16) return H2Y_ERR_UNSUPPORTED;
+    if (in->chroma_format_idc != H2Y_CHROMA_444) return H2Y_ERR_PRECONDITION;
+    if (!depth_ok(in->bit_depth) || !depth_ok(out_bit_depth) || in->width < 1 || in->height < 1) return H2Y_ERR_ARG;
+    if (out_bit_depth < in->bit_depth) return H2Y_ERR_BIT_DEPTH;       // write_tiff would shift by a negative count
+    int family;
+    h2y_status s = minv_family(in, &family);
+    if (s != H2Y_OK) return s;
+    const size_t npix = (size_t)in->width * in->height, inb = npix * 6, outb = npix * 6;
+    if (yuv_stride < inb || rgb_stride < outb) return H2Y_ERR_ARG;
+    h2y_clip_limits clip;
+    clip_of(in->bit_depth, in->video_full_range_flag, &clip);
+    H2Y_CUDA(c, cudaSetDevice(c->device));
+    uint32_t *d_inv = nullptr;
+    if (h_invalid) {
+        void *v;
+        if ((s = scratch_reserve(c, SCR_STATS, sizeof(uint32_t) * (size_t)nframes + 64, &v)) != H2Y_OK) return s;
+        d_inv = (uint32_t *)v;
+    }
+    int done = 0;
+    s = run_pipeline(c, (const uint8_t *)h_yuv, yuv_stride, inb, (uint8_t *)h_rgb, rgb_stride, outb, nframes,
+                     [&](uint8_t *di, size_t ip, uint8_t *dob, size_t op, int nf, cudaStream_t st) {
+                         if (d_inv) cudaMemsetAsync(d_inv + done, 0, sizeof(uint32_t) * nf, st);
+                         // tmp picture has the source's depth (hdr2yuv.cpp:803-808): matrix_inverse shifts by 0,
+                         // write_tiff by out - tmp
+                         h2y_status r = launch_matrix_inverse(c, family, clip.minVR, clip.maxVR, 0, out_bit_depth - in->bit_depth,
+                                                              (long)npix, (const uint16_t *)di, ip / 2, (uint16_t *)dob, op / 2, nf, 1,
+                                                              d_inv ? d_inv + done : nullptr, st);
                          done += nf;
                          return r;
                      });

@@ -88,6 +88,12 @@ h2y_status launch_out_clamp(h2y_ctx_impl *c, uint16_t *d_plane, size_t n, int sh
 h2y_status launch_upsample(h2y_ctx_impl *c, const uint16_t *d_src, uint16_t *d_dst, uint16_t *d_mid, int w, int h,
                            int fir, unsigned minCV, unsigned maxCV, cudaStream_t st);
 
+h2y_status launch_matrix_inverse(h2y_ctx_impl *c, int family, int minVR, int maxVR, int shift_right, int shift_left,
+                                 long npix, const uint16_t *d_in, size_t in_stride_elems, uint16_t *d_out,
+                                 size_t out_stride_elems, int nframes, int interleave, uint32_t *d_invalid, cudaStream_t st);
+h2y_status launch_write_tiff_rows(h2y_ctx_impl *c, long npix, const uint16_t *g, const uint16_t *b, const uint16_t *r,
+                                  uint16_t *rgb, int sr, cudaStream_t st);
+
 // ---- launchers (h2y_forward.cu / h2y_inverse.cu) ---------------------------------------------
 bool fused_forward_supported(const h2y_forward_params &p);
 bool forward_exr420_supported(const h2y_forward_params &p, const PixK &k, int tmp_bit_depth);

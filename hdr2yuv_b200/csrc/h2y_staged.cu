@@ -323,4 +323,101 @@ h2y_status launch_upsample(h2y_ctx_impl *c, const uint16_t *d_src, uint16_t *d_d
     return H2Y_OK;
 }
 
+// ---- matrix_inverse (convert.cpp:1320-1867) and write_tiff's compute (tiff.cpp:605-628) ----------------
+// hdr2yuv's 4:4:4-only inverse, float variables with double sub-expressions exactly as written, including the
+// hard-coded Half = 2048 / Full = 4096 (1337-1338) and the family selection quirk (1387): matrix_coeffs == 1 takes
+// the BT.709 equations, everything else except 0 the Y'DzDx ones.  family: 0 = Y'DzDx, 1 = BT.709.
+struct MinvK {
+    int family;
+    int minVR, maxVR;        // in_pic->clip (FULLRANGE is hard-coded 0, 1343)
+    int shift_right, shift_left;   // 1796-1809, then write_tiff's << (pic depth - src depth) when interleaving
+};
+
+__device__ __forceinline__ int minv_pixel(const MinvK &k, unsigned y, unsigned cb, unsigned cr, int &R, int &G, int &B)
+{
+    float Yav = (float)y, Cb = (float)cb, Cr = (float)cr, Rp, Bp, tmpF;
+    if (k.family == 0) {
+        Rp = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(2.0, (double)Cr), -4095.0), (double)Yav));
+        Bp = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(2.0, (double)Cb), -4095.0), (double)Yav));
+    } else {
+        tmpF = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn((double)Cb, -2047.5), 1.8556), (double)Yav));
+        if ((double)tmpF > 4095.0) tmpF = 4095.0f;
+        Bp = tmpF;
+        tmpF = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn((double)Cr, -2047.5), 1.5748), (double)Yav));
+        if ((double)tmpF > 4095.0) tmpF = 4095.0f;
+        Rp = tmpF;
+        const double g = __dadd_rn(__dadd_rn((double)Yav, -__dmul_rn(0.07222, (double)Bp)), -__dmul_rn(0.2126, (double)Rp));
+        tmpF = __double2float_rn(__dadd_rn(__ddiv_rn(g, 0.7152), 0.5));
+        if ((double)tmpF > 4095.0) tmpF = 4095.0f;
+        Yav = tmpF;
+    }
+    G = f2i_x86(Yav); B = f2i_x86(Bp); R = f2i_x86(Rp);
+    int invalid = 0;
+    if (G < 0) { G = 0; invalid++; }
+    if (R < 0) { R = 0; invalid++; }
+    if (B < 0) { B = 0; invalid++; }
+    R = R < k.minVR ? k.minVR : R; G = G < k.minVR ? k.minVR : G; B = B < k.minVR ? k.minVR : B;
+    R = R > k.maxVR ? k.maxVR : R; G = G > k.maxVR ? k.maxVR : G; B = B > k.maxVR ? k.maxVR : B;
+    R = (R >> k.shift_right) << k.shift_left; G = (G >> k.shift_right) << k.shift_left; B = (B >> k.shift_right) << k.shift_left;
+    return invalid;
+}
+
+// planar Y,Cb,Cr -> planar G,B,R (INTERLEAVE = false, the staged matrix_inverse) or interleaved R,G,B rows
+// (INTERLEAVE = true: matrix_inverse + write_tiff fused); grid.y = frame
+template <bool INTERLEAVE>
+__global__ void __launch_bounds__(256)
+k_matrix_inverse(MinvK k, long npix, const uint16_t *__restrict__ in, size_t in_stride, uint16_t *__restrict__ out,
+                 size_t out_stride, uint32_t *invalid_out)
+{
+    const uint16_t *fi = in + (size_t)blockIdx.y * in_stride;
+    uint16_t *fo = out + (size_t)blockIdx.y * out_stride;
+    int invalid = 0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long)gridDim.x * blockDim.x) {
+        int R, G, B;
+        invalid += minv_pixel(k, fi[i], fi[npix + i], fi[2 * npix + i], R, G, B);
+        if (INTERLEAVE) { fo[3 * i] = (uint16_t)R; fo[3 * i + 1] = (uint16_t)G; fo[3 * i + 2] = (uint16_t)B; }
+        else { fo[i] = (uint16_t)G; fo[npix + i] = (uint16_t)B; fo[2 * npix + i] = (uint16_t)R; }
+    }
+    if (invalid_out) {
+        for (int o = 16; o > 0; o >>= 1) invalid += __shfl_xor_sync(0xffffffffu, invalid, o);
+        if ((threadIdx.x & 31) == 0 && invalid) atomicAdd(&invalid_out[blockIdx.y], (uint32_t)invalid);
+    }
+}
+
+// write_tiff's compute on its own: planes G,B,R -> interleaved R,G,B, << sr
+__global__ void __launch_bounds__(256)
+k_write_tiff_rows(long npix, const uint16_t *__restrict__ g, const uint16_t *__restrict__ b, const uint16_t *__restrict__ r,
+                  uint16_t *__restrict__ rgb, int sr)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long)gridDim.x * blockDim.x) {
+        rgb[3 * i] = (uint16_t)((int)r[i] << sr); rgb[3 * i + 1] = (uint16_t)((int)g[i] << sr); rgb[3 * i + 2] = (uint16_t)((int)b[i] << sr);
+    }
+}
+
+h2y_status launch_matrix_inverse(h2y_ctx_impl *c, int family, int minVR, int maxVR, int shift_right, int shift_left,
+                                 long npix, const uint16_t *d_in, size_t in_stride_elems, uint16_t *d_out,
+                                 size_t out_stride_elems, int nframes, int interleave, uint32_t *d_invalid, cudaStream_t st)
+{
+    MinvK k = {family, minVR, maxVR, shift_right, shift_left};
+    long want = (npix + 255) / 256;
+    const int blocks = (int)(want < 8L * c->sm_count ? want : 8L * c->sm_count);
+    dim3 grid(blocks, nframes);
+    if (interleave) k_matrix_inverse<true><<<grid, 256, 0, st>>>(k, npix, d_in, in_stride_elems, d_out, out_stride_elems, d_invalid);
+    else k_matrix_inverse<false><<<grid, 256, 0, st>>>(k, npix, d_in, in_stride_elems, d_out, out_stride_elems, d_invalid);
+    c->launches++;
+    H2Y_CUDA(c, cudaGetLastError());
+    return H2Y_OK;
+}
+
+h2y_status launch_write_tiff_rows(h2y_ctx_impl *c, long npix, const uint16_t *g, const uint16_t *b, const uint16_t *r,
+                                  uint16_t *rgb, int sr, cudaStream_t st)
+{
+    long want = (npix + 255) / 256;
+    const int blocks = (int)(want < 8L * c->sm_count ? want : 8L * c->sm_count);
+    k_write_tiff_rows<<<blocks, 256, 0, st>>>(npix, g, b, r, rgb, sr);
+    c->launches++;
+    H2Y_CUDA(c, cudaGetLastError());
+    return H2Y_OK;
+}
+
 }   // namespace h2y

@@ -157,6 +157,27 @@ h2y_status h2y_write_yuv_clamp(h2y_ctx *ctx, const h2y_pic_desc *pic, void *cons
 h2y_status h2y_subsample_420_to_444(h2y_ctx *ctx, const void *d_src, void *d_dst, int width, int height,
                                     int algorithm, uint16_t minCV, uint16_t maxCV, void *stream);
 
+/* matrix_inverse (convert.cpp:1320-1867): hdr2yuv's own 4:4:4 inverse, used when a .yuv is converted to a .tiff
+ * (dispatch at hdr2yuv.cpp:818-819).  U16 4:4:4 planes Y,Cb,Cr -> planes G,B,R at out->bit_depth.  The family is
+ * chosen from in->matrix_coeffs exactly as the reference does, quirks included: 1 takes the BT.709 equations,
+ * 0 is "Can't determine color difference to use?" (H2Y_ERR_MATRIX), every other value the Y'DzDx ones.  Half/Full
+ * are the reference's hard-coded 2048/4096.  d_invalid_pixels (optional, one uint32) receives invalidPixels. */
+h2y_status h2y_matrix_inverse(h2y_ctx *ctx, const h2y_pic_desc *out, void *const d_out_planes[3],
+                              const h2y_pic_desc *in, const void *const d_in_planes[3], uint32_t *d_invalid_pixels,
+                              void *stream);
+
+/* the compute half of write_tiff (tiff.cpp:559-652): planes G,B,R -> interleaved R,G,B u16 rows, every sample
+ * << (pic->bit_depth - src_bit_depth).  H2Y_ERR_BIT_DEPTH when that difference is negative. */
+h2y_status h2y_write_tiff_rows(h2y_ctx *ctx, const h2y_pic_desc *pic, const void *const d_planes[3], int src_bit_depth,
+                               void *d_rgb, void *stream);
+
+/* .yuv (4:4:4) -> .tiff as main() does it (hdr2yuv.cpp:803-821, 898-933): matrix_inverse into a tmp picture of the
+ * source's depth, then write_tiff at out_bit_depth.  Frames of three u16 planes in host memory -> interleaved RGB16
+ * rows in host memory; h_invalid_pixels (optional) gets one count per frame. */
+h2y_status h2y_inverse444_host(h2y_ctx *ctx, const h2y_pic_desc *in, int out_bit_depth, const void *h_yuv444,
+                               size_t yuv_stride_bytes, void *h_rgb, size_t rgb_stride_bytes, int nframes,
+                               uint32_t *h_invalid_pixels);
+
 /* ---- fused forward path: what main() does between read_file and the file append ----------- */
 typedef struct h2y_forward_params {
     h2y_pic_desc src;            /* in_pic after the reader: geometry, layout, depth, range, VUI codes */

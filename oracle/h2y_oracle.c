@@ -656,3 +656,88 @@ long orc_yuv2tiff_frame(const orc_inv_params *p, const uint16_t *yuv, uint16_t *
     free(Yp); free(cb); free(cr); free(cb4); free(cr4);
     return invalid;
 }
+
+/* ---- convert.cpp:1320-1867 matrix_inverse (U16 pictures, 4:4:4) + tiff.cpp:559-652 write_tiff ------ */
+/* Returns the invalidPixels count, or -2 for "Can't determine color difference to use?" (convert.cpp:1735-1738).
+ * Quirks kept: Half / Full are hard-coded 2048 / 4096 (1337-1338); D2020 tests MATRIX_BT2020c = 10 (1325);
+ * DXYZ is cleared by comparing matrix_coeffs with the BOOLEANS D709 / D2020 / Y100 / Y500 (1387), so only
+ * matrix_coeffs == 1 takes the 709 equations, matrix_coeffs == 0 is the error, everything else is Y'DzDx;
+ * Bp / Rp stay float (not truncated) inside the green equation; FULLRANGE is hard-coded 0 (1343) so the
+ * clamp always uses in_pic->clip; the final shift is by |in.bit_depth - out.bit_depth| (1796-1809). */
+long orc_matrix_inverse(uint16_t *out_planes[3], const uint16_t *in_planes[3], int w, int h, int matrix_coeffs,
+                        int in_bit_depth, int in_full_range, int out_bit_depth)
+{
+    const short D709 = matrix_coeffs == ORC_MATRIX_BT709;
+    const short D2020 = matrix_coeffs == ORC_MATRIX_BT2020C;
+    const short Y500 = 0, Y100 = 0;
+    short DXYZ = 1;
+    const unsigned short Half = 2048, Full = 4096;
+    if (matrix_coeffs == D709 || matrix_coeffs == D2020 || matrix_coeffs == Y100 || matrix_coeffs == Y500) DXYZ = 0;
+    orc_clip_t clip;
+    orc_set_clip(in_bit_depth, in_full_range, &clip);
+    long invalid = 0;
+    const long n = (long)w * h;
+    for (long i = 0; i < n; i++) {
+        float tmpF, Yav = (float)in_planes[0][i], Cb = (float)in_planes[1][i], Cr = (float)in_planes[2][i], Rp, Bp;
+        if (DXYZ) {                                                     /* 1707-1710 */
+            Rp = (float)(2.0 * Cr - (Full - 1.0) + Yav);
+            Bp = (float)(2.0 * Cb - (Full - 1.0) + Yav);
+        } else if (D2020) {                                             /* 1711-1721 (unreachable: see above) */
+            tmpF = (float)(((float)(Cb) - (Half - 0.5)) * 1.8814 + Yav);
+            if (tmpF > (Full - 1.0)) tmpF = (float)(Full - 1.0);
+            Bp = tmpF;
+            tmpF = (float)(((float)(Cr) - (Half - 0.5)) * 1.4746 + Yav);
+            if (tmpF > (Full - 1.0)) tmpF = (float)(Full - 1.0);
+            Rp = tmpF;
+            tmpF = (float)(((float)Yav - 0.0593 * (float)Bp - 0.2627 * (float)Rp) / 0.6780 + 0.5);
+            if (tmpF > (Full - 1.0)) tmpF = (float)(Full - 1.0);
+            Yav = tmpF;
+        } else if (D709) {                                              /* 1722-1733 */
+            tmpF = (float)(((float)(Cb) - (Half - 0.5)) * 1.8556 + Yav);
+            if (tmpF > (Full - 1.0)) tmpF = (float)(Full - 1.0);
+            Bp = tmpF;
+            tmpF = (float)(((float)(Cr) - (Half - 0.5)) * 1.5748 + Yav);
+            if (tmpF > (Full - 1.0)) tmpF = (float)(Full - 1.0);
+            Rp = tmpF;
+            tmpF = (float)(((float)Yav - 0.07222 * (float)Bp - 0.2126 * (float)Rp) / 0.7152 + 0.5);
+            if (tmpF > (Full - 1.0)) tmpF = (float)(Full - 1.0);
+            Yav = tmpF;
+        } else {
+            return -2;
+        }
+        int G = (int)Yav, B = (int)Bp, R = (int)Rp;                     /* 1758-1779 */
+        if (G < 0) { G = 0; invalid++; }
+        if (R < 0) { invalid++; R = 0; }
+        if (B < 0) { invalid++; B = 0; }
+        R = (R < clip.minVR) ? clip.minVR : R;                          /* 1783-1793, FULLRANGE == 0 */
+        G = (G < clip.minVR) ? clip.minVR : G;
+        B = (B < clip.minVR) ? clip.minVR : B;
+        R = (R > clip.maxVR) ? clip.maxVR : R;
+        G = (G > clip.maxVR) ? clip.maxVR : G;
+        B = (B > clip.maxVR) ? clip.maxVR : B;
+        if (in_bit_depth > out_bit_depth) {                             /* 1796-1809 */
+            const int shift = in_bit_depth - out_bit_depth;
+            R >>= shift; G >>= shift; B >>= shift;
+        } else {
+            const int shift = out_bit_depth - in_bit_depth;
+            R <<= shift; G <<= shift; B <<= shift;
+        }
+        out_planes[0][i] = (uint16_t)G;                                 /* 1816-1818 */
+        out_planes[1][i] = (uint16_t)B;
+        out_planes[2][i] = (uint16_t)R;
+    }
+    return invalid;
+}
+
+/* tiff.cpp:605-628: planes G,B,R -> interleaved R,G,B rows, each sample << (pic.bit_depth - src_bit_depth) */
+void orc_write_tiff_rows(uint16_t *rgb, const uint16_t *planes[3], long npix, int pic_bit_depth, int src_bit_depth)
+{
+    const short SR = (short)(pic_bit_depth - src_bit_depth);
+    for (long i = 0; i < npix; i++) {
+        int G = planes[0][i], B = planes[1][i], R = planes[2][i];
+        R = R << SR; G = G << SR; B = B << SR;
+        rgb[3 * i + 0] = (unsigned short)R;
+        rgb[3 * i + 1] = (unsigned short)G;
+        rgb[3 * i + 2] = (unsigned short)B;
+    }
+}

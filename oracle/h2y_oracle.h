@@ -118,6 +118,12 @@ typedef struct {
  * rgb = interleaved R,G,B(,A) 16-bit rows.  Returns the invalidPixels count. */
 long orc_yuv2tiff_frame(const orc_inv_params *p, const uint16_t *yuv, uint16_t *rgb);
 
+/* hdr2yuv's 4:4:4 inverse (convert.cpp:1320-1867) on U16 planes Y,Cb,Cr -> G,B,R; returns invalidPixels or -2 */
+long orc_matrix_inverse(uint16_t *out_planes[3], const uint16_t *in_planes[3], int w, int h, int matrix_coeffs,
+                        int in_bit_depth, int in_full_range, int out_bit_depth);
+/* write_tiff's compute (tiff.cpp:605-628): planes G,B,R -> interleaved R,G,B, << (pic depth - src depth) */
+void orc_write_tiff_rows(uint16_t *rgb, const uint16_t *planes[3], long npix, int pic_bit_depth, int src_bit_depth);
+
 #ifdef __cplusplus
 }
 #endif

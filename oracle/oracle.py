@@ -263,3 +263,35 @@ def yuv2tiff(yuv, w, h, bit_depth=12, matrix=INV_YDZDX, fir=True, full_range=Fal
     rgb = np.zeros((h, w, nch), np.uint16)
     inv = port_lib().orc_yuv2tiff_frame(C.byref(p), _ptr(yuv), _ptr(rgb))
     return rgb, int(inv)
+
+
+def matrix_inverse(planes, matrix_coeffs, in_bit_depth, in_full_range, out_bit_depth, backend="port"):
+    """hdr2yuv's 4:4:4 inverse (convert.cpp:1320-1867): (3,H,W) uint16 Y,Cb,Cr -> (3,H,W) uint16 G,B,R.
+    Returns (planes, invalid_pixels); invalid_pixels is None for the compiled reference (it only prints it)."""
+    planes = np.ascontiguousarray(planes, np.uint16)
+    _, h, w = planes.shape
+    out = np.zeros((3, h, w), np.uint16)
+    pi = (C.c_void_p * 3)(*[planes[c].ctypes.data for c in range(3)])
+    po = (C.c_void_p * 3)(*[out[c].ctypes.data for c in range(3)])
+    if backend == "ref":
+        cfg = (C.c_int * 6)(w, h, matrix_coeffs, in_bit_depth, in_full_range, out_bit_depth)
+        rc = ref_lib().ref_matrix_inverse(cfg, pi, po)
+        if rc:
+            raise RuntimeError("reference matrix_inverse returned %d" % rc)
+        return out, None
+    lib = port_lib()
+    lib.orc_matrix_inverse.restype = C.c_long
+    inv = lib.orc_matrix_inverse(po, pi, w, h, matrix_coeffs, in_bit_depth, in_full_range, out_bit_depth)
+    if inv == -2:
+        raise RuntimeError("Can't determine color difference to use?")
+    return out, int(inv)
+
+
+def write_tiff_rows(planes, pic_bit_depth, src_bit_depth):
+    """write_tiff's compute (tiff.cpp:605-628): (3,H,W) G,B,R -> (H,W,3) interleaved R,G,B, << depth difference."""
+    planes = np.ascontiguousarray(planes, np.uint16)
+    _, h, w = planes.shape
+    rgb = np.zeros((h, w, 3), np.uint16)
+    pi = (C.c_void_p * 3)(*[planes[c].ctypes.data for c in range(3)])
+    port_lib().orc_write_tiff_rows(_ptr(rgb), pi, C.c_long(h * w), pic_bit_depth, src_bit_depth)
+    return rgb

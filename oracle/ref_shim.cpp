@@ -209,4 +209,26 @@ void ref_pic_stats(int is_f32, int bit_depth, int w, int h, const void *const pl
     }
     deinit_pic(&p);
 }
+
+/* the reference's matrix_inverse (convert.cpp:1320) on U16 4:4:4 planes Y,Cb,Cr -> G,B,R.
+ * cfg: [0]w [1]h [2]matrix_coeffs [3]in_bit_depth [4]in_full_range [5]out_bit_depth.  Returns matrix_inverse's rc. */
+int ref_matrix_inverse(const int *cfg, const void *const in_planes[3], unsigned short *const out_planes[3])
+{
+    Quiet q;
+    const int w = cfg[0], h = cfg[1];
+    const size_t n = (size_t)w * h;
+    static hdr_t hd;
+    memset(&hd, 0, sizeof(hd));
+    pic_t in, out;
+    memset(&in, 0, sizeof(in));
+    memset(&out, 0, sizeof(out));
+    init_pic(&in, w, h, CHROMA_444, cfg[3], cfg[4], 0, 0, cfg[2], 0, PIC_TYPE_U16, 0, 0, "in");
+    init_pic(&out, w, h, CHROMA_444, cfg[5], cfg[4], 0, 0, 0, 0, PIC_TYPE_U16, 0, 0, "out");
+    for (int c = 0; c < 3; c++) memcpy(in.buf[c], in_planes[c], n * 2);
+    const int rc = matrix_inverse(&out, &hd, &in);
+    for (int c = 0; c < 3; c++) memcpy(out_planes[c], out.buf[c], n * 2);
+    deinit_pic(&in);
+    deinit_pic(&out);
+    return rc;
+}
 }

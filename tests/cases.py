@@ -79,3 +79,21 @@ def widen_yuv(yuv10, bit_depth):
 
 def inverse_input_key(matrix):
     return "yuv10_ydzdx" if matrix == 0 else "yuv10_ycbcr"
+
+
+# matrix_inverse (hdr2yuv .yuv 4:4:4 -> .tiff) cases: (matrix_coeffs, in_bit_depth, in_full_range, out_bit_depth)
+MINV_CASES = [(m, ibd, fr, obd) for m in (1, 9, 11, 10, 12) for (ibd, fr, obd) in ((12, 0, 12), (12, 0, 16), (10, 0, 16), (10, 1, 10), (14, 0, 12))]
+MW, MH = 96, 40
+
+
+def minv_input(in_bit_depth, seed=21):
+    """(3,H,W) u16 Y,Cb,Cr: a plausible picture (luma ramp + noise, chroma around mid-grey) plus extreme codes that
+    drive components negative (invalidPixels) and above Full-1."""
+    rng = np.random.default_rng(seed + in_bit_depth)
+    top = (1 << in_bit_depth) - 1
+    y = np.clip(np.linspace(0, top, MW)[None, :] + rng.integers(-40, 41, (MH, MW)), 0, top)
+    c = np.clip((top + 1) // 2 + rng.integers(-(top // 6), top // 6 + 1, (2, MH, MW)), 0, top)
+    pl = np.concatenate([y[None], c], 0).astype(np.uint16)
+    spr = rng.random(pl.shape) < 0.03
+    pl[spr] = rng.choice(np.array([0, 1, top // 2, top - 1, top], np.uint16), int(spr.sum()))
+    return np.ascontiguousarray(pl)

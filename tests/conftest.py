@@ -26,6 +26,12 @@ def golden_inverse():
 
 
 @pytest.fixture(scope="session")
+def golden_minv():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "matrix_inverse.npz"))
+
+
+@pytest.fixture(scope="session")
 def built_lib():
     """Build (or reuse) the in-tree C-ABI library; nvcc cross-compiles without a GPU."""
     from hdr2yuv_b200 import build

@@ -69,7 +69,13 @@ def main():
         inv[key + "/head"] = rgb[:2].copy()
         inv[key + "/invalid"] = np.array([invalid], np.int64)
     np.savez_compressed(os.path.join(HERE, "inverse.npz"), **inv)
-    for f in ("forward.npz", "inverse.npz"):
+    # matrix_inverse (convert.cpp:1320): outputs of the compiled reference; inputs are regenerated from the seed
+    mi = {}
+    for m, ibd, fr, obd in cases.MINV_CASES:
+        out, _ = O.matrix_inverse(cases.minv_input(ibd), m, ibd, fr, obd, backend="ref")
+        mi["m%d_i%d_f%d_o%d" % (m, ibd, fr, obd)] = out
+    np.savez_compressed(os.path.join(HERE, "matrix_inverse.npz"), **mi)
+    for f in ("forward.npz", "inverse.npz", "matrix_inverse.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

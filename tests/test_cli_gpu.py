@@ -100,3 +100,21 @@ def test_yuv2tiff_matches_oracle(cli, tmp_path, golden_inverse):
         got = np.fromfile(tmp_path / "o.raw", np.uint16).reshape(cases.IH, cases.IW, 3)
         assert np.array_equal(got, want)
     assert "Invalid Pixels:  %d" % invalid in text
+
+
+def test_yuv444_to_tiff_uses_matrix_inverse(cli, tmp_path):
+    # the reference's YCbCr 4:4:4 -> RGB tiff case of test.sh:70-80
+    pl = cases.minv_input(12)
+    pl.tofile(tmp_path / "in.yuv")
+    out = tmp_path / "out.tiff"
+    text = run([cli["hdr2yuv"], "--src_filename", str(tmp_path / "in.yuv"), "--dst_filename", str(out), "--src_pic_width", str(cases.MW),
+                "--src_pic_height", str(cases.MH), "--src_bit_depth", "12", "--dst_bit_depth", "16", "--src_chroma_format_idc", "3",
+                "--dst_chroma_format_idc", "3", "--src_matrix_coeffs", "1", "--dst_matrix_coeffs", "0",
+                "--src_transfer_characteristics", "1", "--dst_transfer_characteristics", "1", "--src_colour_primaries", "1",
+                "--dst_colour_primaries", "1", "--verbose_level", "1"])
+    tmp, invalid = O.matrix_inverse(pl, 1, 12, 0, 12, backend="port")
+    want = O.write_tiff_rows(tmp, 16, 12)
+    run([cli["h2y_iotool"], "read-tiff", str(out), str(tmp_path / "o.raw")])
+    got = np.fromfile(tmp_path / "o.raw", np.uint16).reshape(cases.MH, cases.MW, 3)
+    assert np.array_equal(got, want)
+    assert "invalid pixels %d" % invalid in text

@@ -107,3 +107,53 @@ def test_inverse_host_pipeline(ctx):
     ctx.inverse_host(p, src, out, n, invalid=inv)
     assert np.array_equal(out, dev)
     assert np.array_equal(inv.astype(np.int64), dinv.astype(np.int64))
+
+
+# ---- hdr2yuv's own 4:4:4 inverse: matrix_inverse + write_tiff (convert.cpp:1320-1867, tiff.cpp:559-652) ----
+@pytest.mark.parametrize("case", cases.MINV_CASES, ids=lambda c: "m%d_i%d_f%d_o%d" % c)
+def test_matrix_inverse_matches_oracle_and_golden(ctx, golden_minv, case):
+    m, ibd, fr, obd = case
+    pl = cases.minv_input(ibd)
+    want, invalid = O.matrix_inverse(pl, m, ibd, fr, obd, backend="port")
+    assert np.array_equal(want, golden_minv["m%d_i%d_f%d_o%d" % case])
+    h, w = pl.shape[1:]
+    d_in = torch.from_numpy(pl.view(np.int16).reshape(-1)).cuda()
+    d_out = torch.zeros(3 * h * w, dtype=torch.int16, device="cuda")
+    d_inv = torch.zeros(1, dtype=torch.int32, device="cuda")
+    in_pic = api.pic_desc(w, h, 3, 0, 0, m, ibd, fr)
+    out_pic = api.pic_desc(w, h, 3, 0, 0, 0, obd, fr)
+    n = h * w
+    ctx.matrix_inverse(out_pic, [d_out[i * n:(i + 1) * n] for i in range(3)], in_pic, [d_in[i * n:(i + 1) * n] for i in range(3)], invalid=d_inv)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(np.uint16).reshape(3, h, w)
+    assert np.array_equal(got, want)
+    assert int(d_inv.item()) == invalid
+    if obd >= ibd:
+        # write_tiff on top, and the fused host call that does both like main()
+        d_rgb = torch.zeros(3 * n, dtype=torch.int16, device="cuda")
+        tmp, _ = O.matrix_inverse(pl, m, ibd, fr, ibd, backend="port")          # tmp picture keeps the source depth
+        d_tmp = torch.from_numpy(tmp.view(np.int16).reshape(-1)).cuda()
+        ctx.write_tiff_rows(api.pic_desc(w, h, 3, 0, 0, 0, obd, fr), [d_tmp[i * n:(i + 1) * n] for i in range(3)], ibd, d_rgb)
+        torch.cuda.synchronize()
+        want_rgb = O.write_tiff_rows(tmp, obd, ibd)
+        assert np.array_equal(d_rgb.cpu().numpy().view(np.uint16).reshape(h, w, 3), want_rgb)
+        frames = np.ascontiguousarray(np.stack([pl, pl[:, ::-1].copy()], 0))
+        out = np.zeros((2, h, w, 3), np.uint16)
+        inv = np.zeros(2, np.uint32)
+        ctx.inverse444_host(in_pic, obd, frames, out, 2, invalid=inv)
+        assert np.array_equal(out[0], want_rgb)
+        t2, i2 = O.matrix_inverse(frames[1], m, ibd, fr, ibd, backend="port")
+        assert np.array_equal(out[1], O.write_tiff_rows(t2, obd, ibd)) and int(inv[1]) == i2 and int(inv[0]) == invalid
+
+
+def test_matrix_inverse_errors(ctx):
+    w, h = 16, 8
+    d = torch.zeros(3 * w * h, dtype=torch.int16, device="cuda")
+    n = w * h
+    pl = [d[i * n:(i + 1) * n] for i in range(3)]
+    with pytest.raises(cabi.H2YError) as e:              # "Can't determine color difference to use?" (convert.cpp:1735)
+        ctx.matrix_inverse(api.pic_desc(w, h, 3, 0, 0, 0, 12, 0), pl, api.pic_desc(w, h, 3, 0, 0, 0, 12, 0), pl)
+    assert e.value.status == cabi.ERR_MATRIX
+    with pytest.raises(cabi.H2YError) as e:              # write_tiff would shift by a negative count
+        ctx.write_tiff_rows(api.pic_desc(w, h, 3, 0, 0, 0, 10, 0), pl, 12, d)
+    assert e.value.status == cabi.ERR_BIT_DEPTH

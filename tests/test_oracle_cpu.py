@@ -112,3 +112,33 @@ def test_box_and_upsample_roundtrip_constant():
     assert np.all(O.subsample_box(p) == 777)
     up = O.upsample_420to444(np.full((12, 16), 500, np.uint16), 1, 0, 1023)
     assert np.all(up == 500)      # FIR taps sum to 256: DC is preserved exactly
+
+
+@pytest.mark.parametrize("case", cases.MINV_CASES, ids=lambda c: "m%d_i%d_f%d_o%d" % c)
+def test_port_matches_golden_matrix_inverse(golden_minv, case):
+    m, ibd, fr, obd = case
+    out, invalid = O.matrix_inverse(cases.minv_input(ibd), m, ibd, fr, obd, backend="port")
+    assert np.array_equal(out, golden_minv["m%d_i%d_f%d_o%d" % case])
+    assert invalid >= 0
+
+
+def test_matrix_inverse_family_quirks():
+    # convert.cpp:1387 compares matrix_coeffs with booleans: only 1 takes the 709 equations, 0 is the error,
+    # 10 (BT2020c) falls through to Y'DzDx exactly like 9 and 11
+    pl = cases.minv_input(12)
+    a, _ = O.matrix_inverse(pl, 10, 12, 0, 12)
+    b, _ = O.matrix_inverse(pl, 11, 12, 0, 12)
+    c, _ = O.matrix_inverse(pl, 1, 12, 0, 12)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    with pytest.raises(RuntimeError):
+        O.matrix_inverse(pl, 0, 12, 0, 12)
+    rgb = O.write_tiff_rows(a, 16, 12)
+    assert np.array_equal(rgb[..., 0], a[2] << 4) and np.array_equal(rgb[..., 1], a[0] << 4) and np.array_equal(rgb[..., 2], a[1] << 4)
+
+
+@needs_ref
+def test_matrix_inverse_port_vs_reference():
+    rng = np.random.default_rng(8)
+    for m in (1, 9, 11):
+        pl = rng.integers(0, 4096, (3, 33, 50), dtype=np.uint16)
+        assert np.array_equal(O.matrix_inverse(pl, m, 12, 0, 16, "port")[0], O.matrix_inverse(pl, m, 12, 0, 16, "ref")[0])
