@@ -565,6 +565,12 @@ h2y_status h2y_forward(h2y_ctx *c, const h2y_forward_params *p, const void *d_sr
             c->last_stream = st;
         }
         if (c->profile_on) cudaEventRecord(pev[1], st);
+        // TIFF route (integer rows, no transfer change, 4:2:0 FIR): the ring kernel with the reference's arithmetic
+        if (!k.convert_transfer && forward_u16_420_supported(*p, k) && !getenv("H2Y_FORCE_V1")) {
+            if ((s = launch_forward_u16_420(c, *p, k, src, src_stride, dst, dst_stride, nf, st)) != H2Y_OK) return s;
+            if (c->profile_on) { cudaEventRecord(pev[2], st); c->profile_count++; }
+            continue;
+        }
         // EXR route: the v2 kernel converts every "clean" frame, v1 then takes what v2 left (usually nothing)
         int skip_clean = 0;
         if (k.convert_transfer && forward_exr420_supported(*p, k, tmp.bit_depth) && !getenv("H2Y_FORCE_V1")) {

@@ -28,6 +28,7 @@
 //    infinite or NaN samples (never "clean") are left to the v1 kernel, which handles every case.
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "h2y_f32x2.cuh"
 #include "h2y_internal.h"
@@ -203,7 +204,43 @@ __device__ __forceinline__ u64 fir_h7_pair(u64 m5, u64 m3, u64 m1, u64 c, u64 p1
     return fadd2(pk(__int_as_float(a), __int_as_float(b)), pk(-MAGIC, -MAGIC));
 }
 
-template <int MK, int NCH>
+// ---- integer-source route (TIFF rows, tmp depth 16): reference arithmetic, no guard band --------------------
+// At 16-bit scale fp32 has too few fraction bits for the guard-band trick and the FIR's float rounding is
+// observable, so this route keeps the general kernel's FP64 colour difference
+// (reciprocal multiply with 14 guard bits, exact division when unsure) and the reference's float operation order
+// in both filters; it shares the ring / register-blocked vertical stage of k_forward_exr420.
+template <int MK>
+__device__ __forceinline__ void pixels8_u16(const Fwd2Args &a, const unsigned g[8], const unsigned b[8], const unsigned r[8],
+                                            uint4 &ypack, u64 chroma[8], unsigned &fallbacks)
+{
+    const PixK &k = a.k;
+    unsigned yv[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        unsigned gg = g[q], bb = b[q], rr = r[q];
+        if (k.clip_on_load) {                                   // read_tiff's clip (tiff.cpp:296-304)
+            gg = min(max(gg, k.loadLo), k.loadHi); bb = min(max(bb, k.loadLo), k.loadHi); rr = min(max(rr, k.loadLo), k.loadHi);
+        }
+        unsigned Y, Cb, Cr;
+        if (!px_matrix_fast<MK>((float)gg, (float)bb, (float)rr, k, Y, Cb, Cr)) {
+            px_matrix_exact<MK>((float)gg, (float)bb, (float)rr, k, Y, Cb, Cr);
+            fallbacks++;
+        }
+        yv[q] = out_clamp(Y, k.down_shift, k.loY, k.hiY);
+        chroma[q] = pk((float)Cb, (float)Cr);
+    }
+    ypack = make_uint4(yv[0] | (yv[1] << 16), yv[2] | (yv[3] << 16), yv[4] | (yv[5] << 16), yv[6] | (yv[7] << 16));
+}
+
+// horizontal 7-tap in the reference's operation order (convert.cpp:305-317), both planes of a {Cb,Cr} pair
+__device__ __forceinline__ u64 fir_h7_pair_ref(u64 m5, u64 m3, u64 m1, u64 c, u64 p1, u64 p3, u64 p5, float maxCVf)
+{
+    const unsigned x = fir_h7(plo(m5), plo(m3), plo(m1), plo(c), plo(p1), plo(p3), plo(p5), maxCVf);
+    const unsigned y = fir_h7(phi(m5), phi(m3), phi(m1), phi(c), phi(p1), phi(p3), phi(p5), maxCVf);
+    return pk((float)x, (float)y);
+}
+
+template <int MK, int NCH, int SRC = 0>     // SRC: 0 = half source through the LUT (fp32 guard band), 1 = integer source (reference arithmetic)
 __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -224,8 +261,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
         const int strip = item % a.nstrips;
         const int seg = (item / a.nstrips) % a.nsegs;
         const int frame = item / (a.nstrips * a.nsegs);
-        const FrameK &fk = a.framek[frame];
-        if (!fk.clean) continue;                        // v1 converts this frame (uniform per CTA)
+        if (SRC == 0 && !a.framek[frame].clean) continue;      // v1 converts this frame (uniform per CTA)
         const uint8_t *fsrc = a.src + (size_t)frame * a.src_stride;
         uint16_t *fY = reinterpret_cast<uint16_t *>(a.dst + (size_t)frame * a.dst_stride);
         uint16_t *fCb = fY + (size_t)w * h;
@@ -233,7 +269,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
 
         // ---- shared-memory LUT for the frame's code range ----
         __syncthreads();                                // previous item's readers (ring and LUT) are done
-        {
+        if (SRC == 0) {
+            const FrameK &fk = a.framek[frame];
             const unsigned lo = fk.code_lo, hi = fk.code_hi;
             if (fk.lut_slot[0] != cur_slot || lo < cur_lo || hi > cur_hi) {
                 const float *gl = a.luts + (size_t)fk.lut_slot[0] * 65536;
@@ -267,7 +304,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
                 unsigned g[8], b[8], r[8];
                 split_codes<NCH>(raw, g, b, r);
                 uint4 ypack;
-                pixels8<MK>(a, lut, g, b, r, ypack, ch, fallbacks);
+                if (SRC == 0) pixels8<MK>(a, lut, g, b, r, ypack, ch, fallbacks);
+                else pixels8_u16<MK>(a, g, b, r, ypack, ch, fallbacks);
                 if (lane_interior && row >= ys && row < ye) *reinterpret_cast<uint4 *>(fY + (size_t)row * w + xl) = ypack;
             }
             {   // prefetch the next step's row
@@ -284,10 +322,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
                 if (xl == 0) l3 = l5 = l7 = ch[0];                  // replicate s[0]     (convert.cpp:295-300)
                 if (xl + 8 >= w) n1 = n3 = ch[7];                   // replicate s[W-1]
                 if (lane_interior) {
-                    const u64 o0 = fir_h7_pair(l3, l5, l7, ch[0], ch[1], ch[3], ch[5], hi_bits);
-                    const u64 o1 = fir_h7_pair(l5, l7, ch[1], ch[2], ch[3], ch[5], ch[7], hi_bits);
-                    const u64 o2 = fir_h7_pair(l7, ch[1], ch[3], ch[4], ch[5], ch[7], n1, hi_bits);
-                    const u64 o3 = fir_h7_pair(ch[1], ch[3], ch[5], ch[6], ch[7], n1, n3, hi_bits);
+                    u64 o0, o1, o2, o3;
+                    if (SRC == 0) {
+                        o0 = fir_h7_pair(l3, l5, l7, ch[0], ch[1], ch[3], ch[5], hi_bits);
+                        o1 = fir_h7_pair(l5, l7, ch[1], ch[2], ch[3], ch[5], ch[7], hi_bits);
+                        o2 = fir_h7_pair(l7, ch[1], ch[3], ch[4], ch[5], ch[7], n1, hi_bits);
+                        o3 = fir_h7_pair(ch[1], ch[3], ch[5], ch[6], ch[7], n1, n3, hi_bits);
+                    } else {
+                        const float mf = (float)k.maxCV;
+                        o0 = fir_h7_pair_ref(l3, l5, l7, ch[0], ch[1], ch[3], ch[5], mf);
+                        o1 = fir_h7_pair_ref(l5, l7, ch[1], ch[2], ch[3], ch[5], ch[7], mf);
+                        o2 = fir_h7_pair_ref(l7, ch[1], ch[3], ch[4], ch[5], ch[7], n1, mf);
+                        o3 = fir_h7_pair_ref(ch[1], ch[3], ch[5], ch[6], ch[7], n1, n3, mf);
+                    }
                     float *rr = ring + (size_t)((row + RING_ROWS) & (RING_ROWS - 1)) * RING_PITCH + (lane - 1) * 4;
                     *reinterpret_cast<float4 *>(rr) = make_float4(plo(o0), phi(o0), plo(o1), phi(o1));
                     *reinterpret_cast<float4 *>(rr + RING_COLS) = make_float4(plo(o2), phi(o2), plo(o3), phi(o3));
@@ -312,7 +359,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
                     for (int o = 0; o < 4; o++) acc[o] = pk(0.5f, 0.5f);
                     const float *rp = ring + 2 * ring_pos(c);
                     const int rfirst = 2 * j0 - 5;
-                    if (rfirst >= 0 && rfirst + 17 <= h - 1 && ((rfirst & (RING_ROWS - 1)) + 17 < RING_ROWS)) {
+                    const bool linear = rfirst >= 0 && rfirst + 17 <= h - 1 && ((rfirst & (RING_ROWS - 1)) + 17 < RING_ROWS);
+                    if (SRC == 1) {
+                        // reference operation order per output (convert.cpp:365-374): the 18 rows are loaded once
+                        u64 rows[18];
+#pragma unroll
+                        for (int rr = 0; rr < 18; rr++) {
+                            int rowi = rfirst + rr;
+                            rowi = rowi < 0 ? 0 : (rowi > h - 1 ? h - 1 : rowi);
+                            const float2 v = *reinterpret_cast<const float2 *>(rp + (size_t)(rowi & (RING_ROWS - 1)) * RING_PITCH);
+                            rows[rr] = pk(v.x, v.y);
+                        }
+                        const float mf = (float)k.maxCV;
+#pragma unroll
+                        for (int o = 0; o < 4; o++) {
+                            float rx[12], ry[12];
+#pragma unroll
+                            for (int t = 0; t < 12; t++) { rx[t] = plo(rows[2 * o + t]); ry[t] = phi(rows[2 * o + t]); }
+                            // keep the results in the magic-number form the common epilogue expects
+                            acc[o] = pk(__int_as_float(MAGIC_BITS + (int)fir_v12(rx, mf)), __int_as_float(MAGIC_BITS + (int)fir_v12(ry, mf)));
+                        }
+                    } else if (linear) {
                         // interior, no ring wrap: 18 loads at compile-time offsets
                         const float *base = rp + (size_t)(rfirst & (RING_ROWS - 1)) * RING_PITCH;
 #pragma unroll
@@ -345,7 +412,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
                         if (j >= (ys >> 1) && j < (ye >> 1)) {
                             // clamp [0,maxCV] + truncation + write_yuv's shift and range clamp collapse to one
                             // integer clamp of the floored value (all bounds are integers, the map is monotone)
-                            const u64 fl = fadd2_rm(acc[o], pk(MAGIC, MAGIC));
+                            const u64 fl = SRC == 1 ? acc[o] : fadd2_rm(acc[o], pk(MAGIC, MAGIC));
                             const size_t off = (size_t)j * wh + col;
                             fCb[off] = (uint16_t)clamp3(ilo(fl) >> shift, clo, chi);
                             fCr[off] = (uint16_t)clamp3(ihi(fl) >> shift, clo, chi);
@@ -530,6 +597,59 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
+
+bool forward_u16_420_supported(const h2y_forward_params &p, const PixK &k)
+{
+    if (p.src.layout != H2Y_LAYOUT_RGB16 && p.src.layout != H2Y_LAYOUT_RGBA16) return false;
+    if (k.convert_transfer) return false;
+    if (p.dst.chroma_format_idc != H2Y_CHROMA_420 || p.chroma_resampler_type == 0) return false;
+    if (k.mat_kind != MK_YCBCR && k.mat_kind != MK_YDZDX) return false;
+    const int w = p.src.width, h = p.src.height;
+    return w >= 8 && (w & 7) == 0 && h >= 2 && (h & 1) == 0;
+}
+
+static void ring_items(Fwd2Args &a, int nframes, int grid_max)
+{
+    a.strip_w = 240;
+    a.nstrips = (a.w + a.strip_w - 1) / a.strip_w;
+    long want_items = 6L * grid_max;
+    int nsegs = (int)((want_items + (long)nframes * a.nstrips - 1) / ((long)nframes * a.nstrips));
+    int max_segs = a.h / 96 > 0 ? a.h / 96 : 1;
+    if (nsegs > max_segs) nsegs = max_segs;
+    if (nsegs < 1) nsegs = 1;
+    int seg_rows = (a.h + nsegs - 1) / nsegs;
+    seg_rows = (seg_rows + 15) / 16 * 16;
+    a.seg_rows = seg_rows;
+    a.nsegs = (a.h + seg_rows - 1) / seg_rows;
+    a.nitems = nframes * a.nsegs * a.nstrips;
+}
+
+h2y_status launch_forward_u16_420(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, const void *d_src,
+                                  size_t src_stride, void *d_dst, size_t dst_stride, int nframes, cudaStream_t st)
+{
+    Fwd2Args a;
+    memset(&a, 0, sizeof(a));
+    a.src = (const uint8_t *)d_src; a.src_stride = src_stride;
+    a.dst = (uint8_t *)d_dst; a.dst_stride = dst_stride;
+    a.w = p.src.width; a.h = p.src.height; a.nframes = nframes;
+    a.k = k;
+    ring_items(a, nframes, c->sm_count);
+    const size_t smem = (size_t)RING_ROWS * RING_PITCH * sizeof(float);
+    const int grid = a.nitems < c->sm_count ? a.nitems : c->sm_count;
+    const int nch = layout_channels(p.src.layout);
+#define LU(MKV, NC)                                                                                                        \
+    do {                                                                                                                   \
+        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420<MKV, NC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_forward_exr420<MKV, NC, 1><<<grid, THREADS, smem, st>>>(a);                                                     \
+    } while (0)
+    if (k.mat_kind == MK_YCBCR) { if (nch == 3) LU(MK_YCBCR, 3); else LU(MK_YCBCR, 4); }
+    else { if (nch == 3) LU(MK_YDZDX, 3); else LU(MK_YDZDX, 4); }
+#undef LU
+    c->launches++;
+    H2Y_CUDA(c, cudaGetLastError());
+    return H2Y_OK;
+}
+
 
 bool forward_exr420_supported(const h2y_forward_params &p, const PixK &k, int tmp_bit_depth)
 {

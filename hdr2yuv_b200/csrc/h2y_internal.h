@@ -96,6 +96,9 @@ h2y_status launch_write_tiff_rows(h2y_ctx_impl *c, long npix, const uint16_t *g,
 
 // ---- launchers (h2y_forward.cu / h2y_inverse.cu) ---------------------------------------------
 bool fused_forward_supported(const h2y_forward_params &p);
+bool forward_u16_420_supported(const h2y_forward_params &p, const PixK &k);
+h2y_status launch_forward_u16_420(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, const void *d_src,
+                                  size_t src_stride, void *d_dst, size_t dst_stride, int nframes, cudaStream_t st);
 bool forward_exr420_supported(const h2y_forward_params &p, const PixK &k, int tmp_bit_depth);
 h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, int tmp_bit_depth,
                                  const void *d_src, size_t src_stride, void *d_dst, size_t dst_stride, int nframes,
