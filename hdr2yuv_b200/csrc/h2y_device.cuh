@@ -239,6 +239,36 @@ __device__ __forceinline__ bool px_matrix_fast(float G, float B, float R, const 
     return ok;
 }
 
+// Integer-source variant of px_matrix_fast (TIFF rows): identical arithmetic, but the integer codes become doubles /
+// floats through magic-number adds instead of I2F + F2F conversions (16-32 lanes/clk/SM on B200).  u2d/u2f are exact.
+__device__ __forceinline__ double u2d(unsigned v) { return __dadd_rn(__hiloint2double(0x43300000, (int)v), -4503599627370496.0); }
+__device__ __forceinline__ float u2f(unsigned v) { return __fadd_rn(__uint_as_float(0x4B000000u | v), -8388608.0f); }   // v < 2^23
+
+template <int MK>
+__device__ __forceinline__ bool px_matrix_fast_u16(unsigned g, unsigned b, unsigned r, const PixK &k, unsigned &Y,
+                                                   unsigned &Cb, unsigned &Cr)
+{
+    const double MAGICD = 412316860416.0 + 0.5;   // 1.5 * 2^38 + the reference's +0.5
+    bool ok = true;
+    int cb, cr;
+    if (MK == MK_YCBCR) {
+        const double s = __dadd_rn(__dadd_rn(__dmul_rn(k.wr, u2d(r)), __dmul_rn(k.wg, u2d(g))), __dmul_rn(k.wb, u2d(b)));
+        const float tmpF = __double2float_rn(__dadd_rn(s, 0.5));
+        // tmpF >= 0.5 here: truncation = floor, taken by a round-toward-zero add of 2^23
+        Y = min(__float_as_uint(__fadd_rz(tmpF, 8388608.0f)) & 0x7FFFFFu, k.maxCV);
+        ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(u2f(b), tmpF), k.rdb, MAGICD), cb);
+        ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(u2f(r), tmpF), k.rdr, MAGICD), cr);
+    } else {   // MK_YDZDX on integers: (int)(-G/2.0 + B/2.0 + 0.5) == (B - G + 1) / 2 with C's truncating division
+        Y = min(g, k.maxCV);
+        const int tb = (int)b - (int)g + 1, tr = (int)r - (int)g + 1;
+        cb = (tb - (tb >> 31)) >> 1;
+        cr = (tr - (tr >> 31)) >> 1;
+    }
+    Cb = min((unsigned)(cb + k.half_m1), k.maxCV);
+    Cr = min((unsigned)(cr + k.half_m1), k.maxCV);
+    return ok;
+}
+
 // ---- write_yuv's shift + range clamp (tiff.cpp:457-550) --------------------------------------
 __device__ __forceinline__ unsigned out_clamp(unsigned v, int shift, unsigned lo, unsigned hi)
 {
@@ -263,6 +293,21 @@ __device__ __forceinline__ unsigned fir_h7(float m5, float m3, float m1, float c
     return (unsigned)__float2int_rz(t);
 }
 
+// same filter, result kept as a float integer: the (unsigned short) truncation of the clamped value is a
+// round-toward-zero add of 2^23 (t >= 0 after the clamp), so no F2I / I2F pair is needed
+__device__ __forceinline__ float fir_h7_f(float m5, float m3, float m1, float c, float p1, float p3, float p5, float maxCV)
+{
+    const float k21 = 21.0f / 512.0f, k52 = 52.0f / 512.0f, k159 = 159.0f / 512.0f, k256 = 256.0f / 512.0f;
+    float t = __fmul_rn(k21, __fadd_rn(m5, p5));
+    t = __fsub_rn(t, __fmul_rn(k52, __fadd_rn(m3, p3)));
+    t = __fadd_rn(t, __fmul_rn(k159, __fadd_rn(m1, p1)));
+    t = __fadd_rn(t, __fmul_rn(k256, c));
+    t = __fadd_rn(t, 0.5f);
+    t = fminf(t, maxCV);
+    t = fmaxf(t, 0.0f);
+    return __fadd_rn(__fadd_rz(t, 8388608.0f), -8388608.0f);
+}
+
 // 12-tap vertical, half-phase: r[0..11] are rows y-5 .. y+6
 __device__ __forceinline__ unsigned fir_v12(const float r[12], float maxCV)
 {
@@ -278,6 +323,23 @@ __device__ __forceinline__ unsigned fir_v12(const float r[12], float maxCV)
     t = fminf(t, maxCV);
     t = fmaxf(t, 0.0f);
     return (unsigned)__float2int_rz(t);
+}
+
+// same, result as the bit pattern of 1.5*2^23 + trunc(t) (0x4B400000 + value): the form the packed kernels' epilogue uses
+__device__ __forceinline__ int fir_v12_magic(const float r[12], float maxCV)
+{
+    const float k228 = 228.0f / 512.0f, k70 = 70.0f / 512.0f, k37 = 37.0f / 512.0f, k21 = 21.0f / 512.0f,
+                k11 = 11.0f / 512.0f, k5 = 5.0f / 512.0f;
+    float t = __fmul_rn(k228, __fadd_rn(r[5], r[6]));
+    t = __fadd_rn(t, __fmul_rn(k70, __fadd_rn(r[4], r[7])));
+    t = __fsub_rn(t, __fmul_rn(k37, __fadd_rn(r[3], r[8])));
+    t = __fsub_rn(t, __fmul_rn(k21, __fadd_rn(r[2], r[9])));
+    t = __fadd_rn(t, __fmul_rn(k11, __fadd_rn(r[1], r[10])));
+    t = __fadd_rn(t, __fmul_rn(k5, __fadd_rn(r[0], r[11])));
+    t = __fadd_rn(t, 0.5f);
+    t = fminf(t, maxCV);
+    t = fmaxf(t, 0.0f);
+    return __float_as_int(__fadd_rz(t, 12582912.0f));
 }
 
 }   // namespace h2y

@@ -217,17 +217,14 @@ __device__ __forceinline__ void pixels8_u16(const Fwd2Args &a, const unsigned g[
     unsigned yv[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) {
-        unsigned gg = g[q], bb = b[q], rr = r[q];
-        if (k.clip_on_load) {                                   // read_tiff's clip (tiff.cpp:296-304)
-            gg = min(max(gg, k.loadLo), k.loadHi); bb = min(max(bb, k.loadLo), k.loadHi); rr = min(max(rr, k.loadLo), k.loadHi);
-        }
+        const unsigned gg = g[q], bb = b[q], rr = r[q];         // already clipped on load (packed, in the caller)
         unsigned Y, Cb, Cr;
-        if (!px_matrix_fast<MK>((float)gg, (float)bb, (float)rr, k, Y, Cb, Cr)) {
+        if (!px_matrix_fast_u16<MK>(gg, bb, rr, k, Y, Cb, Cr)) {
             px_matrix_exact<MK>((float)gg, (float)bb, (float)rr, k, Y, Cb, Cr);
             fallbacks++;
         }
         yv[q] = out_clamp(Y, k.down_shift, k.loY, k.hiY);
-        chroma[q] = pk((float)Cb, (float)Cr);
+        chroma[q] = pk(u2f(Cb), u2f(Cr));
     }
     ypack = make_uint4(yv[0] | (yv[1] << 16), yv[2] | (yv[3] << 16), yv[4] | (yv[5] << 16), yv[6] | (yv[7] << 16));
 }
@@ -235,9 +232,8 @@ __device__ __forceinline__ void pixels8_u16(const Fwd2Args &a, const unsigned g[
 // horizontal 7-tap in the reference's operation order (convert.cpp:305-317), both planes of a {Cb,Cr} pair
 __device__ __forceinline__ u64 fir_h7_pair_ref(u64 m5, u64 m3, u64 m1, u64 c, u64 p1, u64 p3, u64 p5, float maxCVf)
 {
-    const unsigned x = fir_h7(plo(m5), plo(m3), plo(m1), plo(c), plo(p1), plo(p3), plo(p5), maxCVf);
-    const unsigned y = fir_h7(phi(m5), phi(m3), phi(m1), phi(c), phi(p1), phi(p3), phi(p5), maxCVf);
-    return pk((float)x, (float)y);
+    return pk(fir_h7_f(plo(m5), plo(m3), plo(m1), plo(c), plo(p1), plo(p3), plo(p5), maxCVf),
+              fir_h7_f(phi(m5), phi(m3), phi(m1), phi(c), phi(p1), phi(p3), phi(p5), maxCVf));
 }
 
 template <int MK, int NCH, int SRC = 0>     // SRC: 0 = half source through the LUT (fp32 guard band), 1 = integer source (reference arithmetic)
@@ -302,6 +298,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
             for (int q = 0; q < 8; q++) ch[q] = 0ull;
             if (row_ok && lane_in_pic) {
                 unsigned g[8], b[8], r[8];
+                if (SRC == 1 && k.clip_on_load) {               // read_tiff's clip (tiff.cpp:296-304), two samples per instruction
+                    const unsigned lo2 = k.loadLo * 0x10001u, hi2 = k.loadHi * 0x10001u;
+#pragma unroll
+                    for (int i = 0; i < NCH; i++) {
+                        unsigned *wv = reinterpret_cast<unsigned *>(&raw.v[i]);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            asm("max.u16x2 %0, %0, %1;" : "+r"(wv[j]) : "r"(lo2));
+                            asm("min.u16x2 %0, %0, %1;" : "+r"(wv[j]) : "r"(hi2));
+                        }
+                    }
+                }
                 split_codes<NCH>(raw, g, b, r);
                 uint4 ypack;
                 if (SRC == 0) pixels8<MK>(a, lut, g, b, r, ypack, ch, fallbacks);
@@ -377,7 +385,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
 #pragma unroll
                             for (int t = 0; t < 12; t++) { rx[t] = plo(rows[2 * o + t]); ry[t] = phi(rows[2 * o + t]); }
                             // keep the results in the magic-number form the common epilogue expects
-                            acc[o] = pk(__int_as_float(MAGIC_BITS + (int)fir_v12(rx, mf)), __int_as_float(MAGIC_BITS + (int)fir_v12(ry, mf)));
+                            acc[o] = pk(__int_as_float(fir_v12_magic(rx, mf)), __int_as_float(fir_v12_magic(ry, mf)));
                         }
                     } else if (linear) {
                         // interior, no ring wrap: 18 loads at compile-time offsets
