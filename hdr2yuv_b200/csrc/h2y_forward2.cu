@@ -604,12 +604,57 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
     if (a.fallback_count && fallbacks) atomicAdd(a.fallback_count, (unsigned long long)fallbacks);
 }
 
+// ---- integer source, 4:4:4 output: a pure streaming map (no filter), one 8-pixel group per thread step ---------
+template <int MK, int NCH>
+__global__ void __launch_bounds__(256) k_forward_u16_444(const Fwd2Args a, long groups_per_frame)
+{
+    const PixK &k = a.k;
+    const long total = groups_per_frame * a.nframes;
+    const size_t plane = (size_t)a.w * a.h;
+    for (long gi = (long)blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += (long)gridDim.x * blockDim.x) {
+        const int frame = (int)(gi / groups_per_frame);
+        const long px = (gi - (long)frame * groups_per_frame) * 8;
+        RawPx<NCH> raw;
+        load_px8<NCH>(raw, a.src + (size_t)frame * a.src_stride + (size_t)px * (2 * NCH), 0, 0, 0);
+        if (k.clip_on_load) {                                   // read_tiff's clip (tiff.cpp:296-304)
+            const unsigned lo2 = k.loadLo * 0x10001u, hi2 = k.loadHi * 0x10001u;
+#pragma unroll
+            for (int i = 0; i < NCH; i++) {
+                unsigned *wv = reinterpret_cast<unsigned *>(&raw.v[i]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    asm("max.u16x2 %0, %0, %1;" : "+r"(wv[j]) : "r"(lo2));
+                    asm("min.u16x2 %0, %0, %1;" : "+r"(wv[j]) : "r"(hi2));
+                }
+            }
+        }
+        unsigned g[8], b[8], r[8], Y[8], Cb[8], Cr[8];
+        split_codes<NCH>(raw, g, b, r);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (!px_matrix_fast_u16<MK>(g[q], b[q], r[q], k, Y[q], Cb[q], Cr[q]))
+                px_matrix_exact<MK>((float)g[q], (float)b[q], (float)r[q], k, Y[q], Cb[q], Cr[q]);
+            Y[q] = out_clamp(Y[q], k.down_shift, k.loY, k.hiY);
+            Cb[q] = out_clamp(Cb[q], k.down_shift, k.loC, k.hiC);
+            Cr[q] = out_clamp(Cr[q], k.down_shift, k.loC, k.hiC);
+        }
+        uint16_t *fo = reinterpret_cast<uint16_t *>(a.dst + (size_t)frame * a.dst_stride) + px;
+        *reinterpret_cast<uint4 *>(fo) = make_uint4(Y[0] | (Y[1] << 16), Y[2] | (Y[3] << 16), Y[4] | (Y[5] << 16), Y[6] | (Y[7] << 16));
+        *reinterpret_cast<uint4 *>(fo + plane) = make_uint4(Cb[0] | (Cb[1] << 16), Cb[2] | (Cb[3] << 16), Cb[4] | (Cb[5] << 16), Cb[6] | (Cb[7] << 16));
+        *reinterpret_cast<uint4 *>(fo + 2 * plane) = make_uint4(Cr[0] | (Cr[1] << 16), Cr[2] | (Cr[3] << 16), Cr[4] | (Cr[5] << 16), Cr[6] | (Cr[7] << 16));
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------
 
 bool forward_u16_420_supported(const h2y_forward_params &p, const PixK &k)
 {
     if (p.src.layout != H2Y_LAYOUT_RGB16 && p.src.layout != H2Y_LAYOUT_RGBA16) return false;
     if (k.convert_transfer) return false;
+    if (p.dst.chroma_format_idc == H2Y_CHROMA_444) {                       // streaming map, any height
+        if (k.mat_kind != MK_YCBCR && k.mat_kind != MK_YDZDX) return false;
+        return ((long)p.src.width * p.src.height) % 8 == 0;
+    }
     if (p.dst.chroma_format_idc != H2Y_CHROMA_420 || p.chroma_resampler_type == 0) return false;
     if (k.mat_kind != MK_YCBCR && k.mat_kind != MK_YDZDX) return false;
     const int w = p.src.width, h = p.src.height;
@@ -641,6 +686,22 @@ h2y_status launch_forward_u16_420(h2y_ctx_impl *c, const h2y_forward_params &p, 
     a.dst = (uint8_t *)d_dst; a.dst_stride = dst_stride;
     a.w = p.src.width; a.h = p.src.height; a.nframes = nframes;
     a.k = k;
+    if (p.dst.chroma_format_idc == H2Y_CHROMA_444) {
+        const long groups = (long)a.w * a.h / 8;
+        long want = (groups * nframes + 255) / 256;
+        const int blocks = (int)(want < 16L * c->sm_count ? want : 16L * c->sm_count);
+        const int nch4 = layout_channels(p.src.layout);
+        if (k.mat_kind == MK_YCBCR) {
+            if (nch4 == 3) k_forward_u16_444<MK_YCBCR, 3><<<blocks, 256, 0, st>>>(a, groups);
+            else k_forward_u16_444<MK_YCBCR, 4><<<blocks, 256, 0, st>>>(a, groups);
+        } else {
+            if (nch4 == 3) k_forward_u16_444<MK_YDZDX, 3><<<blocks, 256, 0, st>>>(a, groups);
+            else k_forward_u16_444<MK_YDZDX, 4><<<blocks, 256, 0, st>>>(a, groups);
+        }
+        c->launches++;
+        H2Y_CUDA(c, cudaGetLastError());
+        return H2Y_OK;
+    }
     ring_items(a, nframes, c->sm_count);
     const size_t smem = (size_t)RING_ROWS * RING_PITCH * sizeof(float);
     const int grid = a.nitems < c->sm_count ? a.nitems : c->sm_count;
