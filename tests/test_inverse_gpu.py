@@ -27,8 +27,10 @@ def gpu_inverse(ctx, yuvs, w, h, bd, m, fir, fr, al):
     return rgb, d_inv.cpu().numpy()
 
 
+@pytest.mark.parametrize("kernel", ["tile", "rows"])
 @pytest.mark.parametrize("case", cases.INVERSE_CASES, ids=lambda c: "b%d_m%d_fir%d_fr%d_a%d" % c)
-def test_inverse_matches_golden(ctx, golden_inverse, case):
+def test_inverse_matches_golden(ctx, golden_inverse, case, kernel, monkeypatch):
+    monkeypatch.setenv("H2Y_INVERSE_KERNEL", kernel)          # both kernels behind h2y_inverse
     bd, m, fir, fr, al = case
     yuv = cases.widen_yuv(golden_inverse[cases.inverse_input_key(m)], bd)
     rgb, inv = gpu_inverse(ctx, [yuv], cases.IW, cases.IH, bd, m, fir, fr, al)
@@ -44,8 +46,10 @@ def _yuv_for(w, h, seed, bd, matrix_fwd):
     return O.forward(O.load_half(px), dict(bit_depth=32, full_range=1, transfer=8, primaries=1, matrix=0), dst)
 
 
+@pytest.mark.parametrize("kernel", ["tile", "rows"])
 @pytest.mark.parametrize("w,h", [(8, 2), (128, 16), (136, 34), (1000, 250), (1920, 1080), (3840, 2160)])
-def test_inverse_sizes_vs_oracle(ctx, w, h):
+def test_inverse_sizes_vs_oracle(ctx, w, h, kernel, monkeypatch):
+    monkeypatch.setenv("H2Y_INVERSE_KERNEL", kernel)
     big = w * h > 1 << 20
     for bd, m, m_fwd in ((10, O.INV_2020, 9), (12, O.INV_YDZDX, 11), (10, O.INV_709, 1), (12, O.INV_Y100, 13)):
         if big and m not in (O.INV_2020, O.INV_YDZDX):
@@ -157,3 +161,15 @@ def test_matrix_inverse_errors(ctx):
     with pytest.raises(cabi.H2YError) as e:              # write_tiff would shift by a negative count
         ctx.write_tiff_rows(api.pic_desc(w, h, 3, 0, 0, 0, 10, 0), pl, 12, d)
     assert e.value.status == cabi.ERR_BIT_DEPTH
+
+
+def test_empty_batches_are_no_ops(ctx):
+    d = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    p = cabi.InverseParams(64, 16, 10, O.INV_2020, 1, 0, 0)
+    ctx.inverse(p, d, d, 0)
+    fp = api.forward_params(64, 16, cabi.LAYOUT_RGB16, dict(bit_depth=16, full_range=0, transfer=16, primaries=10, matrix=0),
+                            dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1))
+    ctx.forward(fp, d, d, 0)
+    ctx.forward_host(fp, np.zeros(1, np.uint8), np.zeros(1, np.uint8), 0)
+    ctx.inverse_host(p, np.zeros(1, np.uint8), np.zeros(1, np.uint8), 0)
+    torch.cuda.synchronize()
