@@ -224,8 +224,22 @@ constexpr int RTHREADS = 512, RWARPS = RTHREADS / 32, RSLOTS = 8;
 constexpr float TWO23 = 8388608.0f;
 }
 
+// Per-launch constants: CFG 0 from the launch arguments, CFG 10 = `B10 2020`, video range (yuv2tiff.cpp:137-147,
+// 178-186, 404-413) with every constant an immediate (no constant-bank reloads in the pixel loop).
+template <int CFG> struct IC {
+    static constexpr float G = 1.0f / 2048.0f;
+#define ICF(name, rt, ct) __device__ __forceinline__ static float name(const Inv2Args &A) { return CFG ? (ct) : (rt); }
+#define ICU(name, rt, ct) __device__ __forceinline__ static unsigned name(const Inv2Args &A) { return CFG ? (unsigned)(ct) : (unsigned)(rt); }
+    ICF(hm, A.hm, 511.5f) ICF(kb, A.kb, (float)1.8814) ICF(kr, A.kr, (float)1.4746)
+    ICF(nwb, A.nwb, -(float)0.0593) ICF(nwr, A.nwr, -(float)0.2627) ICF(rwg, A.rwg, (float)(1.0 / 0.6780)) ICF(guard, A.guard, G)
+    ICU(full_range, A.k.full_range, 0) ICU(minVR, A.k.minVR, 64) ICU(maxVR, A.k.maxVR, 940) ICU(minVRC, A.k.minVRC, 64)
+    ICU(maxVRC, A.k.maxVRC, 960) ICU(maxCV, A.k.maxCV, 1023) ICU(Full, A.k.Full, 1024) ICU(SR, A.k.SR, 6)
+#undef ICF
+#undef ICU
+};
+
 // mode: 0 = every pixel through inv_pixel (Y100 / Y500), 1 = guarded fp32 (709 / 2020), 2 = integer Y'DzDx
-template <int MODE, bool FIR, bool ALPHA>
+template <int MODE, bool FIR, bool ALPHA, int CFG = 0>
 __global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -234,13 +248,14 @@ __global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
     float4 *ring = reinterpret_cast<float4 *>(smem_raw) + (size_t)warp * RSLOTS * 2 * 32;      // [slot][half][lane]
     const int w = k.w, h = k.h, wh = w >> 1, hh = h >> 1;
     constexpr int nch = ALPHA ? 4 : 3;
-    const int hi_bits = MAGIC_BITS + (int)k.maxCV;
+    typedef IC<CFG> C;
+    const int hi_bits = MAGIC_BITS + (int)C::maxCV(A);
     const int wk = warp / A.wps, sfirst = warp - wk * A.wps;
     if (wk >= A.sub) return;
     const long K = (long)gridDim.x * A.sub, kid = (long)blockIdx.x * A.sub + wk;
     const long g0 = (kid * A.total_crows) / K, g1 = ((kid + 1) * A.total_crows) / K;
     if (g1 <= g0) return;
-    const float G = A.guard;
+    const float G = C::guard(A);
     int invalid_frame = -1;
     unsigned invalid = 0;
 
@@ -267,8 +282,8 @@ __global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
             };
             auto stash = [&](int r, uint2 vb, uint2 vr) {
                 unsigned wb[2] = {vb.x, vb.y}, wr[2] = {vr.x, vr.y};
-                if (!k.full_range) {                                              // read clamp, yuv2tiff.cpp:297-320
-                    const unsigned lo2 = k.minVRC * 0x10001u, hi2 = k.maxVRC * 0x10001u;
+                if (!C::full_range(A)) {                                          // read clamp, yuv2tiff.cpp:297-320
+                    const unsigned lo2 = C::minVRC(A) * 0x10001u, hi2 = C::maxVRC(A) * 0x10001u;
 #pragma unroll
                     for (int i = 0; i < 2; i++) {
                         asm("max.u16x2 %0, %0, %1;" : "+r"(wb[i]) : "r"(lo2)); asm("min.u16x2 %0, %0, %1;" : "+r"(wb[i]) : "r"(hi2));
@@ -377,26 +392,26 @@ __global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
                         unsigned Y = (q & 1) ? (yw[q >> 1] >> 16) : (yw[q >> 1] & 0xffffu);
-                        if (!k.full_range) Y = min(max(Y, k.minVR), k.maxVR);                 // yuv2tiff.cpp:283-294
+                        if (!C::full_range(A)) Y = min(max(Y, C::minVR(A)), C::maxVR(A));     // yuv2tiff.cpp:283-294
                         const float cbf = plo(cpx[q]), crf = phi(cpx[q]);
                         bool slow = MODE == 0;
                         int Rp = 0, Gp = 0, Bp = 0;
                         if (MODE == 1) {
                             const float Yf = __uint_as_float(0x4B000000u | Y) - TWO23;
                             const float Yg = Yf - G;
-                            const u64 tlo = ffma2(fadd2(cpx[q], pk(-A.hm, -A.hm)), pk(A.kb, A.kr), pk(Yg, Yg));
+                            const u64 tlo = ffma2(fadd2(cpx[q], pk(-C::hm(A), -C::hm(A))), pk(C::kb(A), C::kr(A)), pk(Yg, Yg));
                             int B1, R1, B2, R2;
                             unpk(fadd2_rm(tlo, pk(MAGIC, MAGIC)), B1, R1);
                             unpk(fadd2_rm(fadd2(tlo, pk(2.0f * G, 2.0f * G)), pk(MAGIC, MAGIC)), B2, R2);
                             const int Bc = min(B1, hi_bits), Rc = min(R1, hi_bits);          // t > Full-1 -> Full-1 (406-412)
                             const u64 brf = fadd2(pk(__int_as_float(Bc), __int_as_float(Rc)), pk(-MAGIC, -MAGIC));
-                            const float g = __fmaf_rn(A.nwr, phi(brf), __fmaf_rn(A.nwb, plo(brf), Yf));
-                            const float glo = __fmaf_rn(g, A.rwg, 0.5f - G);
+                            const float g = __fmaf_rn(C::nwr(A), phi(brf), __fmaf_rn(C::nwb(A), plo(brf), Yf));
+                            const float glo = __fmaf_rn(g, C::rwg(A), 0.5f - G);
                             const int G1 = __float_as_int(__fadd_rd(glo, MAGIC)), G2 = __float_as_int(__fadd_rd(glo + 2.0f * G, MAGIC));
                             slow = (((B1 ^ B2) | (R1 ^ R2) | (G1 ^ G2)) != 0) | (min(min(B1, R1), G1) < MAGIC_BITS);
                             Bp = Bc - MAGIC_BITS; Rp = Rc - MAGIC_BITS; Gp = min(G1, hi_bits) - MAGIC_BITS;
                         } else if (MODE == 2) {                                              // yuv2tiff.cpp:401-402
-                            const int off = (int)Y - (int)(k.Full - 1);
+                            const int off = (int)Y - (int)(C::Full(A) - 1);
                             Rp = 2 * (int)crf + off; Bp = 2 * (int)cbf + off; Gp = (int)Y;
                             slow = (Rp | Bp) < 0;
                         }
@@ -404,11 +419,11 @@ __global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
                         if (slow) {
                             invalid += (unsigned)inv_pixel<MODE == 1 ? H2Y_INV_2020 : (MODE == 2 ? H2Y_INV_YDzDx : -1)>(k, (int)Y, cbf, crf, R, Gv, B);
                         } else {
-                            if (!k.full_range) {                                              // yuv2tiff.cpp:515-524
-                                Rp = clamp3(Rp, (int)k.minVR, (int)k.maxVR); Gp = clamp3(Gp, (int)k.minVR, (int)k.maxVR);
-                                Bp = clamp3(Bp, (int)k.minVR, (int)k.maxVR);
+                            if (!C::full_range(A)) {                                          // yuv2tiff.cpp:515-524
+                                Rp = clamp3(Rp, (int)C::minVR(A), (int)C::maxVR(A)); Gp = clamp3(Gp, (int)C::minVR(A), (int)C::maxVR(A));
+                                Bp = clamp3(Bp, (int)C::minVR(A), (int)C::maxVR(A));
                             }
-                            R = ((unsigned)Rp << k.SR) & 0xffffu; Gv = ((unsigned)Gp << k.SR) & 0xffffu; B = ((unsigned)Bp << k.SR) & 0xffffu;
+                            R = ((unsigned)Rp << C::SR(A)) & 0xffffu; Gv = ((unsigned)Gp << C::SR(A)) & 0xffffu; B = ((unsigned)Bp << C::SR(A)) & 0xffffu;
                         }
                         smp[q][0] = R; smp[q][1] = Gv; smp[q][2] = B;
                     }
@@ -490,7 +505,12 @@ h2y_status launch_inverse(h2y_ctx_impl *c, const InvK &k, const void *d_yuv, siz
         else if (k.alpha) LR(M, false, true);                                                                              \
         else LR(M, false, false);                                                                                          \
     } while (0)
-            if (mode == 1) LRM(1); else if (mode == 2) LRM(2); else LRM(0);
+            const bool cfg10 = k.matrix == H2Y_INV_2020 && k.bit_depth == 10 && !k.full_range && k.fir && !k.alpha &&
+                               !getenv("H2Y_NO_SPECIALISED");
+            if (cfg10) {
+                H2Y_CUDA(c, cudaFuncSetAttribute(k_inverse_rows<1, true, false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_inverse_rows<1, true, false, 10><<<grid, RTHREADS, smem, st>>>(A);
+            } else if (mode == 1) LRM(1); else if (mode == 2) LRM(2); else LRM(0);
 #undef LRM
 #undef LR
             c->launches++;
