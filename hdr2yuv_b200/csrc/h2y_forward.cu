@@ -409,8 +409,6 @@ bool fused_forward_supported(const h2y_forward_params &p)
 template <int MK, int CM>
 static h2y_status launch_one(h2y_ctx_impl *c, const FwdArgs &a, int grid, size_t smem, cudaStream_t st)
 {
-    static bool attr_done[8] = {false};
-    (void)attr_done;
     H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_fused<MK, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_forward_fused<MK, CM><<<grid, THREADS, smem, st>>>(a);
     c->launches++;

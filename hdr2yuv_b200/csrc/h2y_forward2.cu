@@ -1,31 +1,27 @@
-// h2y_forward2.cu -- K1 v2: the fused forward kernel for the EXR route (half-float source, transfer
-// change through the per-frame LUT, 4:2:0 FIR, tmp depth <= 12), rebuilt around what the ncu
-// profile of v1 showed: the path is instruction-issue and LSU bound, not HBM bound.
+// h2y_forward2.cu -- the fast forward kernels behind h2y_forward (the general kernel is h2y_forward.cu).
 //
-// Same decomposition as v1 (h2y_forward.cu): persistent CTA per SM, work item = (frame, row segment,
-// 240-px column strip), warp = one image row of the strip per step, lane = 8 consecutive pixels,
-// lanes 0/31 are halo lanes of the horizontal filter.  What changed:
+//   k_forward_exr420<.., SRC=0>   EXR route (half source through the per-frame LUT, 4:2:0 FIR, tmp depth <= 12), small
+//                                 batches: CTA-shared 64-row ring, vertical filter register-blocked 4 outputs x 18 rows
+//   k_forward_exr420_rows         EXR route, large batches: warp-autonomous, vertical filter as six running register
+//                                 accumulators per chroma column, no ring, no CTA barrier inside a frame
+//   k_forward_exr420<.., SRC=1>   integer rows (TIFF), 4:2:0 FIR at 16-bit tmp depth: same ring, reference-order arithmetic
+//   k_forward_u16_444             integer rows, 4:4:4 output: a streaming map at HBM speed
 //
-//  * Per-pixel arithmetic runs on Blackwell's packed fp32x2 pipe (FFMA2 / FADD2 / FMUL2: two lanes of
-//    fp32 per issue slot).  The colour-difference stage is evaluated in fp32 with a guard band: every
-//    truncation is taken twice, at x-G and x+G, with a round-down add of 1.5*2^23 (the integer falls
-//    out of the mantissa, no F2I); when both agree the truncated integer is certain, because the
-//    fp32 evaluation is within G/2 of the reference's double evaluation (bound in DESIGN.md 4).
-//    The rare pixel whose two truncations differ is redone with v1's exact routine.  No FP64 and no
-//    float<->double conversions remain on the common path.
-//  * The range scale (convert.cpp:1139-1144) keeps its two separately rounded fp32 operations, so
-//    the values entering the matrix are the reference's own floats.
-//  * Chroma stays in float from the truncation to the .yuv store; the u16 quantisation of the
-//    reference's `dst422` intermediate and of tmp444 is reproduced by round-down adds + integer
-//    clamps on the magic-number bit pattern.  At tmp depth <= 12 every FIR term is an integer / 512
-//    below 2^24, so the FMA order is free and both filters are FFMA2 chains
-//    on {Cb,Cr} pairs.
-//  * Vertical filter: a thread owns one chroma column and FOUR vertically adjacent outputs, streaming
-//    18 ring rows through 48 FFMA2 (v1 re-read 12 rows per output: 2.7x the shared-memory traffic).
-//    The ring holds {Cb,Cr} float2 per column, 64 rows (power of two), and the two half-CTAs
-//    alternate as vertical-filter workers so one __syncthreads per 16 rows suffices.
-//  * The LUT copy in shared memory covers exactly the frame's code range; frames with negative,
-//    infinite or NaN samples (never "clean") are left to the v1 kernel, which handles every case.
+// Common to the EXR kernels, and why they are still bit-exact (error bound in DESIGN.md 4):
+//  * Per-pixel arithmetic runs on Blackwell's packed fp32x2 pipe (FFMA2 / FADD2: two lanes of fp32 per issue slot).
+//    The colour-difference stage is evaluated in fp32 with a guard band: every truncation is taken twice, at x-G and
+//    x+G, with a round-down add of 1.5*2^23 (the integer falls out of the mantissa, no F2I); when both agree the
+//    truncated integer is certain, because the fp32 evaluation is within G/2 of the reference's double evaluation.
+//    The rare pixel whose two truncations differ is redone with the general kernel's FP64 routine (inlined: an
+//    out-of-line call cost ~2900 cycles per 16-row step through ABI spills).
+//  * The range scale (convert.cpp:1139-1144) keeps its two separately rounded fp32 operations, so the values entering
+//    the matrix are the reference's own floats.
+//  * Chroma stays in float from the truncation to the .yuv store; the u16 quantisation of the reference's `dst422`
+//    intermediate and of tmp444 is reproduced by round-down adds + integer clamps on the magic-number bit pattern.
+//    At tmp depth <= 12 every FIR term is an integer / 512 below 2^24, so the FMA order is free (SURVEY.md Appendix
+//    A.7) and both filters are FFMA2 chains on {Cb,Cr} pairs.
+//  * The LUT copy in shared memory is indexed by the raw half code; frames with negative, infinite or NaN samples
+//    (never "clean") are left to the general kernel, which handles every case.
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -36,7 +32,7 @@
 namespace h2y {
 
 namespace {
-constexpr int THREADS = 512, WARPS = THREADS / 32;
+constexpr int THREADS = 512;
 constexpr int RING_ROWS = 64, RING_COLS = 120;            // float2 per column
 constexpr int RING_PITCH = RING_COLS * 2;                 // floats per ring row
 constexpr int LUT_MAX_CODES = 0x7C00;                     // clean frames: codes 0 .. 0x7BFF

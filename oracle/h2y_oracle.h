@@ -8,7 +8,7 @@
  *
  * Parity status: PINNED.  The restatement is checked sample-for-sample against
  * the reference's own sources compiled unmodified (oracle/_ref/libh2yref.so,
- * built by oracle/build.py from /root/reference) in tests/test_oracle_vs_ref.py,
+ * built by oracle/build.py from /root/reference) in tests/test_oracle_cpu.py,
  * and against golden vectors generated from that compiled reference
  * (tests/golden/, generator tests/golden/make_golden.py).  The reference ships
  * no golden vectors of its own (test.sh:89-94 compares against ref/ files that
