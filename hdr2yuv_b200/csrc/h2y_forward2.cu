@@ -123,7 +123,7 @@ template <int CFG> struct KC {
 };
 
 // ---- per-lane: 8 pixels -> Y (packed, final) and clamped chroma as floats -------------------------
-template <int MK, int CFG = 0>
+template <int MK, int CFG = 0, bool TWO = false>      // TWO: `lut` holds two pre-scaled copies (luma scale, then chroma scale at +LUT2_CODES)
 __device__ __forceinline__ void pixels8(const Fwd2Args &a, const float *lut, const unsigned g[8], const unsigned b[8],
                                         const unsigned r[8], uint4 &ypack, u64 chroma[8], unsigned &fallbacks)
 {
@@ -145,9 +145,17 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, const float *lut, con
 #pragma unroll
     for (int q = 0; q < 8; q += 2) {
         // LUT gather + range scale (two rounded operations each, convert.cpp:1141-1143)
-        const u64 G2 = fadd2(fmul2s(lut[g[q]], lut[g[q + 1]], C::mulY(a)), addY2);
-        const u64 B2 = fadd2(fmul2s(lut[b[q]], lut[b[q + 1]], C::mulC(a)), addC2);
-        const u64 R2 = fadd2(fmul2s(lut[r[q]], lut[r[q + 1]], C::mulC(a)), addC2);
+        u64 G2, B2, R2;
+        if (TWO) {
+            const float *lutC = lut + LUT2_CODES;
+            G2 = pk(lut[g[q]], lut[g[q + 1]]);
+            B2 = pk(lutC[b[q]], lutC[b[q + 1]]);
+            R2 = pk(lutC[r[q]], lutC[r[q + 1]]);
+        } else {
+            G2 = fadd2(fmul2s(lut[g[q]], lut[g[q + 1]], C::mulY(a)), addY2);
+            B2 = fadd2(fmul2s(lut[b[q]], lut[b[q + 1]], C::mulC(a)), addC2);
+            R2 = fadd2(fmul2s(lut[r[q]], lut[r[q + 1]], C::mulC(a)), addC2);
+        }
         u64 y1, y2, base;
         if (MK == MK_YCBCR) {
             const u64 slo = ffma2(wg2, G2, ffma2(wr2, R2, ffma2(wb2, B2, lumc2)));     // luma + 0.5 - G
@@ -466,12 +474,13 @@ struct Fwd3Args {
     Fwd2Args b;
     int sub;                 // row workers per CTA (16 / strips when a picture has fewer than 16 strips)
     int wps;                 // warps per row worker = strips handled side by side
+    int split_by_lut2;       // two instantiations share the frames: TWO takes those with lut2_ok, the other the rest
     long total_rows;         // nframes * h
 };
 
 constexpr int THREADS3 = 512, WARPS3 = THREADS3 / 32;     // 16 warps (12 x 168 registers measured 6 % slower: latency hiding wins)
 
-template <int MK, int NCH, int CFG = 0>
+template <int MK, int NCH, int CFG = 0, bool TWO = false>
 __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3Args A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -511,12 +520,21 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
     for (int frame = f_first; frame <= f_last; frame++) {
         const FrameK &fk = a.framek[frame];
         if (!fk.clean) continue;                         // uniform per CTA: v1 converts this frame
+        if (A.split_by_lut2 && TWO != (fk.lut2_ok != 0)) continue;      // the other instantiation converts this frame
         // ---- LUT for this frame (CTA-wide) ----
         {
             const unsigned lo = fk.code_lo, hi = fk.code_hi;
             if (fk.lut_slot[0] != cur_slot || lo < cur_lo || hi > cur_hi) {
                 __syncthreads();                         // every warp is done with the previous LUT
                 const float *gl = a.luts + (size_t)fk.lut_slot[0] * 65536;
+                if (TWO) {
+                    // two copies with the range scale already applied, exactly as convert.cpp:1141-1143 rounds it
+                    for (unsigned c = lo + threadIdx.x; c <= hi; c += THREADS3) {
+                        const float v = __ldg(gl + c);
+                        lut_s[c] = __fadd_rn(__fmul_rn(v, C::mulY(a)), C::addY(a));
+                        lut_s[LUT2_CODES + c] = __fadd_rn(__fmul_rn(v, C::mulC(a)), C::addC(a));
+                    }
+                } else
                 for (unsigned c = lo + threadIdx.x; c <= hi; c += THREADS3) lut_s[c] = __ldg(gl + c);
                 cur_slot = fk.lut_slot[0]; cur_lo = lo; cur_hi = hi;
                 __syncthreads();
@@ -559,7 +577,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                 split_codes<NCH>(raw, g, b, rr);
                 uint4 ypack;
                 u64 ch[8];
-                pixels8<MK, CFG>(a, lut_s, g, b, rr, ypack, ch, fallbacks);
+                pixels8<MK, CFG, TWO>(a, lut_s, g, b, rr, ypack, ch, fallbacks);
                 if (lane_interior && r >= ys && r < ye) *reinterpret_cast<uint4 *>(yp) = ypack;
                 float l3x = __shfl_up_sync(0xffffffffu, plo(ch[3]), 1), l3y = __shfl_up_sync(0xffffffffu, phi(ch[3]), 1);
                 float l5x = __shfl_up_sync(0xffffffffu, plo(ch[5]), 1), l5y = __shfl_up_sync(0xffffffffu, phi(ch[5]), 1);
@@ -808,6 +826,7 @@ h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, c
         for (int d = 1; d <= WARPS3; d++) if (WARPS3 % d == 0 && a.nstrips % d == 0) A3.wps = d;
         A3.sub = WARPS3 / A3.wps;
         A3.total_rows = (long)nframes * a.h;
+        A3.split_by_lut2 = 0;
         const long rows_per_worker = A3.total_rows / ((long)grid_max * A3.sub);
         const char *force = getenv("H2Y_FORWARD_KERNEL");             // "ring" / "rows": tests and experiments
         const bool want_rows = force ? force[0] == 'r' && force[1] == 'o' : rows_per_worker >= 128;
@@ -832,8 +851,14 @@ h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, c
             if (cfgd) {
 #define L3C(NC, DD)                                                                                                        \
     do {                                                                                                                   \
-        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
-        k_forward_exr420_rows<MK_YCBCR, NC, DD><<<g3, THREADS3, smem3, st>>>(A3);                                         \
+        /* frames whose code range allows two pre-scaled LUT copies, then the rest */                                      \
+        const size_t smem2 = (size_t)2 * LUT2_CODES * sizeof(float);                                                       \
+        A3.split_by_lut2 = 1;                                                                                              \
+        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+        k_forward_exr420_rows<MK_YCBCR, NC, DD, true><<<g3, THREADS3, smem2, st>>>(A3);                                   \
+        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
+        k_forward_exr420_rows<MK_YCBCR, NC, DD, false><<<g3, THREADS3, smem3, st>>>(A3);                                  \
+        c->launches++;                                                                                                     \
     } while (0)
                 if (tmp_bit_depth == 10) { if (nch == 3) L3C(3, 10); else L3C(4, 10); }
                 else { if (nch == 3) L3C(3, 12); else L3C(4, 12); }

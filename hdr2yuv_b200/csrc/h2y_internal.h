@@ -22,7 +22,9 @@ struct FrameK {
     // shared LUT -- the precondition of the v2 kernel (h2y_forward2.cu); code_lo..code_hi = raw code range
     int clean;
     unsigned code_lo, code_hi;
+    int lut2_ok;                // clean and code_hi < LUT2_CODES: two pre-scaled LUT copies fit in shared memory
 };
+constexpr unsigned LUT2_CODES = 29000;   // 2 x 29000 floats = 232 000 B of the 232 448 B a CTA may use (half code 0x7148 ~ 10 800)
 
 struct h2y_ctx_impl {
     int device;

@@ -403,6 +403,7 @@ __global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_fl
         f.code_lo = ulo; f.code_hi = uhi;
         f.clean = is_float && f.same_lut && ulo <= uhi && uhi < 0x7C00u && f.range[0] > 0.0f && f.range[1] > 0.0f &&
                   f.range[2] > 0.0f;
+        f.lut2_ok = f.clean && uhi < LUT2_CODES;
     }
 }
 

@@ -232,11 +232,28 @@ def test_large_4k_batch_takes_rows_kernel_and_matches_oracle(ctx):
     frames = [base[i % 2] for i in range(n)]
     before = ctx.kernel_launches
     got = G.gpu_forward(ctx, frames, _HALF, dst)
-    assert ctx.kernel_launches - before == 6          # init, stats, plan, LUT, rows kernel, v1 sweep for unclean frames
+    # init, stats, plan, LUT, rows kernel (two-LUT instantiation + single-LUT instantiation), general-kernel sweep
+    assert ctx.kernel_launches - before == 7
     for i in (0, 1):
         G.compare_codes(got[i], G.oracle_forward(base[i], _HALF, dst), True, "4K frame %d" % i)
     for i in range(2, n):
         assert np.array_equal(got[i], got[i % 2]), i
+
+
+def test_rows_kernel_splits_frames_by_lut_fit(ctx, monkeypatch):
+    # frames whose largest sample is above ~10 800 (half code >= LUT2_CODES) cannot keep two pre-scaled LUT copies in
+    # shared memory: they go to the single-LUT instantiation, the others to the two-LUT one, in the same call
+    monkeypatch.setenv("H2Y_FORWARD_KERNEL", "rows")
+    w, h = 480, 128
+    dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+    frames = [synth.exr_half_frame(w, h, seed=60 + s, channels=3, hi=hi) for s, hi in enumerate((4000.0, 40000.0, 900.0, 60000.0))]
+    got = G.gpu_forward(ctx, frames, _HALF, dst)
+    for i, f in enumerate(frames):
+        G.compare_codes(got[i], G.oracle_forward(f, _HALF, dst), True, "frame %d" % i)
+    monkeypatch.setenv("H2Y_NO_SPECIALISED", "1")         # and the generic (run-time constants) instantiation agrees
+    again = G.gpu_forward(ctx, frames, _HALF, dst)
+    for a, b in zip(got, again):
+        assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("which", ["ring", "rows"])
