@@ -273,3 +273,15 @@ def test_unclean_frames_fall_back_to_the_general_kernel(ctx, monkeypatch, which)
     monkeypatch.setenv("H2Y_FORCE_V1", "1")
     ref2 = G.gpu_forward(ctx, [frames[2]], _HALF, dst)[0]
     assert np.array_equal(got[2], ref2)
+
+
+@pytest.mark.parametrize("which", ["ring", "rows"])
+def test_wide_and_short_pictures(ctx, monkeypatch, which):
+    # more strips than warps (8K: 32 strips of 240), two-row pictures, a single 8-pixel column
+    _force_kernel(monkeypatch, which)
+    dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+    for (w, h, n) in ((7680, 36, 2), (8, 2, 3), (8, 130, 1), (3848, 2, 2)):
+        frames = [synth.exr_half_frame(w, h, seed=200 + s, channels=3) for s in range(n)]
+        got = G.gpu_forward(ctx, frames, _HALF, dst)
+        for f, g in zip(frames, got):
+            G.compare_codes(g, G.oracle_forward(f, _HALF, dst), True, "%s %dx%d" % (which, w, h))

@@ -173,3 +173,15 @@ def test_empty_batches_are_no_ops(ctx):
     ctx.forward_host(fp, np.zeros(1, np.uint8), np.zeros(1, np.uint8), 0)
     ctx.inverse_host(p, np.zeros(1, np.uint8), np.zeros(1, np.uint8), 0)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("kernel", ["tile", "rows"])
+def test_inverse_wide_and_short_pictures(ctx, kernel, monkeypatch):
+    monkeypatch.setenv("H2Y_INVERSE_KERNEL", kernel)
+    for (w, h) in ((7680, 36), (8, 2), (8, 130), (3848, 4)):
+        yuvs = [_yuv_for(w, h, 300 + s, 10, 9) for s in range(2)]
+        rgb, inv = gpu_inverse(ctx, yuvs, w, h, 10, O.INV_2020, 1, 0, 0)
+        for i in range(2):
+            want, invalid = O.yuv2tiff(yuvs[i], w, h, 10, O.INV_2020, True, False, False)
+            assert np.array_equal(rgb[i], want), (kernel, w, h)
+            assert int(inv[i]) == invalid
