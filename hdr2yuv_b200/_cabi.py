@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhdr2yuv_b200.so")
+# H2Y_LIB selects an experiment build of the same library (tools/build_variants.py); the default is the in-tree product
+LIB_PATH = os.environ.get("H2Y_LIB") or os.path.join(HERE, "libhdr2yuv_b200.so")
 
 # status codes (include/hdr2yuv_b200.h)
 OK, ERR_PRECONDITION, ERR_MATRIX, ERR_BIT_DEPTH, ERR_UNSUPPORTED, ERR_ARG, ERR_CUDA, ERR_NOMEM = range(8)

@@ -50,5 +50,25 @@ __device__ __forceinline__ u64 fadd2_rm(u64 a, u64 b)      // round toward -inf
     return r;
 }
 __device__ __forceinline__ int clamp3(int v, int lo, int hi) { return min(max(v, lo), hi); }
+// two 16-bit codes per register, clamped with one VIMNMX pair (lo / hi hold the bound in both halves)
+__device__ __forceinline__ unsigned clamp_u16x2(unsigned v, unsigned lo, unsigned hi)
+{
+    asm("max.u16x2 %0, %0, %1;" : "+r"(v) : "r"(lo));
+    asm("min.u16x2 %0, %0, %1;" : "+r"(v) : "r"(hi));
+    return v;
+}
+__device__ __forceinline__ unsigned clamp_s16x2(unsigned v, unsigned lo, unsigned hi)
+{
+    asm("max.s16x2 %0, %0, %1;" : "+r"(v) : "r"(lo));
+    asm("min.s16x2 %0, %0, %1;" : "+r"(v) : "r"(hi));
+    return v;
+}
+// 1.0f when x < 0, else 0.0f (FSET.BF)
+__device__ __forceinline__ float fset_lt0(float x)
+{
+    float r;
+    asm("set.lt.f32.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 }   // namespace h2y

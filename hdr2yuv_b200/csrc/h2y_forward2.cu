@@ -29,6 +29,28 @@
 #include "h2y_f32x2.cuh"
 #include "h2y_internal.h"
 
+// experiment switches (profiles/r01/variants.md); the defaults are the shipped configuration
+#ifndef H2Y_ROWS2
+#define H2Y_ROWS2 0
+#endif
+#ifndef H2Y_GUARD_SHIFT
+#define H2Y_GUARD_SHIFT 22
+#endif
+#ifndef H2Y_TIER3_CALL
+#define H2Y_TIER3_CALL 0
+#endif
+#ifndef H2Y_CHROMA_MODE
+#define H2Y_CHROMA_MODE 0
+#endif
+#ifndef H2Y_PACKCLAMP
+#define H2Y_PACKCLAMP 1
+#endif
+#if H2Y_TIER3_CALL
+#define H2Y_TIER3_ATTR __noinline__
+#else
+#define H2Y_TIER3_ATTR __forceinline__
+#endif
+
 namespace h2y {
 
 namespace {
@@ -94,10 +116,23 @@ __device__ __forceinline__ void split_codes(const RawPx<NCH> &raw, unsigned g[8]
 }
 
 // the reference-exact route for a pixel inside the guard band (rare: kept out of line)
+// Two tiers: the FP64 reciprocal form with 14 guard bits settles all but ~2^-13 of the pixels that get here; the
+// reference's true division is a call (its ABI cost does not matter at that rate, its inlined size would: the
+// 32 KB instruction cache has to hold the row loop).
+template <int MK>
+__device__ H2Y_TIER3_ATTR unsigned long long pixel_exact_div(float G, float B, float R, const PixK *k)
+{
+    unsigned Y, Cb, Cr;
+    px_matrix_exact<MK>(G, B, R, *k, Y, Cb, Cr);
+    return (unsigned long long)Y | ((unsigned long long)Cb << 16) | ((unsigned long long)Cr << 32);
+}
 template <int MK>
 __device__ __forceinline__ void pixel_exact(float G, float B, float R, const PixK &k, unsigned &Y, unsigned &Cb, unsigned &Cr)
 {
-    if (!px_matrix_fast<MK>(G, B, R, k, Y, Cb, Cr)) px_matrix_exact<MK>(G, B, R, k, Y, Cb, Cr);
+    if (!px_matrix_fast<MK>(G, B, R, k, Y, Cb, Cr)) {
+        const unsigned long long v = pixel_exact_div<MK>(G, B, R, &k);
+        Y = (unsigned)v & 0xffffu; Cb = (unsigned)(v >> 16) & 0xffffu; Cr = (unsigned)(v >> 32) & 0xffffu;
+    }
 }
 
 // Per-launch constants.  CFG 0 reads them from the launch arguments; CFG 10 / 12 are the headline configurations
@@ -107,7 +142,7 @@ __device__ __forceinline__ void pixel_exact(float G, float B, float R, const Pix
 template <int CFG> struct KC {
     // CFG = 0: run time.  CFG = D (10 or 12): BT.2020nc at D-bit tmp/output depth, video range, no output shift
     static constexpr int D = CFG ? CFG : 10, S = 1 << (D - 8);
-    static constexpr float G = 1.0f / (float)(1 << (21 - D));
+    static constexpr float G = 1.0f / (float)(1 << (H2Y_GUARD_SHIFT - D));
     static constexpr float RDB = (float)(1.0 / 1.8814), RDR = (float)(1.0 / 1.4746);
 #define KCF(name, rt, ct) __device__ __forceinline__ static float name(const Fwd2Args &a) { return CFG ? (ct) : (rt); }
 #define KCI(name, rt, ct) __device__ __forceinline__ static int name(const Fwd2Args &a) { return CFG ? (ct) : (int)(rt); }
@@ -121,6 +156,28 @@ template <int CFG> struct KC {
 #undef KCF
 #undef KCI
 };
+
+// Which frames take the TWO instantiation (two pre-scaled LUT copies in shared memory, chroma without clamp).  The
+// frame's codes must fit the copies, and no Cb/Cr the frame can produce may come near matrix_convert's clamp
+// (convert.cpp:1207-1213): the LUT is monotone over a clean frame's codes, so its values at code_lo / code_hi bound
+// every scaled sample and with them the colour differences.  Evaluated identically by every CTA of both
+// instantiations (plain global reads), so the two launches split the batch consistently.
+template <int CFG>
+__device__ __forceinline__ bool two_lut_frame(const Fwd2Args &a, const FrameK &fk)
+{
+    typedef KC<CFG> C;
+    if (!fk.lut2_ok) return false;
+    const float *gl = a.luts + (size_t)fk.lut_slot[0] * 65536;
+    const float vlo = __ldg(gl + fk.code_lo), vhi = __ldg(gl + fk.code_hi);
+    const float ylo = vlo * C::mulY(a) + C::addY(a), yhi = vhi * C::mulY(a) + C::addY(a);
+    const float clo = vlo * C::mulC(a) + C::addC(a), chi = vhi * C::mulC(a) + C::addC(a);
+    // extremes of (B - Y')/db and (R - Y')/dr over the box, with Y' = wr R + wg G + wb B + 0.5
+    const float wr = C::wr(a), wg = C::wg(a), wb = C::wb(a);
+    const float cb_hi = (chi - (wr * clo + wg * ylo + wb * chi)) * C::rdb(a), cb_lo = (clo - (wr * chi + wg * yhi + wb * clo) - 1.0f) * C::rdb(a);
+    const float cr_hi = (chi - (wr * chi + wg * ylo + wb * clo)) * C::rdr(a), cr_lo = (clo - (wr * clo + wg * yhi + wb * chi) - 1.0f) * C::rdr(a);
+    const float top = (float)(C::maxCV(a) - C::half_m1(a)) - 2.0f, bot = 2.0f - (float)C::half_m1(a);
+    return vlo >= 0.0f && cb_hi < top && cr_hi < top && cb_lo > bot && cr_lo > bot && yhi < (float)C::maxCV(a);
+}
 
 // ---- per-lane: 8 pixels -> Y (packed, final) and clamped chroma as floats -------------------------
 template <int MK, int CFG = 0, bool TWO = false>      // TWO: `lut` holds two pre-scaled copies (luma scale, then chroma scale at +LUT2_CODES)
@@ -168,8 +225,12 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, const float *lut, con
         }
         const u64 nbase = base ^ 0x8000000080000000ull;
         const u64 cbl = ffma2(fadd2(B2, nbase), rdb2, cbc2), crl = ffma2(fadd2(R2, nbase), rdr2, crc2);
-        const u64 cb1 = fadd2_rm(cbl, magic2), cb2 = fadd2_rm(fadd2(cbl, twoG2), magic2);
-        const u64 cr1 = fadd2_rm(crl, magic2), cr2 = fadd2_rm(fadd2(crl, twoG2), magic2);
+        const u64 cbh = fadd2(cbl, twoG2), crh = fadd2(crl, twoG2);
+        const u64 cb1 = fadd2_rm(cbl, magic2), cb2 = fadd2_rm(cbh, magic2);
+        const u64 cr1 = fadd2_rm(crl, magic2), cr2 = fadd2_rm(crh, magic2);
+#if H2Y_CHROMA_MODE == 2
+        const u64 cbf = fadd2(cb1, pk(-MAGIC, -MAGIC)), crf = fadd2(cr1, pk(-MAGIC, -MAGIC));
+#endif
         int Y1[2], Y2[2], B1[2], Bq[2], R1[2], Rq[2], xb[2], xr[2];
         unpk(y1, Y1[0], Y1[1]); unpk(y2, Y2[0], Y2[1]);
         unpk(cb1, B1[0], B1[1]); unpk(cb2, Bq[0], Bq[1]);
@@ -177,12 +238,30 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, const float *lut, con
         unpk(cbl, xb[0], xb[1]); unpk(crl, xr[0], xr[1]);
         int ybits[2];
         unsigned cbi[2], cri[2];
+        float tcb[2], tcr[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             ybits[e] = Y1[e];
-            // trunc toward zero = floor + 1 for negative non-integers (integers are never "safe")
-            cbi[e] = (unsigned)(B1[e] + cbias + (int)((unsigned)xb[e] >> 31));
-            cri[e] = (unsigned)(R1[e] + cbias + (int)((unsigned)xr[e] >> 31));
+            if (TWO) {
+                // no integer in (x-G, x+G] => the reference's value and x+G truncate alike; FRND.TRUNC keeps the
+                // result a float and writes it where the {Cb,Cr} pair lives.  Half-1 is added by the horizontal
+                // filter's constant (its taps sum to 1), and two_lut_frame() has checked that no clamp can bind.
+#if H2Y_CHROMA_MODE == 1
+                tcb[e] = truncf(e ? phi(cbh) : plo(cbh));
+                tcr[e] = truncf(e ? phi(crh) : plo(crh));
+#elif H2Y_CHROMA_MODE == 0
+                tcb[e] = (float)(B1[e] - MAGIC_BITS + (int)((unsigned)xb[e] >> 31));
+                tcr[e] = (float)(R1[e] - MAGIC_BITS + (int)((unsigned)xr[e] >> 31));
+#else
+                // floor as a float (the magic add undone), +1 for negative values: trunc toward zero without I2F
+                tcb[e] = __fadd_rn(e ? phi(cbf) : plo(cbf), fset_lt0(__int_as_float(xb[e])));
+                tcr[e] = __fadd_rn(e ? phi(crf) : plo(crf), fset_lt0(__int_as_float(xr[e])));
+#endif
+            } else {
+                // trunc toward zero = floor + 1 for negative non-integers (integers are never "safe")
+                cbi[e] = (unsigned)(B1[e] + cbias + (int)((unsigned)xb[e] >> 31));
+                cri[e] = (unsigned)(R1[e] + cbias + (int)((unsigned)xr[e] >> 31));
+            }
         }
         const int f0 = (Y1[0] ^ Y2[0]) | (B1[0] ^ Bq[0]) | (R1[0] ^ Rq[0]), f1 = (Y1[1] ^ Y2[1]) | (B1[1] ^ Bq[1]) | (R1[1] ^ Rq[1]);
         if ((f0 | f1) != 0) {
@@ -199,26 +278,34 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, const float *lut, con
                     pixel_exact<MK>(Gs[e], Bs[e], Rs[e], k, Ye, Cbe, Cre);
                     ybits[e] = (int)Ye + MAGIC_BITS;
                     cbi[e] = Cbe; cri[e] = Cre;
+                    tcb[e] = (float)((int)Cbe - C::half_m1(a)); tcr[e] = (float)((int)Cre - C::half_m1(a));
                     fallbacks++;
                 }
         }
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             // write_yuv: >> shift, range clamp; the low 16 bits of the result are the code
-            yv[q + e] = (unsigned)clamp3(ybits[e] >> shift, ylo, yhi);
+            if (!(H2Y_PACKCLAMP && CFG)) yv[q + e] = (unsigned)clamp3(ybits[e] >> shift, ylo, yhi);
+            else yv[q + e] = (unsigned)ybits[e];      // CFG: shift is 0 and Y < 2^16, clamped as a packed pair below
             // matrix_convert's clamp through unsigned long: negatives land on maxCV (convert.cpp:1210-1213)
-            chroma[q + e] = pk((float)(int)min(cbi[e], maxCV), (float)(int)min(cri[e], maxCV));
+            chroma[q + e] = TWO ? pk(tcb[e], tcr[e]) : pk((float)(int)min(cbi[e], maxCV), (float)(int)min(cri[e], maxCV));
         }
     }
     ypack = make_uint4(__byte_perm(yv[0], yv[1], 0x5410), __byte_perm(yv[2], yv[3], 0x5410),
                        __byte_perm(yv[4], yv[5], 0x5410), __byte_perm(yv[6], yv[7], 0x5410));
+    if (H2Y_PACKCLAMP && CFG) {
+        const unsigned lo2 = (unsigned)C::loY(a) * 0x10001u, hi2 = (unsigned)C::hiY(a) * 0x10001u;
+        ypack.x = clamp_u16x2(ypack.x, lo2, hi2); ypack.y = clamp_u16x2(ypack.y, lo2, hi2);
+        ypack.z = clamp_u16x2(ypack.z, lo2, hi2); ypack.w = clamp_u16x2(ypack.w, lo2, hi2);
+    }
 }
 
 // horizontal 7-tap at even x on a {Cb,Cr} pair (convert.cpp:290-321); exact integer arithmetic in fp32
-__device__ __forceinline__ u64 fir_h7_pair(u64 m5, u64 m3, u64 m1, u64 c, u64 p1, u64 p3, u64 p5, int hi_bits)
+// `c0` is the rounding 0.5, plus Half-1 when the caller's samples come without it (the taps sum to exactly 1)
+__device__ __forceinline__ u64 fir_h7_pair(u64 m5, u64 m3, u64 m1, u64 c, u64 p1, u64 p3, u64 p5, int hi_bits, float c0 = 0.5f)
 {
     const u64 k21 = pk(21.0f / 512.0f, 21.0f / 512.0f), k52n = pk(-52.0f / 512.0f, -52.0f / 512.0f),
-              k159 = pk(159.0f / 512.0f, 159.0f / 512.0f), k256 = pk(0.5f, 0.5f), half2v = pk(0.5f, 0.5f);
+              k159 = pk(159.0f / 512.0f, 159.0f / 512.0f), k256 = pk(0.5f, 0.5f), half2v = pk(c0, c0);
     u64 t = ffma2(k21, m5, half2v);
     t = ffma2(k21, p5, t);
     t = ffma2(k52n, m3, t);
@@ -493,6 +580,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
     const int hi_bits = MAGIC_BITS + C::maxCV(a);
     const int shift = C::shift(a);
     const int clo = C::loC(a) + (MAGIC_BITS >> shift), chi = C::hiC(a) + (MAGIC_BITS >> shift);
+    const float hc0 = TWO ? (float)C::half_m1(a) + 0.5f : 0.5f;     // pixels8<TWO> leaves Half-1 to the filter
     unsigned fallbacks = 0;
 
     // this warp's worker and strip set
@@ -520,7 +608,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
     for (int frame = f_first; frame <= f_last; frame++) {
         const FrameK &fk = a.framek[frame];
         if (!fk.clean) continue;                         // uniform per CTA: v1 converts this frame
-        if (A.split_by_lut2 && TWO != (fk.lut2_ok != 0)) continue;      // the other instantiation converts this frame
+        if (A.split_by_lut2 && TWO != two_lut_frame<CFG>(a, fk)) continue;   // the other instantiation converts this frame
         // ---- LUT for this frame (CTA-wide) ----
         {
             const unsigned lo = fk.code_lo, hi = fk.code_hi;
@@ -587,57 +675,94 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                 u64 l3 = pk(l3x, l3y), l5 = pk(l5x, l5y), l7 = pk(l7x, l7y), n1 = pk(n1x, n1y), n3 = pk(n3x, n3y);
                 if (left_edge) l3 = l5 = l7 = ch[0];                // replicate s[0]     (convert.cpp:295-300)
                 if (right_edge) n1 = n3 = ch[7];                    // replicate s[W-1]
-                o[0] = fir_h7_pair(l3, l5, l7, ch[0], ch[1], ch[3], ch[5], hi_bits);
-                o[1] = fir_h7_pair(l5, l7, ch[1], ch[2], ch[3], ch[5], ch[7], hi_bits);
-                o[2] = fir_h7_pair(l7, ch[1], ch[3], ch[4], ch[5], ch[7], n1, hi_bits);
-                o[3] = fir_h7_pair(ch[1], ch[3], ch[5], ch[6], ch[7], n1, n3, hi_bits);
+                o[0] = fir_h7_pair(l3, l5, l7, ch[0], ch[1], ch[3], ch[5], hi_bits, hc0);
+                o[1] = fir_h7_pair(l5, l7, ch[1], ch[2], ch[3], ch[5], ch[7], hi_bits, hc0);
+                o[2] = fir_h7_pair(l7, ch[1], ch[3], ch[4], ch[5], ch[7], n1, hi_bits, hc0);
+                o[3] = fir_h7_pair(ch[1], ch[3], ch[5], ch[6], ch[7], n1, n3, hi_bits, hc0);
             };
             // advance the source pointer from (clamped) row r to (clamped) row r+1
             auto next_src = [&](int r) { sp += ((unsigned)r < (unsigned)(h - 1)) ? spitch : 0; };
 
-            RawPx<NCH> raw, cur;
-            load_px8<NCH>(raw, sp, 0, 0, 0);
-#pragma unroll 1
-            for (int r = rfirst; r <= rlast; r++) {          // one row body for both parities: the instruction cache is a limit
-                cur = raw;
-                next_src(r);
-                if (r < rlast) load_px8<NCH>(raw, sp, 0, 0, 0);                 // prefetch the next row
-                u64 o[4];
-                row_front(cur, r, o);
-                yp += w;
-                if ((r & 1) == 0) {
-                    // even row r = 2m: acc[i] is output j = m-3+i and receives tap 11-2i; acc[0] completes
+            // even row r = 2m: acc[i] is output j = m-3+i and receives tap 11-2i; acc[0] completes
+            auto row_even = [&](const u64 o[4], int r) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+#pragma unroll
+                    for (int i = 0; i < 6; i++) acc[i][c] = ffma2(kv[11 - 2 * i], o[c], acc[i][c]);
+                }
+                const int j = (r >> 1) - 3;
+                if (lane_interior && j >= (ys >> 1) && j < (ye >> 1)) {
+                    unsigned cbv[4], crv[4];
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
-#pragma unroll
-                        for (int i = 0; i < 6; i++) acc[i][c] = ffma2(kv[11 - 2 * i], o[c], acc[i][c]);
-                    }
-                    const int j = (r >> 1) - 3;
-                    if (lane_interior && j >= (ys >> 1) && j < (ye >> 1)) {
-                        unsigned cbv[4], crv[4];
-#pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                            // clamp [0,maxCV] + truncation + write_yuv's shift and range clamp: one integer clamp of the floor
-                            int lo_, hi_;
-                            unpk(fadd2_rm(acc[0][c], pk(MAGIC, MAGIC)), lo_, hi_);
+                        // clamp [0,maxCV] + truncation + write_yuv's shift and range clamp: one integer clamp of the floor
+                        int lo_, hi_;
+                        unpk(fadd2_rm(acc[0][c], pk(MAGIC, MAGIC)), lo_, hi_);
+                        if (H2Y_PACKCLAMP && CFG) {
+                            // the floor is in [-2^15, 2^15): its low half is the s16 value, clamped two at a time below
+                            cbv[c] = (unsigned)lo_; crv[c] = (unsigned)hi_;
+                        } else {
                             cbv[c] = (unsigned)clamp3(lo_ >> shift, clo, chi);
                             crv[c] = (unsigned)clamp3(hi_ >> shift, clo, chi);
                         }
-                        *reinterpret_cast<uint2 *>(cbp) = make_uint2(__byte_perm(cbv[0], cbv[1], 0x5410), __byte_perm(cbv[2], cbv[3], 0x5410));
-                        *reinterpret_cast<uint2 *>(cbp + crd) = make_uint2(__byte_perm(crv[0], crv[1], 0x5410), __byte_perm(crv[2], crv[3], 0x5410));
                     }
-                    cbp += wh;
-                } else {
-                    // odd row r = 2m+1: the accumulators shift down by one output (the FFMA2 writes the neighbour);
-                    // old acc[i+1] receives tap 10-2i and a new output starts in acc[5] with tap 0
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-#pragma unroll
-                        for (int i = 0; i < 5; i++) acc[i][c] = ffma2(kv[10 - 2 * i], o[c], acc[i + 1][c]);
-                        acc[5][c] = ffma2(kv[0], o[c], pk(0.5f, 0.5f));
+                    uint2 cbo = make_uint2(__byte_perm(cbv[0], cbv[1], 0x5410), __byte_perm(cbv[2], cbv[3], 0x5410));
+                    uint2 cro = make_uint2(__byte_perm(crv[0], crv[1], 0x5410), __byte_perm(crv[2], crv[3], 0x5410));
+                    if (H2Y_PACKCLAMP && CFG) {
+                        const unsigned lo2 = (unsigned)C::loC(a) * 0x10001u, hi2 = (unsigned)C::hiC(a) * 0x10001u;
+                        cbo.x = clamp_s16x2(cbo.x, lo2, hi2); cbo.y = clamp_s16x2(cbo.y, lo2, hi2);
+                        cro.x = clamp_s16x2(cro.x, lo2, hi2); cro.y = clamp_s16x2(cro.y, lo2, hi2);
                     }
+                    *reinterpret_cast<uint2 *>(cbp) = cbo;
+                    *reinterpret_cast<uint2 *>(cbp + crd) = cro;
                 }
+                cbp += wh;
+            };
+            // odd row r = 2m+1: the accumulators shift down by one output (the FFMA2 writes the neighbour);
+            // old acc[i+1] receives tap 10-2i and a new output starts in acc[5] with tap 0
+            auto row_odd = [&](const u64 o[4]) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+#pragma unroll
+                    for (int i = 0; i < 5; i++) acc[i][c] = ffma2(kv[10 - 2 * i], o[c], acc[i + 1][c]);
+                    acc[5][c] = ffma2(kv[0], o[c], pk(0.5f, 0.5f));
+                }
+            };
+
+            // two rows per trip (rfirst is even): the second buffer replaces a 12-register copy, and the accumulator
+            // rotation of the odd row needs no moves when the trip ends where it began.  The trip that starts at
+            // rlast also runs row rlast+1; it feeds outputs past ye/2 that are never stored.
+#if H2Y_ROWS2
+            RawPx<NCH> rawA, rawB;
+            load_px8<NCH>(rawA, sp, 0, 0, 0);
+#pragma unroll 1
+            for (int r = rfirst; r <= rlast; r += 2) {
+                u64 o[4];
+                next_src(r);
+                load_px8<NCH>(rawB, sp, 0, 0, 0);                               // prefetch the odd row
+                row_front(rawA, r, o);
+                yp += w;
+                row_even(o, r);
+                next_src(r + 1);
+                if (r + 2 <= rlast) load_px8<NCH>(rawA, sp, 0, 0, 0);           // prefetch the next even row
+                row_front(rawB, r + 1, o);
+                yp += w;
+                row_odd(o);
             }
+#else
+            RawPx<NCH> raw, cur;
+            load_px8<NCH>(raw, sp, 0, 0, 0);
+#pragma unroll 1
+            for (int r = rfirst; r <= rlast; r++) {
+                cur = raw;
+                next_src(r);
+                if (r < rlast) load_px8<NCH>(raw, sp, 0, 0, 0);
+                u64 o[4];
+                row_front(cur, r, o);
+                yp += w;
+                if ((r & 1) == 0) row_even(o, r); else row_odd(o);
+            }
+#endif
         }
     }
     if (a.fallback_count && fallbacks) atomicAdd(a.fallback_count, (unsigned long long)fallbacks);
@@ -793,7 +918,7 @@ h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, c
     a.framek = d_framek; a.luts = d_luts;
     a.fallback_count = nullptr;
     // the fp32 evaluation is within G/2 of the reference at this depth: G = 2^(depth-21)
-    a.guard = 1.0f / (float)(1 << (21 - tmp_bit_depth));
+    a.guard = 1.0f / (float)(1 << (H2Y_GUARD_SHIFT - tmp_bit_depth));
     if (const char *e = getenv("H2Y_EXPERIMENT_GUARD_LOG2")) a.guard = exp2f(-(float)atoi(e));   // timing experiments only: breaks parity
     a.wr = (float)k.wr; a.wg = (float)k.wg; a.wb = (float)k.wb;
     a.rdb = k.mat_kind == MK_YCBCR ? (float)k.rdb : 0.5f;
