@@ -38,6 +38,12 @@ __device__ __forceinline__ u64 fadd2(u64 a, u64 b)
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ u64 fsub2(u64 a, u64 b)         // FADD2 with a negated operand
+{
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 // {a.lo*m, a.hi*m}, each product rounded on its own.  NOT mul.rn.f32x2: ptxas 12.9 contracts mul.rn.f32x2 +
 // add.rn.f32x2 into one FFMA2 even with explicit .rn and -fmad=false (checked in the SASS), which would drop
 // the reference's separate rounding of x*maxVR before +minVR (convert.cpp:1141).  Scalar FMULs are left alone.

@@ -29,26 +29,10 @@
 #include "h2y_f32x2.cuh"
 #include "h2y_internal.h"
 
-// experiment switches (profiles/r01/variants.md); the defaults are the shipped configuration
-#ifndef H2Y_ROWS2
-#define H2Y_ROWS2 0
-#endif
+// Guard-band half width G = 2^(depth - H2Y_GUARD_SHIFT); see the error bound in DESIGN.md section 4.  A build switch
+// only for the A/B timings in profiles/r01/variants.md (21 was the first, more conservative, choice).
 #ifndef H2Y_GUARD_SHIFT
 #define H2Y_GUARD_SHIFT 22
-#endif
-#ifndef H2Y_TIER3_CALL
-#define H2Y_TIER3_CALL 0
-#endif
-#ifndef H2Y_CHROMA_MODE
-#define H2Y_CHROMA_MODE 0
-#endif
-#ifndef H2Y_PACKCLAMP
-#define H2Y_PACKCLAMP 1
-#endif
-#if H2Y_TIER3_CALL
-#define H2Y_TIER3_ATTR __noinline__
-#else
-#define H2Y_TIER3_ATTR __forceinline__
 #endif
 
 namespace h2y {
@@ -116,23 +100,10 @@ __device__ __forceinline__ void split_codes(const RawPx<NCH> &raw, unsigned g[8]
 }
 
 // the reference-exact route for a pixel inside the guard band (rare: kept out of line)
-// Two tiers: the FP64 reciprocal form with 14 guard bits settles all but ~2^-13 of the pixels that get here; the
-// reference's true division is a call (its ABI cost does not matter at that rate, its inlined size would: the
-// 32 KB instruction cache has to hold the row loop).
-template <int MK>
-__device__ H2Y_TIER3_ATTR unsigned long long pixel_exact_div(float G, float B, float R, const PixK *k)
-{
-    unsigned Y, Cb, Cr;
-    px_matrix_exact<MK>(G, B, R, *k, Y, Cb, Cr);
-    return (unsigned long long)Y | ((unsigned long long)Cb << 16) | ((unsigned long long)Cr << 32);
-}
 template <int MK>
 __device__ __forceinline__ void pixel_exact(float G, float B, float R, const PixK &k, unsigned &Y, unsigned &Cb, unsigned &Cr)
 {
-    if (!px_matrix_fast<MK>(G, B, R, k, Y, Cb, Cr)) {
-        const unsigned long long v = pixel_exact_div<MK>(G, B, R, &k);
-        Y = (unsigned)v & 0xffffu; Cb = (unsigned)(v >> 16) & 0xffffu; Cr = (unsigned)(v >> 32) & 0xffffu;
-    }
+    if (!px_matrix_fast<MK>(G, B, R, k, Y, Cb, Cr)) px_matrix_exact<MK>(G, B, R, k, Y, Cb, Cr);
 }
 
 // Per-launch constants.  CFG 0 reads them from the launch arguments; CFG 10 / 12 are the headline configurations
@@ -179,10 +150,24 @@ __device__ __forceinline__ bool two_lut_frame(const Fwd2Args &a, const FrameK &f
     return vlo >= 0.0f && cb_hi < top && cr_hi < top && cb_lo > bot && cr_lo > bot && yhi < (float)C::maxCV(a);
 }
 
-// ---- per-lane: 8 pixels -> Y (packed, final) and clamped chroma as floats -------------------------
-template <int MK, int CFG = 0, bool TWO = false>      // TWO: `lut` holds two pre-scaled copies (luma scale, then chroma scale at +LUT2_CODES)
-__device__ __forceinline__ void pixels8(const Fwd2Args &a, const float *lut, const unsigned g[8], const unsigned b[8],
-                                        const unsigned r[8], uint4 &ypack, u64 chroma[8], unsigned &fallbacks)
+// LUT entry `code` of the table at shared-window address `lut` (+OFS bytes).  An explicit shared-space load: the
+// generic form makes ptxas rebuild the window base (S2UR + UMOV + ULEA) in front of every group of gathers.
+template <int OFS>
+__device__ __forceinline__ float lds_lut(unsigned lut, unsigned code)
+{
+    float v;
+    unsigned addr;
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"(code), "r"(lut));       // one IMAD (FMA pipe), not shift + add
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFS));
+    return v;
+}
+
+// ---- per-lane: 8 pixels -> luma (floor bits, not yet clamped) and chroma as floats ---------------------------
+// TWO:   `lut` holds two pre-scaled copies (luma scale, then chroma scale at +LUT2_CODES); chroma comes without
+//        Half-1 and without matrix_convert's clamp (two_lut_frame() has checked that it cannot bind).
+template <int MK, int CFG = 0, bool TWO = false>
+__device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, const unsigned g[8], const unsigned b[8],
+                                            const unsigned r[8], unsigned ybits[8], u64 chroma[8], unsigned &fallbacks)
 {
     typedef KC<CFG> C;
     const PixK &k = a.k;
@@ -193,25 +178,20 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, const float *lut, con
     const u64 rdb2 = pk(rdb, rdb), rdr2 = pk(rdr, rdr);
     const u64 lumc2 = pk(C::lumc(a), C::lumc(a));
     const u64 cbc2 = pk(C::cbc(a), C::cbc(a)), crc2 = pk(C::crc(a), C::crc(a));
-    const int shift = C::shift(a);
-    const int ylo = C::loY(a) + (MAGIC_BITS >> shift), yhi = C::hiY(a) + (MAGIC_BITS >> shift);
     const int cbias = C::half_m1(a) - MAGIC_BITS;
     const unsigned maxCV = (unsigned)C::maxCV(a);
-
-    unsigned yv[8];
 #pragma unroll
     for (int q = 0; q < 8; q += 2) {
         // LUT gather + range scale (two rounded operations each, convert.cpp:1141-1143)
         u64 G2, B2, R2;
         if (TWO) {
-            const float *lutC = lut + LUT2_CODES;
-            G2 = pk(lut[g[q]], lut[g[q + 1]]);
-            B2 = pk(lutC[b[q]], lutC[b[q + 1]]);
-            R2 = pk(lutC[r[q]], lutC[r[q + 1]]);
+            G2 = pk(lds_lut<0>(lut, g[q]), lds_lut<0>(lut, g[q + 1]));
+            B2 = pk(lds_lut<LUT2_CODES * 4>(lut, b[q]), lds_lut<LUT2_CODES * 4>(lut, b[q + 1]));
+            R2 = pk(lds_lut<LUT2_CODES * 4>(lut, r[q]), lds_lut<LUT2_CODES * 4>(lut, r[q + 1]));
         } else {
-            G2 = fadd2(fmul2s(lut[g[q]], lut[g[q + 1]], C::mulY(a)), addY2);
-            B2 = fadd2(fmul2s(lut[b[q]], lut[b[q + 1]], C::mulC(a)), addC2);
-            R2 = fadd2(fmul2s(lut[r[q]], lut[r[q + 1]], C::mulC(a)), addC2);
+            G2 = fadd2(fmul2s(lds_lut<0>(lut, g[q]), lds_lut<0>(lut, g[q + 1]), C::mulY(a)), addY2);
+            B2 = fadd2(fmul2s(lds_lut<0>(lut, b[q]), lds_lut<0>(lut, b[q + 1]), C::mulC(a)), addC2);
+            R2 = fadd2(fmul2s(lds_lut<0>(lut, r[q]), lds_lut<0>(lut, r[q + 1]), C::mulC(a)), addC2);
         }
         u64 y1, y2, base;
         if (MK == MK_YCBCR) {
@@ -223,48 +203,31 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, const float *lut, con
             y1 = y2 = fadd2_rm(G2, magic2);
             base = G2;
         }
-        const u64 nbase = base ^ 0x8000000080000000ull;
-        const u64 cbl = ffma2(fadd2(B2, nbase), rdb2, cbc2), crl = ffma2(fadd2(R2, nbase), rdr2, crc2);
-        const u64 cbh = fadd2(cbl, twoG2), crh = fadd2(crl, twoG2);
-        const u64 cb1 = fadd2_rm(cbl, magic2), cb2 = fadd2_rm(cbh, magic2);
-        const u64 cr1 = fadd2_rm(crl, magic2), cr2 = fadd2_rm(crh, magic2);
-#if H2Y_CHROMA_MODE == 2
-        const u64 cbf = fadd2(cb1, pk(-MAGIC, -MAGIC)), crf = fadd2(cr1, pk(-MAGIC, -MAGIC));
-#endif
+        const u64 cbl = ffma2(fsub2(B2, base), rdb2, cbc2), crl = ffma2(fsub2(R2, base), rdr2, crc2);
+        const u64 cb1 = fadd2_rm(cbl, magic2), cb2 = fadd2_rm(fadd2(cbl, twoG2), magic2);
+        const u64 cr1 = fadd2_rm(crl, magic2), cr2 = fadd2_rm(fadd2(crl, twoG2), magic2);
         int Y1[2], Y2[2], B1[2], Bq[2], R1[2], Rq[2], xb[2], xr[2];
         unpk(y1, Y1[0], Y1[1]); unpk(y2, Y2[0], Y2[1]);
         unpk(cb1, B1[0], B1[1]); unpk(cb2, Bq[0], Bq[1]);
         unpk(cr1, R1[0], R1[1]); unpk(cr2, Rq[0], Rq[1]);
         unpk(cbl, xb[0], xb[1]); unpk(crl, xr[0], xr[1]);
-        int ybits[2];
         unsigned cbi[2], cri[2];
         float tcb[2], tcr[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            ybits[e] = Y1[e];
+            ybits[q + e] = (unsigned)Y1[e];
+            // trunc toward zero = floor + 1 for negative non-integers (an integer is never "safe": no integer lies in
+            // (x-G, x+G], so the reference's value and x-G floor alike and have the same sign)
             if (TWO) {
-                // no integer in (x-G, x+G] => the reference's value and x+G truncate alike; FRND.TRUNC keeps the
-                // result a float and writes it where the {Cb,Cr} pair lives.  Half-1 is added by the horizontal
-                // filter's constant (its taps sum to 1), and two_lut_frame() has checked that no clamp can bind.
-#if H2Y_CHROMA_MODE == 1
-                tcb[e] = truncf(e ? phi(cbh) : plo(cbh));
-                tcr[e] = truncf(e ? phi(crh) : plo(crh));
-#elif H2Y_CHROMA_MODE == 0
                 tcb[e] = (float)(B1[e] - MAGIC_BITS + (int)((unsigned)xb[e] >> 31));
                 tcr[e] = (float)(R1[e] - MAGIC_BITS + (int)((unsigned)xr[e] >> 31));
-#else
-                // floor as a float (the magic add undone), +1 for negative values: trunc toward zero without I2F
-                tcb[e] = __fadd_rn(e ? phi(cbf) : plo(cbf), fset_lt0(__int_as_float(xb[e])));
-                tcr[e] = __fadd_rn(e ? phi(crf) : plo(crf), fset_lt0(__int_as_float(xr[e])));
-#endif
             } else {
-                // trunc toward zero = floor + 1 for negative non-integers (integers are never "safe")
                 cbi[e] = (unsigned)(B1[e] + cbias + (int)((unsigned)xb[e] >> 31));
                 cri[e] = (unsigned)(R1[e] + cbias + (int)((unsigned)xr[e] >> 31));
             }
         }
-        const int f0 = (Y1[0] ^ Y2[0]) | (B1[0] ^ Bq[0]) | (R1[0] ^ Rq[0]), f1 = (Y1[1] ^ Y2[1]) | (B1[1] ^ Bq[1]) | (R1[1] ^ Rq[1]);
-        if ((f0 | f1) != 0) {
+        const bool f0 = Y1[0] != Y2[0] || B1[0] != Bq[0] || R1[0] != Rq[0], f1 = Y1[1] != Y2[1] || B1[1] != Bq[1] || R1[1] != Rq[1];
+        if (f0 || f1) {
             // within the guard band of an integer: take the reference-exact route for that pixel (one branch per pair)
             float Gs[2], Bs[2], Rs[2];
             int t0, t1;
@@ -273,31 +236,40 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, const float *lut, con
             unpk(R2, t0, t1); Rs[0] = __int_as_float(t0); Rs[1] = __int_as_float(t1);
 #pragma unroll
             for (int e = 0; e < 2; e++)
-                if ((e ? f1 : f0) != 0) {
+                if (e ? f1 : f0) {
                     unsigned Ye, Cbe, Cre;
                     pixel_exact<MK>(Gs[e], Bs[e], Rs[e], k, Ye, Cbe, Cre);
-                    ybits[e] = (int)Ye + MAGIC_BITS;
+                    ybits[q + e] = Ye + (unsigned)MAGIC_BITS;
                     cbi[e] = Cbe; cri[e] = Cre;
                     tcb[e] = (float)((int)Cbe - C::half_m1(a)); tcr[e] = (float)((int)Cre - C::half_m1(a));
                     fallbacks++;
                 }
         }
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-            // write_yuv: >> shift, range clamp; the low 16 bits of the result are the code
-            if (!(H2Y_PACKCLAMP && CFG)) yv[q + e] = (unsigned)clamp3(ybits[e] >> shift, ylo, yhi);
-            else yv[q + e] = (unsigned)ybits[e];      // CFG: shift is 0 and Y < 2^16, clamped as a packed pair below
+        for (int e = 0; e < 2; e++)
             // matrix_convert's clamp through unsigned long: negatives land on maxCV (convert.cpp:1210-1213)
             chroma[q + e] = TWO ? pk(tcb[e], tcr[e]) : pk((float)(int)min(cbi[e], maxCV), (float)(int)min(cri[e], maxCV));
-        }
     }
-    ypack = make_uint4(__byte_perm(yv[0], yv[1], 0x5410), __byte_perm(yv[2], yv[3], 0x5410),
-                       __byte_perm(yv[4], yv[5], 0x5410), __byte_perm(yv[6], yv[7], 0x5410));
-    if (H2Y_PACKCLAMP && CFG) {
+}
+
+// write_yuv on the luma floor bits: >> shift, range clamp, pack (the low 16 bits of the clamped value are the code)
+template <int CFG>
+__device__ __forceinline__ uint4 pack_luma(const Fwd2Args &a, const unsigned ybits[8])
+{
+    typedef KC<CFG> C;
+    if (CFG) {
+        // shift is 0 and Y < 2^16: pack first, then clamp two codes per instruction
         const unsigned lo2 = (unsigned)C::loY(a) * 0x10001u, hi2 = (unsigned)C::hiY(a) * 0x10001u;
-        ypack.x = clamp_u16x2(ypack.x, lo2, hi2); ypack.y = clamp_u16x2(ypack.y, lo2, hi2);
-        ypack.z = clamp_u16x2(ypack.z, lo2, hi2); ypack.w = clamp_u16x2(ypack.w, lo2, hi2);
+        return make_uint4(clamp_u16x2(__byte_perm(ybits[0], ybits[1], 0x5410), lo2, hi2), clamp_u16x2(__byte_perm(ybits[2], ybits[3], 0x5410), lo2, hi2),
+                          clamp_u16x2(__byte_perm(ybits[4], ybits[5], 0x5410), lo2, hi2), clamp_u16x2(__byte_perm(ybits[6], ybits[7], 0x5410), lo2, hi2));
     }
+    const int shift = C::shift(a);
+    const int ylo = C::loY(a) + (MAGIC_BITS >> shift), yhi = C::hiY(a) + (MAGIC_BITS >> shift);
+    unsigned yv[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) yv[i] = (unsigned)clamp3((int)ybits[i] >> shift, ylo, yhi);
+    return make_uint4(__byte_perm(yv[0], yv[1], 0x5410), __byte_perm(yv[2], yv[3], 0x5410),
+                      __byte_perm(yv[4], yv[5], 0x5410), __byte_perm(yv[6], yv[7], 0x5410));
 }
 
 // horizontal 7-tap at even x on a {Cb,Cr} pair (convert.cpp:290-321); exact integer arithmetic in fp32
@@ -390,7 +362,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
                 __syncthreads();
             }
         }
-        const float *lut = lut_s;                       // indexed by the raw code; entries cur_lo..cur_hi are valid
+        const unsigned lut_sa = (unsigned)__cvta_generic_to_shared(lut_s);   // indexed by the raw code; entries cur_lo..cur_hi are valid
 
         const int x0 = strip * a.strip_w;
         const int ys = seg * a.seg_rows, ye = min(ys + a.seg_rows, h);
@@ -427,7 +399,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
                 }
                 split_codes<NCH>(raw, g, b, r);
                 uint4 ypack;
-                if (SRC == 0) pixels8<MK>(a, lut, g, b, r, ypack, ch, fallbacks);
+                if (SRC == 0) { unsigned yb[8]; pixels8<MK>(a, lut_sa, g, b, r, yb, ch, fallbacks); ypack = pack_luma<0>(a, yb); }
                 else pixels8_u16<MK>(a, g, b, r, ypack, ch, fallbacks);
                 if (lane_interior && row >= ys && row < ye) *reinterpret_cast<uint4 *>(fY + (size_t)row * w + xl) = ypack;
             }
@@ -572,6 +544,10 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *lut_s = reinterpret_cast<float *>(smem_raw);
+    // shared-window address of the LUT, held in an ordinary register (the asm hides that it is uniform: as a uniform
+    // value ptxas rebuilds it from SR_CgaCtaId in front of every group of gathers)
+    unsigned lut_sa;
+    asm volatile("mov.u32 %0, %1;" : "=r"(lut_sa) : "r"((unsigned)__cvta_generic_to_shared(lut_s)));
     const Fwd2Args &a = A.b;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PixK &k = a.k;
@@ -660,12 +636,15 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
             const ptrdiff_t crd = fCr - fCb;
 
             // one row: 8 pixels -> Y store, chroma, horizontal 7-tap -> o[4]
+            // advance the source pointer from (clamped) row r to (clamped) row r+1
+            auto next_src = [&](int r) { sp += ((unsigned)r < (unsigned)(h - 1)) ? spitch : 0; };
             auto row_front = [&](const RawPx<NCH> &raw, int r, u64 o[4]) {
                 unsigned g[8], b[8], rr[8];
                 split_codes<NCH>(raw, g, b, rr);
-                uint4 ypack;
+                unsigned yb[8];
                 u64 ch[8];
-                pixels8<MK, CFG, TWO>(a, lut_s, g, b, rr, ypack, ch, fallbacks);
+                pixels8<MK, CFG, TWO>(a, lut_sa, g, b, rr, yb, ch, fallbacks);
+                const uint4 ypack = pack_luma<CFG>(a, yb);
                 if (lane_interior && r >= ys && r < ye) *reinterpret_cast<uint4 *>(yp) = ypack;
                 float l3x = __shfl_up_sync(0xffffffffu, plo(ch[3]), 1), l3y = __shfl_up_sync(0xffffffffu, phi(ch[3]), 1);
                 float l5x = __shfl_up_sync(0xffffffffu, plo(ch[5]), 1), l5y = __shfl_up_sync(0xffffffffu, phi(ch[5]), 1);
@@ -680,8 +659,6 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                 o[2] = fir_h7_pair(l7, ch[1], ch[3], ch[4], ch[5], ch[7], n1, hi_bits, hc0);
                 o[3] = fir_h7_pair(ch[1], ch[3], ch[5], ch[6], ch[7], n1, n3, hi_bits, hc0);
             };
-            // advance the source pointer from (clamped) row r to (clamped) row r+1
-            auto next_src = [&](int r) { sp += ((unsigned)r < (unsigned)(h - 1)) ? spitch : 0; };
 
             // even row r = 2m: acc[i] is output j = m-3+i and receives tap 11-2i; acc[0] completes
             auto row_even = [&](const u64 o[4], int r) {
@@ -698,7 +675,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                         // clamp [0,maxCV] + truncation + write_yuv's shift and range clamp: one integer clamp of the floor
                         int lo_, hi_;
                         unpk(fadd2_rm(acc[0][c], pk(MAGIC, MAGIC)), lo_, hi_);
-                        if (H2Y_PACKCLAMP && CFG) {
+                        if (CFG) {
                             // the floor is in [-2^15, 2^15): its low half is the s16 value, clamped two at a time below
                             cbv[c] = (unsigned)lo_; crv[c] = (unsigned)hi_;
                         } else {
@@ -708,7 +685,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                     }
                     uint2 cbo = make_uint2(__byte_perm(cbv[0], cbv[1], 0x5410), __byte_perm(cbv[2], cbv[3], 0x5410));
                     uint2 cro = make_uint2(__byte_perm(crv[0], crv[1], 0x5410), __byte_perm(crv[2], crv[3], 0x5410));
-                    if (H2Y_PACKCLAMP && CFG) {
+                    if (CFG) {
                         const unsigned lo2 = (unsigned)C::loC(a) * 0x10001u, hi2 = (unsigned)C::hiC(a) * 0x10001u;
                         cbo.x = clamp_s16x2(cbo.x, lo2, hi2); cbo.y = clamp_s16x2(cbo.y, lo2, hi2);
                         cro.x = clamp_s16x2(cro.x, lo2, hi2); cro.y = clamp_s16x2(cro.y, lo2, hi2);
@@ -729,40 +706,20 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                 }
             };
 
-            // two rows per trip (rfirst is even): the second buffer replaces a 12-register copy, and the accumulator
-            // rotation of the odd row needs no moves when the trip ends where it began.  The trip that starts at
-            // rlast also runs row rlast+1; it feeds outputs past ye/2 that are never stored.
-#if H2Y_ROWS2
-            RawPx<NCH> rawA, rawB;
-            load_px8<NCH>(rawA, sp, 0, 0, 0);
-#pragma unroll 1
-            for (int r = rfirst; r <= rlast; r += 2) {
-                u64 o[4];
-                next_src(r);
-                load_px8<NCH>(rawB, sp, 0, 0, 0);                               // prefetch the odd row
-                row_front(rawA, r, o);
-                yp += w;
-                row_even(o, r);
-                next_src(r + 1);
-                if (r + 2 <= rlast) load_px8<NCH>(rawA, sp, 0, 0, 0);           // prefetch the next even row
-                row_front(rawB, r + 1, o);
-                yp += w;
-                row_odd(o);
-            }
-#else
+            // one row body for both parities (measured: a two-row trip with two sample buffers spills and is 20 % slower,
+            // loading the next row only after the pixel stage exposes the load latency: profiles/r01/variants.md)
             RawPx<NCH> raw, cur;
             load_px8<NCH>(raw, sp, 0, 0, 0);
 #pragma unroll 1
             for (int r = rfirst; r <= rlast; r++) {
                 cur = raw;
                 next_src(r);
-                if (r < rlast) load_px8<NCH>(raw, sp, 0, 0, 0);
+                if (r < rlast) load_px8<NCH>(raw, sp, 0, 0, 0);                 // prefetch the next row
                 u64 o[4];
                 row_front(cur, r, o);
                 yp += w;
                 if ((r & 1) == 0) row_even(o, r); else row_odd(o);
             }
-#endif
         }
     }
     if (a.fallback_count && fallbacks) atomicAdd(a.fallback_count, (unsigned long long)fallbacks);
