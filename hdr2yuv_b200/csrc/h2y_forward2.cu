@@ -34,6 +34,9 @@
 #ifndef H2Y_GUARD_SHIFT
 #define H2Y_GUARD_SHIFT 22
 #endif
+#ifndef H2Y_PAIRS_PER_BRANCH
+#define H2Y_PAIRS_PER_BRANCH 2
+#endif
 
 namespace h2y {
 
@@ -167,7 +170,7 @@ __device__ __forceinline__ float lds_lut(unsigned lut, unsigned code)
 //        Half-1 and without matrix_convert's clamp (two_lut_frame() has checked that it cannot bind).
 template <int MK, int CFG = 0, bool TWO = false>
 __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, const unsigned g[8], const unsigned b[8],
-                                            const unsigned r[8], unsigned ybits[8], u64 chroma[8], unsigned &fallbacks)
+                                            const unsigned r[8], unsigned ybits[8], u64 chroma[8])
 {
     typedef KC<CFG> C;
     const PixK &k = a.k;
@@ -180,75 +183,90 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, const u
     const u64 cbc2 = pk(C::cbc(a), C::cbc(a)), crc2 = pk(C::crc(a), C::crc(a));
     const int cbias = C::half_m1(a) - MAGIC_BITS;
     const unsigned maxCV = (unsigned)C::maxCV(a);
+    // PG pixel pairs share one guard-band branch: fewer, larger basic blocks for the scheduler at the price of keeping
+    // the scaled samples of PG pairs alive until the branch
+    constexpr int PG = H2Y_PAIRS_PER_BRANCH;
 #pragma unroll
-    for (int q = 0; q < 8; q += 2) {
-        // LUT gather + range scale (two rounded operations each, convert.cpp:1141-1143)
-        u64 G2, B2, R2;
-        if (TWO) {
-            G2 = pk(lds_lut<0>(lut, g[q]), lds_lut<0>(lut, g[q + 1]));
-            B2 = pk(lds_lut<LUT2_CODES * 4>(lut, b[q]), lds_lut<LUT2_CODES * 4>(lut, b[q + 1]));
-            R2 = pk(lds_lut<LUT2_CODES * 4>(lut, r[q]), lds_lut<LUT2_CODES * 4>(lut, r[q + 1]));
-        } else {
-            G2 = fadd2(fmul2s(lds_lut<0>(lut, g[q]), lds_lut<0>(lut, g[q + 1]), C::mulY(a)), addY2);
-            B2 = fadd2(fmul2s(lds_lut<0>(lut, b[q]), lds_lut<0>(lut, b[q + 1]), C::mulC(a)), addC2);
-            R2 = fadd2(fmul2s(lds_lut<0>(lut, r[q]), lds_lut<0>(lut, r[q + 1]), C::mulC(a)), addC2);
-        }
-        u64 y1, y2, base;
-        if (MK == MK_YCBCR) {
-            const u64 slo = ffma2(wg2, G2, ffma2(wr2, R2, ffma2(wb2, B2, lumc2)));     // luma + 0.5 - G
-            y1 = fadd2_rm(slo, magic2);
-            y2 = fadd2_rm(fadd2(slo, twoG2), magic2);
-            base = slo;
-        } else {                                     // Y'DzDx: Y = (unsigned)G', exact
-            y1 = y2 = fadd2_rm(G2, magic2);
-            base = G2;
-        }
-        const u64 cbl = ffma2(fsub2(B2, base), rdb2, cbc2), crl = ffma2(fsub2(R2, base), rdr2, crc2);
-        const u64 cb1 = fadd2_rm(cbl, magic2), cb2 = fadd2_rm(fadd2(cbl, twoG2), magic2);
-        const u64 cr1 = fadd2_rm(crl, magic2), cr2 = fadd2_rm(fadd2(crl, twoG2), magic2);
-        int Y1[2], Y2[2], B1[2], Bq[2], R1[2], Rq[2], xb[2], xr[2];
-        unpk(y1, Y1[0], Y1[1]); unpk(y2, Y2[0], Y2[1]);
-        unpk(cb1, B1[0], B1[1]); unpk(cb2, Bq[0], Bq[1]);
-        unpk(cr1, R1[0], R1[1]); unpk(cr2, Rq[0], Rq[1]);
-        unpk(cbl, xb[0], xb[1]); unpk(crl, xr[0], xr[1]);
-        unsigned cbi[2], cri[2];
-        float tcb[2], tcr[2];
+    for (int q0 = 0; q0 < 8; q0 += 2 * PG) {
+        u64 G2[PG], B2[PG], R2[PG];
+        unsigned cbi[2 * PG], cri[2 * PG];
+        float tcb[2 * PG], tcr[2 * PG];
+        bool flag[2 * PG];
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-            ybits[q + e] = (unsigned)Y1[e];
-            // trunc toward zero = floor + 1 for negative non-integers (an integer is never "safe": no integer lies in
-            // (x-G, x+G], so the reference's value and x-G floor alike and have the same sign)
+        for (int p = 0; p < PG; p++) {
+            const int q = q0 + 2 * p;
+            // LUT gather + range scale (two rounded operations each, convert.cpp:1141-1143)
             if (TWO) {
-                tcb[e] = (float)(B1[e] - MAGIC_BITS + (int)((unsigned)xb[e] >> 31));
-                tcr[e] = (float)(R1[e] - MAGIC_BITS + (int)((unsigned)xr[e] >> 31));
+                G2[p] = pk(lds_lut<0>(lut, g[q]), lds_lut<0>(lut, g[q + 1]));
+                B2[p] = pk(lds_lut<LUT2_CODES * 4>(lut, b[q]), lds_lut<LUT2_CODES * 4>(lut, b[q + 1]));
+                R2[p] = pk(lds_lut<LUT2_CODES * 4>(lut, r[q]), lds_lut<LUT2_CODES * 4>(lut, r[q + 1]));
             } else {
-                cbi[e] = (unsigned)(B1[e] + cbias + (int)((unsigned)xb[e] >> 31));
-                cri[e] = (unsigned)(R1[e] + cbias + (int)((unsigned)xr[e] >> 31));
+                G2[p] = fadd2(fmul2s(lds_lut<0>(lut, g[q]), lds_lut<0>(lut, g[q + 1]), C::mulY(a)), addY2);
+                B2[p] = fadd2(fmul2s(lds_lut<0>(lut, b[q]), lds_lut<0>(lut, b[q + 1]), C::mulC(a)), addC2);
+                R2[p] = fadd2(fmul2s(lds_lut<0>(lut, r[q]), lds_lut<0>(lut, r[q + 1]), C::mulC(a)), addC2);
+            }
+            u64 y1, y2, base;
+            if (MK == MK_YCBCR) {
+                const u64 slo = ffma2(wg2, G2[p], ffma2(wr2, R2[p], ffma2(wb2, B2[p], lumc2)));     // luma + 0.5 - G
+                y1 = fadd2_rm(slo, magic2);
+                y2 = fadd2_rm(fadd2(slo, twoG2), magic2);
+                base = slo;
+            } else {                                     // Y'DzDx: Y = (unsigned)G', exact
+                y1 = y2 = fadd2_rm(G2[p], magic2);
+                base = G2[p];
+            }
+            const u64 cbl = ffma2(fsub2(B2[p], base), rdb2, cbc2), crl = ffma2(fsub2(R2[p], base), rdr2, crc2);
+            const u64 cb1 = fadd2_rm(cbl, magic2), cb2 = fadd2_rm(fadd2(cbl, twoG2), magic2);
+            const u64 cr1 = fadd2_rm(crl, magic2), cr2 = fadd2_rm(fadd2(crl, twoG2), magic2);
+            int Y1[2], Y2[2], B1[2], Bq[2], R1[2], Rq[2], xb[2], xr[2];
+            unpk(y1, Y1[0], Y1[1]); unpk(y2, Y2[0], Y2[1]);
+            unpk(cb1, B1[0], B1[1]); unpk(cb2, Bq[0], Bq[1]);
+            unpk(cr1, R1[0], R1[1]); unpk(cr2, Rq[0], Rq[1]);
+            unpk(cbl, xb[0], xb[1]); unpk(crl, xr[0], xr[1]);
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                ybits[q + e] = (unsigned)Y1[e];
+                // trunc toward zero = floor + 1 for negative non-integers (an integer is never "safe": no integer lies
+                // in (x-G, x+G], so the reference's value and x-G floor alike and have the same sign)
+                if (TWO) {
+                    tcb[2 * p + e] = (float)(B1[e] - MAGIC_BITS + (int)((unsigned)xb[e] >> 31));
+                    tcr[2 * p + e] = (float)(R1[e] - MAGIC_BITS + (int)((unsigned)xr[e] >> 31));
+                } else {
+                    cbi[2 * p + e] = (unsigned)(B1[e] + cbias + (int)((unsigned)xb[e] >> 31));
+                    cri[2 * p + e] = (unsigned)(R1[e] + cbias + (int)((unsigned)xr[e] >> 31));
+                }
+                flag[2 * p + e] = Y1[e] != Y2[e] || B1[e] != Bq[e] || R1[e] != Rq[e];
             }
         }
-        const bool f0 = Y1[0] != Y2[0] || B1[0] != Bq[0] || R1[0] != Rq[0], f1 = Y1[1] != Y2[1] || B1[1] != Bq[1] || R1[1] != Rq[1];
-        if (f0 || f1) {
-            // within the guard band of an integer: take the reference-exact route for that pixel (one branch per pair)
-            float Gs[2], Bs[2], Rs[2];
-            int t0, t1;
-            unpk(G2, t0, t1); Gs[0] = __int_as_float(t0); Gs[1] = __int_as_float(t1);
-            unpk(B2, t0, t1); Bs[0] = __int_as_float(t0); Bs[1] = __int_as_float(t1);
-            unpk(R2, t0, t1); Rs[0] = __int_as_float(t0); Rs[1] = __int_as_float(t1);
+        bool any = false;
 #pragma unroll
-            for (int e = 0; e < 2; e++)
-                if (e ? f1 : f0) {
+        for (int i = 0; i < 2 * PG; i++) any = any || flag[i];
+        if (any) {
+            // within the guard band of an integer: take the reference-exact route for those pixels
+#pragma unroll
+            for (int i = 0; i < 2 * PG; i++)
+                if (flag[i]) {
+                    // gathered again rather than kept alive across the branch (registers are the scarce resource here)
+                    float Gs, Bs, Rs;
+                    if (TWO) {
+                        Gs = lds_lut<0>(lut, g[q0 + i]); Bs = lds_lut<LUT2_CODES * 4>(lut, b[q0 + i]); Rs = lds_lut<LUT2_CODES * 4>(lut, r[q0 + i]);
+                    } else {
+                        Gs = __fadd_rn(__fmul_rn(lds_lut<0>(lut, g[q0 + i]), C::mulY(a)), C::addY(a));
+                        Bs = __fadd_rn(__fmul_rn(lds_lut<0>(lut, b[q0 + i]), C::mulC(a)), C::addC(a));
+                        Rs = __fadd_rn(__fmul_rn(lds_lut<0>(lut, r[q0 + i]), C::mulC(a)), C::addC(a));
+                    }
                     unsigned Ye, Cbe, Cre;
-                    pixel_exact<MK>(Gs[e], Bs[e], Rs[e], k, Ye, Cbe, Cre);
-                    ybits[q + e] = Ye + (unsigned)MAGIC_BITS;
-                    cbi[e] = Cbe; cri[e] = Cre;
-                    tcb[e] = (float)((int)Cbe - C::half_m1(a)); tcr[e] = (float)((int)Cre - C::half_m1(a));
-                    fallbacks++;
+                    pixel_exact<MK>(Gs, Bs, Rs, k, Ye, Cbe, Cre);
+                    ybits[q0 + i] = Ye + (unsigned)MAGIC_BITS;
+                    cbi[i] = Cbe; cri[i] = Cre;
+                    tcb[i] = (float)((int)Cbe - C::half_m1(a)); tcr[i] = (float)((int)Cre - C::half_m1(a));
+                    if (a.fallback_count) atomicAdd(a.fallback_count, 1ull);     // diagnostics only (null in production launches)
                 }
         }
 #pragma unroll
-        for (int e = 0; e < 2; e++)
+        for (int i = 0; i < 2 * PG; i++)
             // matrix_convert's clamp through unsigned long: negatives land on maxCV (convert.cpp:1210-1213)
-            chroma[q + e] = TWO ? pk(tcb[e], tcr[e]) : pk((float)(int)min(cbi[e], maxCV), (float)(int)min(cri[e], maxCV));
+            chroma[q0 + i] = TWO ? pk(tcb[i], tcr[i]) : pk((float)(int)min(cbi[i], maxCV), (float)(int)min(cri[i], maxCV));
     }
 }
 
@@ -399,7 +417,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
                 }
                 split_codes<NCH>(raw, g, b, r);
                 uint4 ypack;
-                if (SRC == 0) { unsigned yb[8]; pixels8<MK>(a, lut_sa, g, b, r, yb, ch, fallbacks); ypack = pack_luma<0>(a, yb); }
+                if (SRC == 0) { unsigned yb[8]; pixels8<MK>(a, lut_sa, g, b, r, yb, ch); ypack = pack_luma<0>(a, yb); }
                 else pixels8_u16<MK>(a, g, b, r, ypack, ch, fallbacks);
                 if (lane_interior && row >= ys && row < ye) *reinterpret_cast<uint4 *>(fY + (size_t)row * w + xl) = ypack;
             }
@@ -557,7 +575,6 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
     const int shift = C::shift(a);
     const int clo = C::loC(a) + (MAGIC_BITS >> shift), chi = C::hiC(a) + (MAGIC_BITS >> shift);
     const float hc0 = TWO ? (float)C::half_m1(a) + 0.5f : 0.5f;     // pixels8<TWO> leaves Half-1 to the filter
-    unsigned fallbacks = 0;
 
     // this warp's worker and strip set
     const int wk = warp / A.wps;                         // worker within the CTA
@@ -629,11 +646,11 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
 
             const int rfirst = ys - 6, rlast = ye + 4;                          // rows feeding outputs ys/2 .. ye/2-1 (both even)
             // running pointers: source row (clamped = edge replicate), Y row, chroma output row
-            const size_t spitch = (size_t)w * (2 * NCH);
+            const unsigned spitch = (unsigned)w * (2 * NCH);
             const uint8_t *sp = fsrc + (size_t)min(max(rfirst, 0), h - 1) * spitch + (size_t)xload * (2 * NCH);
             uint16_t *yp = fY + (ptrdiff_t)rfirst * w + xl;
             uint16_t *cbp = fCb + ((ptrdiff_t)(rfirst >> 1) - 3) * wh + (xl >> 1);
-            const ptrdiff_t crd = fCr - fCb;
+            const int crd = (int)(fCr - fCb);                                    // elements; a plane is far below 2^31
 
             // one row: 8 pixels -> Y store, chroma, horizontal 7-tap -> o[4]
             // advance the source pointer from (clamped) row r to (clamped) row r+1
@@ -643,7 +660,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                 split_codes<NCH>(raw, g, b, rr);
                 unsigned yb[8];
                 u64 ch[8];
-                pixels8<MK, CFG, TWO>(a, lut_sa, g, b, rr, yb, ch, fallbacks);
+                pixels8<MK, CFG, TWO>(a, lut_sa, g, b, rr, yb, ch);
                 const uint4 ypack = pack_luma<CFG>(a, yb);
                 if (lane_interior && r >= ys && r < ye) *reinterpret_cast<uint4 *>(yp) = ypack;
                 float l3x = __shfl_up_sync(0xffffffffu, plo(ch[3]), 1), l3y = __shfl_up_sync(0xffffffffu, phi(ch[3]), 1);
@@ -722,7 +739,6 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
             }
         }
     }
-    if (a.fallback_count && fallbacks) atomicAdd(a.fallback_count, (unsigned long long)fallbacks);
 }
 
 // ---- integer source, 4:4:4 output: a pure streaming map (no filter), one 8-pixel group per thread step ---------
