@@ -216,8 +216,9 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, const u
                 base = G2[p];
             }
             const u64 cbl = ffma2(fsub2(B2[p], base), rdb2, cbc2), crl = ffma2(fsub2(R2[p], base), rdr2, crc2);
-            const u64 cb1 = fadd2_rm(cbl, magic2), cb2 = fadd2_rm(fadd2(cbl, twoG2), magic2);
-            const u64 cr1 = fadd2_rm(crl, magic2), cr2 = fadd2_rm(fadd2(crl, twoG2), magic2);
+            const u64 cbh = fadd2(cbl, twoG2), crh = fadd2(crl, twoG2);
+            const u64 cb1 = fadd2_rm(cbl, magic2), cb2 = fadd2_rm(cbh, magic2);
+            const u64 cr1 = fadd2_rm(crl, magic2), cr2 = fadd2_rm(crh, magic2);
             int Y1[2], Y2[2], B1[2], Bq[2], R1[2], Rq[2], xb[2], xr[2];
             unpk(y1, Y1[0], Y1[1]); unpk(y2, Y2[0], Y2[1]);
             unpk(cb1, B1[0], B1[1]); unpk(cb2, Bq[0], Bq[1]);
@@ -226,12 +227,15 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, const u
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 ybits[q + e] = (unsigned)Y1[e];
-                // trunc toward zero = floor + 1 for negative non-integers (an integer is never "safe": no integer lies
-                // in (x-G, x+G], so the reference's value and x-G floor alike and have the same sign)
+                // An unflagged sample has no integer in (x, x+2G], where x is the lowered value: the reference's value
+                // lies strictly inside that window, so it truncates like either end and has the same sign.
                 if (TWO) {
-                    tcb[2 * p + e] = (float)(B1[e] - MAGIC_BITS + (int)((unsigned)xb[e] >> 31));
-                    tcr[2 * p + e] = (float)(R1[e] - MAGIC_BITS + (int)((unsigned)xr[e] >> 31));
+                    // FRND.TRUNC of the upper end is the float the filter wants, written straight into the {Cb,Cr}
+                    // pair: one XU instruction per sample instead of sign fix + rebias + I2F
+                    tcb[2 * p + e] = truncf(e ? phi(cbh) : plo(cbh));
+                    tcr[2 * p + e] = truncf(e ? phi(crh) : plo(crh));
                 } else {
+                    // trunc toward zero = floor + 1 for negative non-integers
                     cbi[2 * p + e] = (unsigned)(B1[e] + cbias + (int)((unsigned)xb[e] >> 31));
                     cri[2 * p + e] = (unsigned)(R1[e] + cbias + (int)((unsigned)xr[e] >> 31));
                 }
