@@ -386,15 +386,22 @@ __global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
                     }
                     if (!lane_interior) continue;
                     // ---- eight pixels of luma row 2c + half ----
+                    // Phase 1, branch-free: the colour difference inverse as integers Rp/Gp/Bp (before the output clamp
+                    // and shift) plus one bit per pixel that needs the reference-exact routine.
                     const uint4 yr = half ? yrow[1] : yrow[0];
-                    const unsigned yw[4] = {yr.x, yr.y, yr.z, yr.w};
-                    unsigned smp[8][3];
+                    unsigned yw[4] = {yr.x, yr.y, yr.z, yr.w};
+                    if (!C::full_range(A)) {                                                  // yuv2tiff.cpp:283-294
+                        const unsigned lo2 = C::minVR(A) * 0x10001u, hi2 = C::maxVR(A) * 0x10001u;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) yw[i] = clamp_u16x2(yw[i], lo2, hi2);
+                    }
+                    int Yv[8], Rv[8], Gv8[8], Bv[8];
+                    unsigned slow_mask = MODE == 0 ? 0xffu : 0u;
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
-                        unsigned Y = (q & 1) ? (yw[q >> 1] >> 16) : (yw[q >> 1] & 0xffffu);
-                        if (!C::full_range(A)) Y = min(max(Y, C::minVR(A)), C::maxVR(A));     // yuv2tiff.cpp:283-294
+                        const unsigned Y = (q & 1) ? (yw[q >> 1] >> 16) : (yw[q >> 1] & 0xffffu);
+                        Yv[q] = (int)Y;
                         const float cbf = plo(cpx[q]), crf = phi(cpx[q]);
-                        bool slow = MODE == 0;
                         int Rp = 0, Gp = 0, Bp = 0;
                         if (MODE == 1) {
                             const float Yf = __uint_as_float(0x4B000000u | Y) - TWO23;
@@ -408,32 +415,50 @@ __global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
                             const float g = __fmaf_rn(C::nwr(A), phi(brf), __fmaf_rn(C::nwb(A), plo(brf), Yf));
                             const float glo = __fmaf_rn(g, C::rwg(A), 0.5f - G);
                             const int G1 = __float_as_int(__fadd_rd(glo, MAGIC)), G2 = __float_as_int(__fadd_rd(glo + 2.0f * G, MAGIC));
-                            slow = (((B1 ^ B2) | (R1 ^ R2) | (G1 ^ G2)) != 0) | (min(min(B1, R1), G1) < MAGIC_BITS);
+                            // guarded (a floor changed inside the band) or negative (bit 22 of MAGIC_BITS + n clear)
+                            const bool slow = (((B1 ^ B2) | (R1 ^ R2) | (G1 ^ G2)) != 0) | (((B1 & R1 & G1) & 0x00400000) == 0);
+                            if (slow) slow_mask |= 1u << q;
                             Bp = Bc - MAGIC_BITS; Rp = Rc - MAGIC_BITS; Gp = min(G1, hi_bits) - MAGIC_BITS;
                         } else if (MODE == 2) {                                              // yuv2tiff.cpp:401-402
                             const int off = (int)Y - (int)(C::Full(A) - 1);
                             Rp = 2 * (int)crf + off; Bp = 2 * (int)cbf + off; Gp = (int)Y;
-                            slow = (Rp | Bp) < 0;
+                            if ((Rp | Bp) < 0) slow_mask |= 1u << q;
                         }
-                        unsigned R, Gv, B;
-                        if (slow) {
-                            invalid += (unsigned)inv_pixel<MODE == 1 ? H2Y_INV_2020 : (MODE == 2 ? H2Y_INV_YDzDx : -1)>(k, (int)Y, cbf, crf, R, Gv, B);
-                        } else {
-                            if (!C::full_range(A)) {                                          // yuv2tiff.cpp:515-524
-                                Rp = clamp3(Rp, (int)C::minVR(A), (int)C::maxVR(A)); Gp = clamp3(Gp, (int)C::minVR(A), (int)C::maxVR(A));
-                                Bp = clamp3(Bp, (int)C::minVR(A), (int)C::maxVR(A));
-                            }
-                            R = ((unsigned)Rp << C::SR(A)) & 0xffffu; Gv = ((unsigned)Gp << C::SR(A)) & 0xffffu; B = ((unsigned)Bp << C::SR(A)) & 0xffffu;
-                        }
-                        smp[q][0] = R; smp[q][1] = Gv; smp[q][2] = B;
+                        Rv[q] = Rp; Gv8[q] = Gp; Bv[q] = Bp;
                     }
+                    // Phase 2, rare and divergent: the reference's own arithmetic (double, true division, invalid-pixel
+                    // rules).  Its result is final (clamped, shifted); shifted back it passes the common tail unchanged.
+                    if (slow_mask) {
+#pragma unroll
+                        for (int q = 0; q < 8; q++)
+                            if (slow_mask & (1u << q)) {
+                                unsigned R, Gg, B;
+                                invalid += (unsigned)inv_pixel<MODE == 1 ? H2Y_INV_2020 : (MODE == 2 ? H2Y_INV_YDzDx : -1)>(k, Yv[q], plo(cpx[q]), phi(cpx[q]), R, Gg, B);
+                                Rv[q] = (int)(R >> C::SR(A)); Gv8[q] = (int)(Gg >> C::SR(A)); Bv[q] = (int)(B >> C::SR(A));
+                            }
+                    }
+                    // Phase 3: interleave, then output clamp (yuv2tiff.cpp:515-524) and << SR on two samples at a time
+                    // (samples are below 2^(16-SR), so a 32-bit shift cannot carry between the halves)
                     unsigned ow[16];
                     if (!ALPHA) {
+                        int flat[24];
 #pragma unroll
-                        for (int i = 0; i < 12; i++) ow[i] = smp[(2 * i) / 3][(2 * i) % 3] | (smp[(2 * i + 1) / 3][(2 * i + 1) % 3] << 16);
+                        for (int q = 0; q < 8; q++) { flat[3 * q] = Rv[q]; flat[3 * q + 1] = Gv8[q]; flat[3 * q + 2] = Bv[q]; }
+#pragma unroll
+                        for (int i = 0; i < 12; i++) ow[i] = __byte_perm((unsigned)flat[2 * i], (unsigned)flat[2 * i + 1], 0x5410);
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 8; q++) { ow[2 * q] = smp[q][0] | (smp[q][1] << 16); ow[2 * q + 1] = smp[q][2] | 0xffff0000u; }
+                        for (int q = 0; q < 8; q++) { ow[2 * q] = __byte_perm((unsigned)Rv[q], (unsigned)Gv8[q], 0x5410); ow[2 * q + 1] = (unsigned)Bv[q] & 0xffffu; }
+                    }
+                    {
+                        const unsigned lo2 = C::minVR(A) * 0x10001u, hi2 = C::maxVR(A) * 0x10001u;
+#pragma unroll
+                        for (int i = 0; i < (ALPHA ? 16 : 12); i++) {
+                            if (!C::full_range(A)) ow[i] = clamp_u16x2(ow[i], ALPHA && (i & 1) ? (lo2 & 0xffffu) : lo2, ALPHA && (i & 1) ? (hi2 & 0xffffu) : hi2);
+                            else if (MODE == 2) ow[i] &= (0xffffu >> C::SR(A)) * 0x10001u;    // unclamped Y'DzDx sums wrap like the reference's u16 store
+                            ow[i] <<= C::SR(A);
+                            if (ALPHA && (i & 1)) ow[i] |= 0xffff0000u;
+                        }
                     }
                     uint4 *o = reinterpret_cast<uint4 *>(frgb + ((size_t)(2 * c + half) * w + xl) * nch);
 #pragma unroll
