@@ -398,33 +398,49 @@ __global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
                     int Yv[8], Rv[8], Gv8[8], Bv[8];
                     unsigned slow_mask = MODE == 0 ? 0xffu : 0u;
 #pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const unsigned Y = (q & 1) ? (yw[q >> 1] >> 16) : (yw[q >> 1] & 0xffffu);
-                        Yv[q] = (int)Y;
-                        const float cbf = plo(cpx[q]), crf = phi(cpx[q]);
-                        int Rp = 0, Gp = 0, Bp = 0;
+                    for (int q = 0; q < 8; q += 2) {                     // two pixels at a time: one luma word
+                        const unsigned Y0 = yw[q >> 1] & 0xffffu, Y1 = yw[q >> 1] >> 16;
+                        Yv[q] = (int)Y0; Yv[q + 1] = (int)Y1;
                         if (MODE == 1) {
-                            const float Yf = __uint_as_float(0x4B000000u | Y) - TWO23;
-                            const float Yg = Yf - G;
-                            const u64 tlo = ffma2(fadd2(cpx[q], pk(-C::hm(A), -C::hm(A))), pk(C::kb(A), C::kr(A)), pk(Yg, Yg));
-                            int B1, R1, B2, R2;
-                            unpk(fadd2_rm(tlo, pk(MAGIC, MAGIC)), B1, R1);
-                            unpk(fadd2_rm(fadd2(tlo, pk(2.0f * G, 2.0f * G)), pk(MAGIC, MAGIC)), B2, R2);
-                            const int Bc = min(B1, hi_bits), Rc = min(R1, hi_bits);          // t > Full-1 -> Full-1 (406-412)
-                            const u64 brf = fadd2(pk(__int_as_float(Bc), __int_as_float(Rc)), pk(-MAGIC, -MAGIC));
-                            const float g = __fmaf_rn(C::nwr(A), phi(brf), __fmaf_rn(C::nwb(A), plo(brf), Yf));
-                            const float glo = __fmaf_rn(g, C::rwg(A), 0.5f - G);
-                            const int G1 = __float_as_int(__fadd_rd(glo, MAGIC)), G2 = __float_as_int(__fadd_rd(glo + 2.0f * G, MAGIC));
-                            // guarded (a floor changed inside the band) or negative (bit 22 of MAGIC_BITS + n clear)
-                            const bool slow = (((B1 ^ B2) | (R1 ^ R2) | (G1 ^ G2)) != 0) | (((B1 & R1 & G1) & 0x00400000) == 0);
-                            if (slow) slow_mask |= 1u << q;
-                            Bp = Bc - MAGIC_BITS; Rp = Rc - MAGIC_BITS; Gp = min(G1, hi_bits) - MAGIC_BITS;
-                        } else if (MODE == 2) {                                              // yuv2tiff.cpp:401-402
-                            const int off = (int)Y - (int)(C::Full(A) - 1);
-                            Rp = 2 * (int)crf + off; Bp = 2 * (int)cbf + off; Gp = (int)Y;
-                            if ((Rp | Bp) < 0) slow_mask |= 1u << q;
+                            // B', R' on the {Cb,Cr} pair of each pixel, G' on the pixel pair: all packed
+                            const u64 Yf2 = fadd2(pk(__uint_as_float(0x4B000000u | Y0), __uint_as_float(0x4B000000u | Y1)), pk(-TWO23, -TWO23));
+                            const u64 Yg2 = fadd2(Yf2, pk(-G, -G));
+                            int B1[2], R1[2], B2[2], R2[2], Bc[2], Rc[2];
+#pragma unroll
+                            for (int e = 0; e < 2; e++) {
+                                const float Yg = e ? phi(Yg2) : plo(Yg2);
+                                const u64 tlo = ffma2(fadd2(cpx[q + e], pk(-C::hm(A), -C::hm(A))), pk(C::kb(A), C::kr(A)), pk(Yg, Yg));
+                                unpk(fadd2_rm(tlo, pk(MAGIC, MAGIC)), B1[e], R1[e]);
+                                unpk(fadd2_rm(fadd2(tlo, pk(2.0f * G, 2.0f * G)), pk(MAGIC, MAGIC)), B2[e], R2[e]);
+                                Bc[e] = min(B1[e], hi_bits); Rc[e] = min(R1[e], hi_bits);    // t > Full-1 -> Full-1 (406-412)
+                            }
+                            const u64 bf = fadd2(pk(__int_as_float(Bc[0]), __int_as_float(Bc[1])), pk(-MAGIC, -MAGIC));
+                            const u64 rf = fadd2(pk(__int_as_float(Rc[0]), __int_as_float(Rc[1])), pk(-MAGIC, -MAGIC));
+                            const u64 g2 = ffma2(pk(C::nwr(A), C::nwr(A)), rf, ffma2(pk(C::nwb(A), C::nwb(A)), bf, Yf2));
+                            const u64 glo = ffma2(g2, pk(C::rwg(A), C::rwg(A)), pk(0.5f - G, 0.5f - G));
+                            int G1[2], G2[2];
+                            unpk(fadd2_rm(glo, pk(MAGIC, MAGIC)), G1[0], G1[1]);
+                            unpk(fadd2_rm(fadd2(glo, pk(2.0f * G, 2.0f * G)), pk(MAGIC, MAGIC)), G2[0], G2[1]);
+#pragma unroll
+                            for (int e = 0; e < 2; e++) {
+                                // guarded (a floor changed inside the band) or negative (bit 22 of MAGIC_BITS + n clear)
+                                const bool slow = (((B1[e] ^ B2[e]) | (R1[e] ^ R2[e]) | (G1[e] ^ G2[e])) != 0) | (((B1[e] & R1[e] & G1[e]) & 0x00400000) == 0);
+                                if (slow) slow_mask |= 1u << (q + e);
+                                Bv[q + e] = Bc[e] - MAGIC_BITS; Rv[q + e] = Rc[e] - MAGIC_BITS; Gv8[q + e] = min(G1[e], hi_bits) - MAGIC_BITS;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 2; e++) {
+                                const int Y = e ? (int)Y1 : (int)Y0;
+                                int Rp = 0, Gp = 0, Bp = 0;
+                                if (MODE == 2) {                                             // yuv2tiff.cpp:401-402
+                                    const int off = Y - (int)(C::Full(A) - 1);
+                                    Rp = 2 * (int)phi(cpx[q + e]) + off; Bp = 2 * (int)plo(cpx[q + e]) + off; Gp = Y;
+                                    if ((Rp | Bp) < 0) slow_mask |= 1u << (q + e);
+                                }
+                                Rv[q + e] = Rp; Gv8[q + e] = Gp; Bv[q + e] = Bp;
+                            }
                         }
-                        Rv[q] = Rp; Gv8[q] = Gp; Bv[q] = Bp;
                     }
                     // Phase 2, rare and divergent: the reference's own arithmetic (double, true division, invalid-pixel
                     // rules).  Its result is final (clamped, shifted); shifted back it passes the common tail unchanged.
