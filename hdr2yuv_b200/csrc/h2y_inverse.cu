@@ -353,9 +353,11 @@ __global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
 
 #pragma unroll 1
                 for (int half = 0; half < 2; half++) {                  // not unrolled: the instruction cache is the limit
-                    u64 d[4];                                           // selects, not a run-time array index (no local memory)
+                    // both passes read dv[0] / yrow[0]; the second row moves down at the end of the first pass
+                    // (12 moves per chroma row instead of 12 selects per luma row, and no run-time array index)
+                    u64 d[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) d[i] = half ? dv[1][i] : dv[0][i];
+                    for (int i = 0; i < 4; i++) d[i] = dv[0][i];
                     // ---- horizontal: even x copies, odd x 6-tap over columns i-2 .. i+3 (yuv2tiff.cpp:655-683) ----
                     u64 cpx[8];
 #pragma unroll
@@ -384,11 +386,14 @@ __global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
 #pragma unroll
                         for (int i = 0; i < 4; i++) cpx[2 * i + 1] = d[i];
                     }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) dv[0][i] = dv[1][i];
+                    const uint4 yr = yrow[0];
+                    yrow[0] = yrow[1];
                     if (!lane_interior) continue;
                     // ---- eight pixels of luma row 2c + half ----
                     // Phase 1, branch-free: the colour difference inverse as integers Rp/Gp/Bp (before the output clamp
                     // and shift) plus one bit per pixel that needs the reference-exact routine.
-                    const uint4 yr = half ? yrow[1] : yrow[0];
                     unsigned yw[4] = {yr.x, yr.y, yr.z, yr.w};
                     if (!C::full_range(A)) {                                                  // yuv2tiff.cpp:283-294
                         const unsigned lo2 = C::minVR(A) * 0x10001u, hi2 = C::maxVR(A) * 0x10001u;
@@ -426,7 +431,8 @@ __global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
                                 // guarded (a floor changed inside the band) or negative (bit 22 of MAGIC_BITS + n clear)
                                 const bool slow = (((B1[e] ^ B2[e]) | (R1[e] ^ R2[e]) | (G1[e] ^ G2[e])) != 0) | (((B1[e] & R1[e] & G1[e]) & 0x00400000) == 0);
                                 if (slow) slow_mask |= 1u << (q + e);
-                                Bv[q + e] = Bc[e] - MAGIC_BITS; Rv[q + e] = Rc[e] - MAGIC_BITS; Gv8[q + e] = min(G1[e], hi_bits) - MAGIC_BITS;
+                                // still biased by MAGIC_BITS, whose low half is zero: phase 3 packs the low halves
+                                Bv[q + e] = Bc[e]; Rv[q + e] = Rc[e]; Gv8[q + e] = min(G1[e], hi_bits);
                             }
                         } else {
 #pragma unroll
