@@ -400,15 +400,15 @@ __global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
 #pragma unroll
                         for (int i = 0; i < 4; i++) yw[i] = clamp_u16x2(yw[i], lo2, hi2);
                     }
-                    int Yv[8], Rv[8], Gv8[8], Bv[8];
+                    int Rv[8], Gv8[8], Bv[8];
                     unsigned slow_mask = MODE == 0 ? 0xffu : 0u;
 #pragma unroll
                     for (int q = 0; q < 8; q += 2) {                     // two pixels at a time: one luma word
-                        const unsigned Y0 = yw[q >> 1] & 0xffffu, Y1 = yw[q >> 1] >> 16;
-                        Yv[q] = (int)Y0; Yv[q + 1] = (int)Y1;
                         if (MODE == 1) {
-                            // B', R' on the {Cb,Cr} pair of each pixel, G' on the pixel pair: all packed
-                            const u64 Yf2 = fadd2(pk(__uint_as_float(0x4B000000u | Y0), __uint_as_float(0x4B000000u | Y1)), pk(-TWO23, -TWO23));
+                            // B', R' on the {Cb,Cr} pair of each pixel, G' on the pixel pair: all packed.
+                            // One PRMT per pixel builds the float 2^23 + Y from the luma word.
+                            const u64 Yf2 = fadd2(pk(__uint_as_float(__byte_perm(yw[q >> 1], 0x4B000000u, 0x7610)),
+                                                     __uint_as_float(__byte_perm(yw[q >> 1], 0x4B000000u, 0x7632))), pk(-TWO23, -TWO23));
                             const u64 Yg2 = fadd2(Yf2, pk(-G, -G));
                             int B1[2], R1[2], B2[2], R2[2], Bc[2], Rc[2];
 #pragma unroll
@@ -432,12 +432,14 @@ __global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
                                 const bool slow = (((B1[e] ^ B2[e]) | (R1[e] ^ R2[e]) | (G1[e] ^ G2[e])) != 0) | (((B1[e] & R1[e] & G1[e]) & 0x00400000) == 0);
                                 if (slow) slow_mask |= 1u << (q + e);
                                 // still biased by MAGIC_BITS, whose low half is zero: phase 3 packs the low halves
-                                Bv[q + e] = Bc[e]; Rv[q + e] = Rc[e]; Gv8[q + e] = min(G1[e], hi_bits);
+                                Bv[q + e] = Bc[e]; Rv[q + e] = Rc[e];
+                                // G > Full-1 -> Full-1 (yuv2tiff.cpp:412); the video-range output clamp below is tighter
+                                Gv8[q + e] = C::full_range(A) ? min(G1[e], hi_bits) : G1[e];
                             }
                         } else {
 #pragma unroll
                             for (int e = 0; e < 2; e++) {
-                                const int Y = e ? (int)Y1 : (int)Y0;
+                                const int Y = (int)(e ? yw[q >> 1] >> 16 : yw[q >> 1] & 0xffffu);
                                 int Rp = 0, Gp = 0, Bp = 0;
                                 if (MODE == 2) {                                             // yuv2tiff.cpp:401-402
                                     const int off = Y - (int)(C::Full(A) - 1);
@@ -455,7 +457,7 @@ __global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
                         for (int q = 0; q < 8; q++)
                             if (slow_mask & (1u << q)) {
                                 unsigned R, Gg, B;
-                                invalid += (unsigned)inv_pixel<MODE == 1 ? H2Y_INV_2020 : (MODE == 2 ? H2Y_INV_YDzDx : -1)>(k, Yv[q], plo(cpx[q]), phi(cpx[q]), R, Gg, B);
+                                invalid += (unsigned)inv_pixel<MODE == 1 ? H2Y_INV_2020 : (MODE == 2 ? H2Y_INV_YDzDx : -1)>(k, (int)((q & 1) ? yw[q >> 1] >> 16 : yw[q >> 1] & 0xffffu), plo(cpx[q]), phi(cpx[q]), R, Gg, B);
                                 Rv[q] = (int)(R >> C::SR(A)); Gv8[q] = (int)(Gg >> C::SR(A)); Bv[q] = (int)(B >> C::SR(A));
                             }
                     }
