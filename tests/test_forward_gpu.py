@@ -256,6 +256,27 @@ def test_rows_kernel_splits_frames_by_lut_fit(ctx, monkeypatch):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("depth", [10, 12])
+def test_rows_kernel_keeps_the_clamp_when_a_frame_can_reach_it(ctx, monkeypatch, depth):
+    # The two-LUT instantiation drops matrix_convert's chroma clamp only for frames whose LUT extremes prove it cannot
+    # bind.  A frame with max in [1, 2) has range (int)max - (int)min = 1, so its normalised samples reach ~1.9 and the
+    # PQ values ~1.07: such frames must take the single-LUT instantiation (clamp kept) inside the same call, next to
+    # ordinary frames that take the clamp-free one.  Saturated primaries make the clamp actually bind.
+    monkeypatch.setenv("H2Y_FORWARD_KERNEL", "rows")
+    w, h = 480, 128
+    dst = dict(bit_depth=depth, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+    frames = [synth.exr_half_frame(w, h, seed=80 + s, channels=3, hi=hi) for s, hi in enumerate((1.9, 4000.0, 1.02, 1.5, 3.7))]
+    sat = frames[0].copy()
+    sat[::2, ::3, 0] = 0x3F99          # R ~ 1.9 next to G = B = 0: Cr far above, Cb far below the legal range
+    sat[::2, ::3, 1:] = 0
+    sat[1::2, 1::3, 2] = 0x3F99        # and the same for B
+    sat[1::2, 1::3, :2] = 0
+    frames.append(sat)
+    got = G.gpu_forward(ctx, frames, _HALF, dst)
+    for i, f in enumerate(frames):
+        G.compare_codes(got[i], G.oracle_forward(f, _HALF, dst), True, "frame %d" % i)
+
+
 @pytest.mark.parametrize("which", ["ring", "rows"])
 def test_unclean_frames_fall_back_to_the_general_kernel(ctx, monkeypatch, which):
     # negative zero, +inf and a different (floor, ceiling) per frame: frames 1 and 2 are not "clean" and must come
