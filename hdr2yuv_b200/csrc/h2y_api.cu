@@ -339,7 +339,6 @@ h2y_status h2y_convert(h2y_ctx *c, const h2y_pic_desc *out, void *const d_out[3]
 {
     if (!c || !out || !in || !d_out || !d_in) return H2Y_ERR_ARG;
     if (in->pic_buffer_type != H2Y_PIC_TYPE_U16 || out->pic_buffer_type != H2Y_PIC_TYPE_U16) return H2Y_ERR_PRECONDITION;
-    if (out->matrix_coeffs == H2Y_MATRIX_YUVPRIME2 && out->chroma_format_idc == H2Y_CHROMA_420) return H2Y_ERR_UNSUPPORTED;
     if (!depth_ok(in->bit_depth)) return H2Y_ERR_ARG;
     const int w = in->width, h = in->height;
     cudaStream_t st = (cudaStream_t)stream;
@@ -348,7 +347,15 @@ h2y_status h2y_convert(h2y_ctx *c, const h2y_pic_desc *out, void *const d_out[3]
     clip_of(in->bit_depth, in->video_full_range_flag, &clip);     // clip of the INPUT picture, convert.cpp:520
     h2y_status s = H2Y_OK;
     const size_t plane = (size_t)w * h * 2;
-    if (out->chroma_format_idc == H2Y_CHROMA_420) {
+    if (out->matrix_coeffs == H2Y_MATRIX_YUVPRIME2 && out->chroma_format_idc == H2Y_CHROMA_420) {
+        // Y'u''v'' (convert.cpp:533-801): the planes are Y', Z, X at 16-bit scale
+        if ((w & 1) || (h & 1) || (resampler != 0 && resampler != 1)) return H2Y_ERR_ARG;
+        if (resampler == 0 && ((w & 3) || (h & 3))) return H2Y_ERR_ARG;
+        void *scr;
+        if ((s = scratch_reserve(c, SCR_TMP444, (size_t)w * h * 2 * 3 + 65536 * 2, &scr)) != H2Y_OK) return s;
+        const uint16_t *pin[3] = {(const uint16_t *)d_in[0], (const uint16_t *)d_in[1], (const uint16_t *)d_in[2]};
+        s = launch_yuvprime2_420(c, pin, (uint16_t *)d_out[1], (uint16_t *)d_out[2], (uint16_t *)scr, w, h, resampler, clip.maxCV, st);
+    } else if (out->chroma_format_idc == H2Y_CHROMA_420) {
         if ((w & 1) || (h & 1)) return H2Y_ERR_ARG;
         if (resampler == 0) {
             if ((w & 3) || (h & 3)) return H2Y_ERR_ARG;
@@ -475,7 +482,6 @@ static h2y_status forward_validate(const h2y_forward_params *p, h2y_pic_desc *tm
     h2y_status st = make_pixk(s, *tmp, d.bit_depth, d.video_full_range_flag, p->clip_on_load, k);
     if (st != H2Y_OK) return st;
     if (k->down_shift < 0) return H2Y_ERR_BIT_DEPTH;
-    if (d.matrix_coeffs == H2Y_MATRIX_YUVPRIME2 && d.chroma_format_idc == H2Y_CHROMA_420) return H2Y_ERR_UNSUPPORTED;
     if (d.chroma_format_idc == H2Y_CHROMA_420) {
         if ((s.width & 1) || (s.height & 1)) return H2Y_ERR_ARG;
         if (p->chroma_resampler_type == 0 && ((s.width & 3) || (s.height & 3))) return H2Y_ERR_ARG;

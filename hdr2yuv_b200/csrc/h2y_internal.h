@@ -85,6 +85,8 @@ h2y_status launch_fir_420(h2y_ctx_impl *c, const uint16_t *d_src, uint16_t *d_ds
 h2y_status launch_fir_422(h2y_ctx_impl *c, const uint16_t *d_src, uint16_t *d_dst, int w, int h, unsigned maxCV,
                           cudaStream_t st);
 h2y_status launch_box_420(h2y_ctx_impl *c, const uint16_t *d_src, uint16_t *d_dst, int w, int h, cudaStream_t st);
+h2y_status launch_yuvprime2_420(h2y_ctx_impl *c, const uint16_t *const d_in[3], uint16_t *d_u, uint16_t *d_v, uint16_t *scratch,
+                                int w, int h, int resampler, unsigned maxCV, cudaStream_t st);
 h2y_status launch_out_clamp(h2y_ctx_impl *c, uint16_t *d_plane, size_t n, int shift, unsigned lo, unsigned hi,
                             cudaStream_t st);
 h2y_status launch_upsample(h2y_ctx_impl *c, const uint16_t *d_src, uint16_t *d_dst, uint16_t *d_mid, int w, int h,

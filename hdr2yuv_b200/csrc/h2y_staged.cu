@@ -216,6 +216,66 @@ h2y_status launch_box_420(h2y_ctx_impl *c, const uint16_t *d_src, uint16_t *d_ds
     return H2Y_OK;
 }
 
+// ---- Y'u''v'' 4:2:0 (convert.cpp:533-801) ------------------------------------------------------------
+// Stage 1: linear Y from the rho-gamma coded 16-bit luma (561-596).  One table entry per code, built on the fly:
+// the function of a single 16-bit value is evaluated once per code (FP64 pow), then the plane is a gather.
+__global__ void __launch_bounds__(256) k_prime2_lut(uint16_t *lut)
+{
+    const unsigned code = blockIdx.x * blockDim.x + threadIdx.x;
+    const float gamma_Y = __double2float_rn(__ddiv_rn((double)(float)code, 65535.0));
+    const float Y_f = tf_rho_eotf(gamma_Y);
+    lut[code] = (uint16_t)d2i_x86(__dmul_rn((double)Y_f, 65535.0));
+}
+
+__global__ void __launch_bounds__(256) k_prime2_linear_y(const uint16_t *__restrict__ y, const uint16_t *__restrict__ lut,
+                                                         uint16_t *__restrict__ lin, long n)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lin[i] = __ldg(lut + y[i]);
+}
+
+// Stage 3: u' = 4X/(X+15Y+3Z), v' = 9Y/(X+15Y+3Z) on the subsampled planes, clipped to [0,1], 16-bit (662-753).
+// The reference then replaces u'',v'' by u',v' ("HACK", 732-734), so the coded luma and the 0.25 floor drop out.
+__global__ void __launch_bounds__(256) k_prime2_uv(const uint16_t *__restrict__ sX, const uint16_t *__restrict__ sY,
+                                                   const uint16_t *__restrict__ sZ, uint16_t *__restrict__ u,
+                                                   uint16_t *__restrict__ v, long n)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double X = __ddiv_rn((double)sX[i], 65535.0), Z = __ddiv_rn((double)sZ[i], 65535.0), Y = __ddiv_rn((double)sY[i], 65535.0);
+    const double sum = __dadd_rn(__dadd_rn(X, __dmul_rn(15.0, Y)), __dmul_rn(3.0, Z));
+    double up = 0.0, vp = 0.0;
+    if (sum > 0.0) { up = __ddiv_rn(__dmul_rn(4.0, X), sum); vp = __ddiv_rn(__dmul_rn(9.0, Y), sum); }
+    up = up < 0.0 ? 0.0 : up; vp = vp < 0.0 ? 0.0 : vp;
+    up = up > 1.0 ? 1.0 : up; vp = vp > 1.0 ? 1.0 : vp;
+    u[i] = (uint16_t)d2i_x86(__dmul_rn(up, 65535.0));
+    v[i] = (uint16_t)d2i_x86(__dmul_rn(vp, 65535.0));
+}
+
+// d_in: the 4:4:4 planes Y', Z, X (plane 1 is Z, plane 2 is X: convert.cpp:593-594); d_u / d_v: (w/2)x(h/2).
+// scratch: 4 planes of w*h u16 (linear Y, three subsampled planes sharing one, FIR intermediate) + the 128 KiB table.
+h2y_status launch_yuvprime2_420(h2y_ctx_impl *c, const uint16_t *const d_in[3], uint16_t *d_u, uint16_t *d_v, uint16_t *scratch,
+                                int w, int h, int resampler, unsigned maxCV, cudaStream_t st)
+{
+    const long n = (long)w * h, nc = (long)(w / 2) * (h / 2);
+    uint16_t *lin = scratch, *sub = scratch + n, *mid = scratch + 2 * n, *lut = scratch + 3 * n;
+    uint16_t *sY = sub, *sZ = sub + nc, *sX = sub + 2 * nc;
+    k_prime2_lut<<<256, 256, 0, st>>>(lut);
+    k_prime2_linear_y<<<(int)((n + 255) / 256), 256, 0, st>>>(d_in[0], lut, lin, n);
+    c->launches += 2;
+    const uint16_t *src[3] = {lin, d_in[1], d_in[2]};
+    uint16_t *dst[3] = {sY, sZ, sX};
+    for (int p = 0; p < 3; p++) {
+        h2y_status s = resampler == 0 ? launch_box_420(c, src[p], dst[p], w, h, st)
+                                      : launch_fir_420(c, src[p], dst[p], mid, w, h, maxCV, st);
+        if (s != H2Y_OK) return s;
+    }
+    k_prime2_uv<<<(int)((nc + 255) / 256), 256, 0, st>>>(sX, sY, sZ, d_u, d_v, nc);
+    c->launches++;
+    H2Y_CUDA(c, cudaGetLastError());
+    return H2Y_OK;
+}
+
 // ---- write_yuv compute stage (tiff.cpp:457-550) ---------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_out_clamp(uint16_t *p, size_t n, int shift, unsigned lo, unsigned hi)

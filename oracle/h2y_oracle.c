@@ -381,7 +381,43 @@ int orc_convert(orc_pic_t *out, const orc_pic_t *in, int resampler)
     orc_clip_t clip;
     orc_set_clip(in->bit_depth, in->video_full_range_flag, &clip);      /* clip of the INPUT pic, 520 */
     const int w = in->width, h = in->height;
-    if (out->chroma_format_idc == ORC_CHROMA_420) {
+    if (out->matrix_coeffs == ORC_MATRIX_YUVPRIME2 && out->chroma_format_idc == ORC_CHROMA_420) {
+        /* Y'u''v'' (convert.cpp:533-801).  The 16-bit source planes are Y' (rho-gamma coded), Z, X.  Linear Y from
+         * the EOTF, four planes subsampled, then u' = 4X/(X+15Y+3Z), v' = 9Y/(X+15Y+3Z) per 4:2:0 sample.  The
+         * reference overwrites u'',v'' with u',v' ("HACK", 732-734), so the Y' plane and the 0.25 floor never enter. */
+        if (resampler != 0 && resampler != 1) return 5;            /* neither branch runs: planes stay unwritten */
+        const size_t n = (size_t)w * h;
+        uint16_t *linY = (uint16_t *)malloc(n * 2), *sY = (uint16_t *)malloc(n * 2), *sZ = (uint16_t *)malloc(n * 2),
+                 *sX = (uint16_t *)malloc(n * 2);
+        for (size_t i = 0; i < n; i++) {                           /* 561-596 */
+            float gamma_Y = ((float)in->buf[0][i]) / 65535.0;      /* float / double -> double -> float */
+            float Y_f = orc_rho_gamma_eotf(gamma_Y);
+            linY[i] = (unsigned short)(Y_f * 65535.0);
+        }
+        if (resampler == 1) {                                      /* 600-631 */
+            orc_subsample_fir(sY, linY, w, h, clip.minCV, clip.maxCV);
+            orc_subsample_fir(sZ, in->buf[1], w, h, clip.minCV, clip.maxCV);
+            orc_subsample_fir(sX, in->buf[2], w, h, clip.minCV, clip.maxCV);
+        } else {
+            orc_subsample_box(sY, linY, w, h);
+            orc_subsample_box(sZ, in->buf[1], w, h);
+            orc_subsample_box(sX, in->buf[2], w, h);
+        }
+        const long nc = (long)(w / 2) * (h / 2);
+        for (long i = 0; i < nc; i++) {                            /* 662-753 */
+            double X = ((double)sX[i]) / 65535.0, Z = ((double)sZ[i]) / 65535.0, Y = ((double)sY[i]) / 65535.0;
+            double sum = (X + 15.0 * Y + 3.0 * Z);
+            double u_prime = 0.0, v_prime = 0.0;
+            if (sum > 0.0) { u_prime = 4.0 * X / sum; v_prime = 9.0 * Y / sum; }
+            u_prime = u_prime < 0.0 ? 0.0 : u_prime;
+            v_prime = v_prime < 0.0 ? 0.0 : v_prime;
+            u_prime = u_prime > 1.0 ? 1.0 : u_prime;
+            v_prime = v_prime > 1.0 ? 1.0 : v_prime;
+            out->buf[1][i] = (unsigned short)(u_prime * 65535.0);
+            out->buf[2][i] = (unsigned short)(v_prime * 65535.0);
+        }
+        free(linY); free(sY); free(sZ); free(sX);
+    } else if (out->chroma_format_idc == ORC_CHROMA_420) {
         for (int c = 1; c < 3; c++) {
             if (resampler == 0) orc_subsample_box(out->buf[c], in->buf[c], w, h);
             else orc_subsample_fir(out->buf[c], in->buf[c], w, h, clip.minCV, clip.maxCV);

@@ -30,6 +30,11 @@ _add("tiff_422_m9", "tiff16", _TIFF,
 for tr in (1, 8, 18):
     _add(f"tiff_transfer16to{tr}", "tiff16", dict(_TIFF, primaries=9),
          dict(bit_depth=10, full_range=0, transfer=tr, primaries=9, matrix=9, chroma=1, resampler=1))
+# Y'u''v'' 4:2:0 (convert.cpp:533-801): rho-gamma coded 16-bit source, libm pow on the luma plane
+_add("tiff_prime2_fir_b16", "tiff16", dict(_TIFF, transfer=18, full_range=1),
+     dict(bit_depth=16, full_range=1, transfer=18, primaries=10, matrix=15, chroma=1, resampler=1))
+_add("tiff_prime2_box_b12", "tiff16", dict(_TIFF, transfer=18),
+     dict(bit_depth=12, full_range=0, transfer=18, primaries=10, matrix=15, chroma=1, resampler=0))
 _HALF = dict(bit_depth=32, full_range=1, transfer=8, primaries=1, matrix=0)
 for m in (9, 11, 1, 13):
     for bd in (10, 12):

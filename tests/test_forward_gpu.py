@@ -16,7 +16,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _uses_transfer(src, dst):
-    return src["transfer"] != dst["transfer"]
+    # libm on the path (transfer change, or the rho-gamma EOTF inside Y'u''v''): <= 1 code, deviations counted
+    return src["transfer"] != dst["transfer"] or (dst["matrix"] == 15 and dst["chroma"] == 1)
 
 
 @pytest.mark.parametrize("name,src,dst", cases.FORWARD_CASES, ids=[c[0] for c in cases.FORWARD_CASES])
