@@ -45,7 +45,7 @@ class ForwardParams(C.Structure):
 
 class InverseParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bit_depth", C.c_int32), ("matrix", C.c_int32),
-                ("fir", C.c_int32), ("full_range", C.c_int32), ("alpha", C.c_int32)]
+                ("fir", C.c_int32), ("full_range", C.c_int32), ("alpha", C.c_int32), ("ybar", C.c_int32)]
 
 
 _P3 = C.c_void_p * 3
@@ -107,7 +107,7 @@ def lib():
             fn = getattr(l, name)          # AttributeError if the header and the library disagree
             fn.restype = res
             fn.argtypes = args
-        if l.h2y_abi_version() != 1:
+        if l.h2y_abi_version() != 2:
             raise ImportError("hdr2yuv_b200: ABI version mismatch")
         _lib = l
     return _lib

@@ -1,6 +1,6 @@
 // yuv2tiff -- command-line host of the inverse path with the reference's keyword surface
 // (yuv2tiff.cpp:106-198): yuv2tiff <in.yuv> [B10|B14] [709|2020|Y100|Y500] [HD1920|HD960] [BOX] [FULL] [ALPHA]
-// [-f frames] [-I].  Frames of planar 4:2:0 u16 go to the GPU through h2y_inverse_host; each frame is written
+// [-f frames] [-I] [-X] [YUVPRIME2].  Frames of planar 4:2:0 u16 go to the GPU through h2y_inverse_host; each frame is written
 // as tifXYZ/XpYpZp%05d.tif (16-bit RGB, one strip per row), as the reference does (yuv2tiff.cpp:322-342).
 //
 // Beyond the reference: -d N shards the frames over N GPUs, -o DIR changes the output directory.  The
@@ -50,10 +50,9 @@ int main(int argc, char *argv[])
         else if (!strcmp(k, "-f") && arg + 1 < argc) frames = atoi(argv[++arg]);
         else if (!strcmp(k, "-d") && arg + 1 < argc) devices = atoi(argv[++arg]);
         else if (!strcmp(k, "-o") && arg + 1 < argc) outdir = argv[++arg];
-        else if (!strcmp(k, "YUVPRIME2") || !strcmp(k, "-X")) {
-            printf("%s: %s\n", k, h2y_status_string(H2Y_ERR_UNSUPPORTED));
-            return 1;
-        }
+        else if (!strcmp(k, "-X")) ip.ybar = 1;                  // Ybar reconstruction inside Y'DzDx (yuv2tiff.cpp:162, 365-399)
+        else if (!strcmp(k, "YUVPRIME2"))                        // sets a flag no reachable branch tests: DXYZ stays 1 (86, 159, 389)
+            printf("Processing for Y'u''v'' (Y=rho-gamma, u'',v'' = linear)\n");
     }
     if (ip.matrix == H2Y_INV_709) printf("Processing for Rec709\n");
     if (ip.matrix == H2Y_INV_2020) printf("Processing for Rec2020\n");

@@ -112,7 +112,7 @@ h2y_status launch_forward_fused(h2y_ctx_impl *c, const h2y_forward_params &p, co
                                 const FrameK *d_framek, const float *d_luts, cudaStream_t st, int skip_clean = 0);
 
 struct InvK {
-    int w, h, bit_depth, matrix, fir, full_range, alpha;
+    int w, h, bit_depth, matrix, fir, full_range, alpha, ybar;
     int SR;
     unsigned Half, Full, maxCV;
     unsigned minVR, maxVR, minVRC, maxVRC;

@@ -35,16 +35,27 @@ __device__ __forceinline__ float up_fin(float t, float hi)
 
 // per-pixel inverse colour difference (yuv2tiff.cpp:399-430, 478-544); returns invalid count
 // MKIND: -1 = decide at run time from k.matrix; H2Y_INV_* = compiled for that family only (smaller code)
+// Ybar > 0: the -X mode, Y'DzDx rebuilt around the 2x2 luma mean and rescaled by Y'/Ybar (yuv2tiff.cpp:390-398)
 template <int MKIND = -1>
 __device__ __forceinline__ int inv_pixel(const InvK &k, int Y, float fcb, float fcr, unsigned &Ro, unsigned &Go,
-                                         unsigned &Bo)
+                                         unsigned &Bo, int Ybar = 0)
 {
     const int matrix = MKIND < 0 ? k.matrix : MKIND;
     int Yav = Y, Rp, Bp;
     const int Ysave = Y;
     const double top = (double)k.Full - 1.0;
     const double halfm = (double)k.Half - 0.5;
-    if (matrix == H2Y_INV_YDzDx) {
+    if (matrix == H2Y_INV_YDzDx && Ybar > 0) {
+        // all operands are small integers in double: the sums and the product are exact, the division rounds once,
+        // then the reference stores to float and truncates
+        const double fm1 = (double)(float)((double)k.Full - 1.0), yb = (double)(float)Ybar, ya = (double)(float)Yav;
+        float RED = __double2float_rn(__ddiv_rn(__dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(2.0, (double)fcr), -fm1), yb), ya), yb));
+        float BLUE = __double2float_rn(__ddiv_rn(__dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(2.0, (double)fcb), -fm1), yb), ya), yb));
+        if ((double)RED > (double)k.Full - 1.5) RED = (float)((double)k.Full - 1.0);
+        if ((double)BLUE > (double)k.Full - 1.5) BLUE = (float)((double)k.Full - 1.0);
+        Rp = f2i_x86(RED);
+        Bp = f2i_x86(BLUE);
+    } else if (matrix == H2Y_INV_YDzDx) {
         Rp = 2 * (int)fcr - (int)(k.Full - 1) + Yav;
         Bp = 2 * (int)fcb - (int)(k.Full - 1) + Yav;
     } else if (matrix == H2Y_INV_2020 || matrix == H2Y_INV_709) {
@@ -146,6 +157,11 @@ k_inverse_fused(InvK k, const uint16_t *__restrict__ yuv, size_t yuv_stride_elem
     if (x < w && y < h) {
         const uint4 yv = *reinterpret_cast<const uint4 *>(fy + (size_t)y * w + x);
         const unsigned yw[4] = {yv.x, yv.y, yv.z, yv.w};
+        unsigned yo[4] = {0, 0, 0, 0};             // the other row of the 2x2 luma blocks (-X only)
+        if (k.ybar) {
+            const uint4 t = *reinterpret_cast<const uint4 *>(fy + (size_t)(y ^ 1) * w + x);
+            yo[0] = t.x; yo[1] = t.y; yo[2] = t.z; yo[3] = t.w;
+        }
         unsigned outw[16];   // up to 8 px * 4 samples, packed 2 per word
         constexpr int nch = ALPHA ? 4 : 3;
         unsigned short samples[32];
@@ -174,8 +190,20 @@ k_inverse_fused(InvK k, const uint16_t *__restrict__ yuv, size_t yuv_stride_elem
                 cb = s_src[0][(ty >> 1) + 3][ci];
                 cr = s_src[1][(ty >> 1) + 3][ci];
             }
+            int Ybar = 0;
+            if (k.ybar) {                                 // yuv2tiff.cpp:365-387: mean of the clamped 2x2 block, in [1, Full-1]
+                unsigned b4[4] = {yw[q >> 1] & 0xffffu, yw[q >> 1] >> 16, yo[q >> 1] & 0xffffu, yo[q >> 1] >> 16};
+                int sum = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    unsigned v = b4[i];
+                    if (!k.full_range) { v = v < k.minVR ? k.minVR : v; v = v > k.maxVR ? k.maxVR : v; }
+                    sum += (int)v;
+                }
+                Ybar = min(max(sum / 4, 1), (int)k.Full - 1);
+            }
             unsigned R, G, B;
-            invalid += inv_pixel(k, (int)Y, cb, cr, R, G, B);
+            invalid += inv_pixel(k, (int)Y, cb, cr, R, G, B, Ybar);
             samples[q * nch + 0] = (unsigned short)R;
             samples[q * nch + 1] = (unsigned short)G;
             samples[q * nch + 2] = (unsigned short)B;
@@ -502,6 +530,7 @@ h2y_status make_invk(const h2y_inverse_params &p, InvK *k)
     if (p.matrix < H2Y_INV_YDzDx || p.matrix > H2Y_INV_Y500) return H2Y_ERR_ARG;
     k->w = p.width; k->h = p.height; k->bit_depth = p.bit_depth; k->matrix = p.matrix;
     k->fir = p.fir != 0; k->full_range = p.full_range != 0; k->alpha = p.alpha != 0;
+    k->ybar = p.ybar != 0 && p.matrix == H2Y_INV_YDzDx;          // -X only acts inside the Y'DzDx branch (yuv2tiff.cpp:389-399)
     k->SR = 16 - p.bit_depth;                                   // yuv2tiff.cpp:89, 139, 150
     k->Half = 1u << (p.bit_depth - 1);
     k->Full = 1u << p.bit_depth;
@@ -536,7 +565,7 @@ h2y_status launch_inverse(h2y_ctx_impl *c, const InvK &k, const void *d_yuv, siz
         A.guard = 1.0f / (float)(1 << (21 - k.bit_depth));          // same bound as the forward kernel
         const long rows_per_worker = A.total_crows / ((long)c->sm_count * A.sub);
         const char *force = getenv("H2Y_INVERSE_KERNEL");           // "tile" / "rows": tests and experiments
-        const bool want_rows = force ? force[0] == 'r' : rows_per_worker >= 48;
+        const bool want_rows = !k.ybar && (force ? force[0] == 'r' : rows_per_worker >= 48);     // -X: tile kernel only
         if (want_rows) {
             int grid = c->sm_count;
             while (grid > 1 && A.total_crows / ((long)grid * A.sub) < 4) grid >>= 1;

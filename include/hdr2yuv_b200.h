@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define H2Y_ABI_VERSION 1
+#define H2Y_ABI_VERSION 2
 
 typedef enum h2y_status {
     H2Y_OK = 0,
@@ -213,6 +213,7 @@ typedef struct h2y_inverse_params {
     int32_t fir;            /* 0 when BOX is given (117) */
     int32_t full_range;     /* FULL (118) */
     int32_t alpha;          /* ALPHA: 4 samples per pixel, A = 65535 (119-123, 544) */
+    int32_t ybar;           /* -X: Y'DzDx rebuilt around the 2x2 mean of Y' (162, 365-399); ignored by the other matrices */
 } h2y_inverse_params;
 
 size_t h2y_rgb_frame_bytes(const h2y_inverse_params *p);   /* W*H*(3|4)*2 */

@@ -651,7 +651,21 @@ long orc_yuv2tiff_frame(const orc_inv_params *p, const uint16_t *yuv, uint16_t *
         int Rp, Bp;
         const float fcb = (float)cb4[i], fcr = (float)cr4[i];
         const double top = Full - 1.0;
-        if (p->matrix == ORC_INV_YDZDX) {                               /* 399-402 */
+        if (p->matrix == ORC_INV_YDZDX && p->ybar) {                    /* -X: 365-399 */
+            /* mean of the 2x2 luma block this pixel belongs to, clamped to [1, Full-1] */
+            const size_t x = i % (size_t)w, y = i / (size_t)w, bx = x & ~(size_t)1, by = y & ~(size_t)1;
+            int Ybar = (int)Yp[by * w + bx] + (int)Yp[by * w + bx + 1] + (int)Yp[(by + 1) * w + bx] + (int)Yp[(by + 1) * w + bx + 1];
+            Ybar = Ybar / 4;
+            if (Ybar < 1) Ybar = 1;
+            if (Ybar > (Full - 1)) Ybar = Full - 1;
+            float RED, BLUE;
+            RED = (2.0 * (float)(cr4[i]) - (float)(Full - 1.0) + (float)Ybar) * ((float)Yav) / ((float)Ybar);
+            BLUE = (2.0 * (float)(cb4[i]) - (float)(Full - 1.0) + (float)Ybar) * ((float)Yav) / ((float)Ybar);
+            if (RED > (Full - 1.5)) RED = Full - 1.0;
+            if (BLUE > (Full - 1.5)) BLUE = Full - 1.0;
+            Rp = RED;
+            Bp = BLUE;
+        } else if (p->matrix == ORC_INV_YDZDX) {                        /* 399-402 */
             Rp = 2 * (int)cr4[i] - (int)top + Yav;
             Bp = 2 * (int)cb4[i] - (int)top + Yav;
         } else if (p->matrix == ORC_INV_2020 || p->matrix == ORC_INV_709) {   /* 403-423 */

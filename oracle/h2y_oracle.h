@@ -113,6 +113,7 @@ typedef struct {
     int fir;             /* 0 when BOX given (yuv2tiff.cpp:117) */
     int full_range;      /* FULL keyword */
     int alpha;           /* ALPHA keyword: 4 samples per pixel, A=65535 */
+    int ybar;            /* -X keyword: Y'DzDx rebuilt around the 2x2 mean of Y' (yuv2tiff.cpp:162, 365-399) */
 } orc_inv_params;
 /* one loop iteration of yuv2tiff main (yuv2tiff.cpp:278-552): yuv = Y,Cb,Cr 4:2:0 planes;
  * rgb = interleaved R,G,B(,A) 16-bit rows.  Returns the invalidPixels count. */

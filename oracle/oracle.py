@@ -45,7 +45,7 @@ class _Dst(C.Structure):
 
 class _Inv(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("bit_depth", C.c_int), ("matrix", C.c_int),
-                ("fir", C.c_int), ("full_range", C.c_int), ("alpha", C.c_int)]
+                ("fir", C.c_int), ("full_range", C.c_int), ("alpha", C.c_int), ("ybar", C.c_int)]
 
 
 def _build():
@@ -240,7 +240,7 @@ def load_half(px):
     return planes
 
 
-def yuv2tiff(yuv, w, h, bit_depth=12, matrix=INV_YDZDX, fir=True, full_range=False, alpha=False, backend="port"):
+def yuv2tiff(yuv, w, h, bit_depth=12, matrix=INV_YDZDX, fir=True, full_range=False, alpha=False, backend="port", ybar=False):
     """One 4:2:0 frame (flat u16 Y,Cb,Cr) -> (H,W,3|4) interleaved RGB16.  Returns (rgb, invalid_pixels)."""
     yuv = np.ascontiguousarray(yuv, np.uint16)
     nch = 4 if alpha else 3
@@ -248,7 +248,8 @@ def yuv2tiff(yuv, w, h, bit_depth=12, matrix=INV_YDZDX, fir=True, full_range=Fal
         # the reference program only knows 3840x2160 / 1920x1080 / 960x540 (yuv2tiff.cpp:188-198)
         size_kw = {(3840, 2160): None, (1920, 1080): "HD1920", (960, 540): "HD960"}[(w, h)]
         args = [k for k in (size_kw, {10: "B10", 12: None, 14: "B14"}[bit_depth], _INV_KEYWORD[matrix],
-                            None if fir else "BOX", "FULL" if full_range else None, "ALPHA" if alpha else None) if k]
+                            None if fir else "BOX", "FULL" if full_range else None, "ALPHA" if alpha else None,
+                            "-X" if ybar else None) if k]
         exe = os.path.join(HERE, "_ref", "yuv2tiff_ref")
         with tempfile.TemporaryDirectory() as d:
             os.mkdir(os.path.join(d, "tifXYZ"))
@@ -259,7 +260,7 @@ def yuv2tiff(yuv, w, h, bit_depth=12, matrix=INV_YDZDX, fir=True, full_range=Fal
             rgb = np.fromfile(os.path.join(d, "tifXYZ", "XpYpZp00000.tif"), np.uint16).reshape(h, w, nch)
         invalid = [int(l.split(":")[1]) for l in text.splitlines() if l.startswith("Invalid Pixels:")]
         return rgb, (invalid[0] if invalid else -1)
-    p = _Inv(w, h, bit_depth, matrix, int(fir), int(full_range), int(alpha))
+    p = _Inv(w, h, bit_depth, matrix, int(fir), int(full_range), int(alpha), int(ybar))
     rgb = np.zeros((h, w, nch), np.uint16)
     inv = port_lib().orc_yuv2tiff_frame(C.byref(p), _ptr(yuv), _ptr(rgb))
     return rgb, int(inv)

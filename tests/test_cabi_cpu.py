@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for n in names:
         assert hasattr(lib, n), "header declares %s but the library does not export it" % n
     assert sorted(cabi.SYMBOLS) == names, "ctypes binding and header disagree"
-    assert cabi.lib().h2y_abi_version() == 1
+    assert cabi.lib().h2y_abi_version() == 2
 
 
 def test_clip_limits_match_oracle(built_lib):

@@ -14,8 +14,8 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def gpu_inverse(ctx, yuvs, w, h, bd, m, fir, fr, al):
-    p = cabi.InverseParams(w, h, bd, m, fir, fr, al)
+def gpu_inverse(ctx, yuvs, w, h, bd, m, fir, fr, al, ybar=0):
+    p = cabi.InverseParams(w, h, bd, m, fir, fr, al, ybar)
     n = len(yuvs)
     d_yuv = G.to_dev(np.stack(yuvs, 0))
     nch = 4 if al else 3
@@ -38,6 +38,33 @@ def test_inverse_matches_golden(ctx, golden_inverse, case, kernel, monkeypatch):
     assert np.array_equal(rgb[0][:2], golden_inverse[key + "/head"])
     assert hashlib.sha256(rgb[0].tobytes()).digest() == golden_inverse[key + "/sha256"].tobytes()
     assert int(inv[0]) == int(golden_inverse[key + "/invalid"][0])
+
+
+@pytest.mark.parametrize("kernel", ["tile", "rows"])
+@pytest.mark.parametrize("bd,fir,fr,al", [(12, 1, 0, 0), (10, 0, 0, 1), (14, 1, 1, 0)])
+def test_ybar_mode_matches_oracle(ctx, kernel, bd, fir, fr, al, monkeypatch):
+    # yuv2tiff -X (yuv2tiff.cpp:365-399): Y'DzDx rebuilt around the 2x2 luma mean.  The oracle's restatement is pinned
+    # against the reference binary in test_oracle_cpu.  Random luma next to mid-range chroma produces many negative
+    # (invalid) pixels and values above Full-1.5, so every branch of the mode is taken.  A forced "rows" request still
+    # runs the tile kernel (the only one with this mode); with a 709 matrix the flag is inert, as in the reference.
+    monkeypatch.setenv("H2Y_INVERSE_KERNEL", kernel)
+    w, h = 264, 70
+    rng = np.random.default_rng(bd)
+    top = (1 << bd) - 1
+    yuvs = []
+    for s in range(2):
+        y = rng.integers(0, top + 1, w * h, dtype=np.uint16)
+        y[:40] = 0
+        c = rng.integers(top // 4, 3 * top // 4, w * h // 2, dtype=np.uint16)
+        yuvs.append(np.concatenate([y, c]))
+    rgb, inv = gpu_inverse(ctx, yuvs, w, h, bd, O.INV_YDZDX, fir, fr, al, ybar=1)
+    for i, y in enumerate(yuvs):
+        want, winv = O.yuv2tiff(y, w, h, bd, O.INV_YDZDX, bool(fir), bool(fr), bool(al), ybar=True)
+        assert np.array_equal(rgb[i], want), (kernel, bd, i)
+        assert int(inv[i]) == winv
+    plain, _ = gpu_inverse(ctx, yuvs[:1], w, h, bd, O.INV_709, fir, fr, al, ybar=0)
+    inert, _ = gpu_inverse(ctx, yuvs[:1], w, h, bd, O.INV_709, fir, fr, al, ybar=1)
+    assert np.array_equal(plain, inert)
 
 
 def _yuv_for(w, h, seed, bd, matrix_fwd):

@@ -142,3 +142,25 @@ def test_matrix_inverse_port_vs_reference():
     for m in (1, 9, 11):
         pl = rng.integers(0, 4096, (3, 33, 50), dtype=np.uint16)
         assert np.array_equal(O.matrix_inverse(pl, m, 12, 0, 16, "port")[0], O.matrix_inverse(pl, m, 12, 0, 16, "ref")[0])
+
+
+@needs_ref
+def test_ybar_mode_and_yuvprime2_keyword_vs_reference_binary():
+    # yuv2tiff -X (yuv2tiff.cpp:162, 365-399) against the reference's own executable; and Y'u''v'' 4:2:0 of the
+    # forward chain (convert.cpp:533-801) against the reference's convert()
+    w, h = 960, 540
+    rng = np.random.default_rng(11)
+    for bd, full, fir in ((12, False, True), (10, False, False)):
+        top = (1 << bd) - 1
+        y = rng.integers(0, top + 1, w * h, dtype=np.uint16)
+        y[:50] = 0
+        c = rng.integers(top // 4, 3 * top // 4, w * h // 2, dtype=np.uint16)
+        yuv = np.concatenate([y, c])
+        a, ia = O.yuv2tiff(yuv, w, h, bit_depth=bd, fir=fir, full_range=full, backend="ref", ybar=True)
+        b, ib = O.yuv2tiff(yuv, w, h, bit_depth=bd, fir=fir, full_range=full, backend="port", ybar=True)
+        assert np.array_equal(a, b) and ia == ib
+    planes = rng.integers(0, 65536, (3, 36, 64), dtype=np.uint16)
+    src = dict(bit_depth=16, full_range=1, transfer=18, primaries=10, matrix=0)
+    for res, bd, fr in ((1, 16, 1), (0, 12, 0)):
+        dst = dict(bit_depth=bd, full_range=fr, transfer=18, primaries=10, matrix=15, chroma=1, resampler=res)
+        assert np.array_equal(O.forward(planes, src, dst, backend="ref"), O.forward(planes, src, dst, backend="port"))
