@@ -18,6 +18,7 @@ TRANSFER_PQ, TRANSFER_RHO_GAMMA = 16, 18
 MATRIX_GBR, MATRIX_BT709, MATRIX_BT2020nc, MATRIX_BT2020c = 0, 1, 9, 10
 MATRIX_YDzDx, MATRIX_YDzDx_Y500, MATRIX_YDzDx_Y100, MATRIX_YUVPRIME1, MATRIX_YUVPRIME2 = 11, 12, 13, 14, 15
 LAYOUT_PLANAR_U16, LAYOUT_PLANAR_F32, LAYOUT_RGB16, LAYOUT_RGBA16, LAYOUT_HALF_RGB, LAYOUT_HALF_RGBA = range(6)
+LAYOUT_DPX10_BE, LAYOUT_DPX10_LE = 6, 7
 INV_YDzDx, INV_709, INV_2020, INV_Y100, INV_Y500 = range(5)
 
 

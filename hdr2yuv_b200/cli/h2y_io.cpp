@@ -480,6 +480,77 @@ bool exr_write_half(const std::string &path, const uint16_t *src, int width, int
     return ferror(f.f) ? fail(err, "write error on " + path) : true;
 }
 
+// ---- DPX ---------------------------------------------------------------------------------------------
+namespace {
+uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+uint32_t le32(const uint8_t *p) { return ((uint32_t)p[3] << 24) | ((uint32_t)p[2] << 16) | ((uint32_t)p[1] << 8) | p[0]; }
+}   // namespace
+
+bool dpx_probe(const std::string &path, ImageInfo *info, std::string *err)
+{
+    File f(path, "rb");
+    if (!f.f) return fail(err, "Cannot open dpx input file " + path);
+    uint8_t h[2048];
+    if (!f.read_at(h, sizeof(h), 0)) return fail(err, path + ": shorter than a dpx header");
+    const bool be = !memcmp(h, "SDPX", 4), le = !memcmp(h, "XPDS", 4);
+    if (!be && !le) return fail(err, path + ": bad magic number in dpx header");
+    auto u32 = [&](int off) { return be ? be32(h + off) : le32(h + off); };
+    info->big_endian = be;
+    info->data_offset = u32(4);
+    info->width = (int)(int16_t)u32(772);         // dpx_read narrows both to short (dpx.cpp:296-304)
+    info->height = (int)(int16_t)u32(776);
+    info->bits = h[803];
+    info->channels = 3;
+    info->is_half = false;
+    if (info->bits != 10) {
+        char msg[96];
+        snprintf(msg, sizeof(msg), ": dpx packing is %d-bits, only the 10-bit packing is served", info->bits);
+        return fail(err, path + msg);
+    }
+    if (info->width < 1 || info->height < 1) return fail(err, path + ": bad dpx picture size");
+    return true;
+}
+
+bool dpx_read_words(const std::string &path, uint32_t *dst, ImageInfo *info, std::string *err)
+{
+    if (!dpx_probe(path, info, err)) return false;
+    File f(path, "rb");
+    if (!f.f) return fail(err, "Cannot open dpx input file " + path);
+    if (!f.read_at(dst, (size_t)info->width * info->height * 4, info->data_offset)) return fail(err, "short read from " + path);
+    return true;
+}
+
+bool dpx_write_10bit(const std::string &path, const uint16_t *rgb10, int width, int height, bool big_endian, std::string *err)
+{
+    File f(path, "wb");
+    if (!f.f) return fail(err, "unable to create " + path);
+    std::vector<uint8_t> h(2048, 0);
+    auto put = [&](int off, uint32_t v) {
+        for (int i = 0; i < 4; i++) h[off + i] = (uint8_t)(v >> (big_endian ? 24 - 8 * i : 8 * i));
+    };
+    memcpy(h.data(), big_endian ? "SDPX" : "XPDS", 4);
+    put(4, 2048);                                   // offset to image data
+    memcpy(h.data() + 8, "V1.0", 4);
+    put(16, 2048 + (uint32_t)width * height * 4);   // file size
+    h[768] = 0; h[769] = 0;                         // orientation
+    h[770] = big_endian ? 0 : 1; h[771] = big_endian ? 1 : 0;   // number of image elements = 1
+    put(772, (uint32_t)width);
+    put(776, (uint32_t)height);
+    h[800] = 50;                                    // descriptor: RGB
+    h[803] = 10;                                    // bit size
+    fwrite(h.data(), 1, h.size(), f.f);
+    std::vector<uint8_t> row((size_t)width * 4);
+    for (int y = 0; y < height; y++) {
+        for (int x = 0; x < width; x++) {
+            const uint16_t *px = rgb10 + ((size_t)y * width + x) * 3;
+            const uint32_t w = ((uint32_t)(px[0] & 1023) << 22) | ((uint32_t)(px[1] & 1023) << 12) | ((uint32_t)(px[2] & 1023) << 2);
+            for (int i = 0; i < 4; i++) row[(size_t)x * 4 + i] = (uint8_t)(w >> (big_endian ? 24 - 8 * i : 8 * i));
+        }
+        fwrite(row.data(), 1, row.size(), f.f);
+    }
+    return ferror(f.f) ? fail(err, "write error on " + path) : true;
+}
+
 // ---- raw ---------------------------------------------------------------------------------------------
 uint64_t file_size(const std::string &path)
 {

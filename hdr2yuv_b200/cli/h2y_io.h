@@ -6,6 +6,8 @@
 //         either byte order (tiff.cpp:54-362 reads raw strips the same way); centre cut-outs as tiff.cpp:191-220
 //   EXR   single-part scanline files, HALF (or FLOAT, narrowed to half like Imf::RgbaInputFile) channels R,G,B[,A],
 //         compression NONE / ZIPS / ZIP via zlib (exr.cpp:138-261 goes through RgbaInputFile)
+//   DPX   10-bit packed RGB, one 32-bit word per pixel, either byte order (dpx.cpp:210-360, 506-531); the words go
+//         to the GPU as they are in the file (H2Y_LAYOUT_DPX10_BE / _LE), the unpack and /1023.0 happen there
 //   raw   planar .rgb (R,G,B planes) and .yuv frames of u16 (hdr2yuv.cpp:582-656)
 // Every reader delivers the decoder's natural interleaved layout; the de-interleave to G,B,R planes, the
 // on-read clip and the half->float widening happen on the GPU (h2y_layout).
@@ -22,6 +24,8 @@ struct ImageInfo {
     int channels = 0;          // 3 or 4 (interleaved R,G,B[,A])
     int bits = 0;              // 16
     bool is_half = false;      // EXR: half bit patterns; TIFF: integer codes
+    bool big_endian = false;   // DPX: byte order of the pixel words
+    uint32_t data_offset = 0;  // DPX: offset of the image data
 };
 
 // --- TIFF -----------------------------------------------------------------------------------------------
@@ -40,6 +44,15 @@ bool exr_read_half(const std::string &path, uint16_t *dst, int out_channels, Ima
 // Test helper and --dst .exr is out of scope: writes an uncompressed or ZIP scanline file of HALF channels.
 bool exr_write_half(const std::string &path, const uint16_t *src, int width, int height, int channels, int compression,
                     std::string *err);
+
+// --- DPX ------------------------------------------------------------------------------------------------
+// Header fields dpx_read uses: magic (byte order), image offset at byte 4, width / height at 772 / 776, bit size at
+// 803 (dpx.cpp:268-348).  Only the 10-bit packing is served (16-bit and float DPX are refused with a message).
+bool dpx_probe(const std::string &path, ImageInfo *info, std::string *err);
+// dst: width*height 32-bit words exactly as stored (no byte swap: the layout tells the GPU the order)
+bool dpx_read_words(const std::string &path, uint32_t *dst, ImageInfo *info, std::string *err);
+// Test helper: a 2048-byte generic header + packed words, like dpx_write_10bit_from_float's (dpx.cpp:554-716).
+bool dpx_write_10bit(const std::string &path, const uint16_t *rgb10, int width, int height, bool big_endian, std::string *err);
 
 // --- raw planar -----------------------------------------------------------------------------------------
 // .rgb: planes R,G,B of width*height u16 each; returns interleaved R,G,B in dst (frame index `frame`)

@@ -66,6 +66,21 @@ int main(int argc, char **argv)
         printf("%d %d %d\n", info.width, info.height, info.channels);
         return dump(argv[3], v) ? 0 : 1;
     }
+    if (argc >= 7 && !strcmp(argv[1], "write-dpx")) {            // write-dpx out.dpx W H BE(0|1) rgb10.bin (u16 R,G,B codes)
+        const int w = atoi(argv[3]), h = atoi(argv[4]), be = atoi(argv[5]);
+        std::vector<uint16_t> v;
+        if (!slurp(argv[6], &v, (size_t)w * h * 3)) { printf("cannot read %s\n", argv[6]); return 1; }
+        if (!h2yio::dpx_write_10bit(argv[2], v.data(), w, h, be != 0, &err)) { printf("%s\n", err.c_str()); return 1; }
+        return 0;
+    }
+    if (argc >= 4 && !strcmp(argv[1], "read-dpx")) {             // read-dpx in.dpx words.bin: the stored words, as read
+        h2yio::ImageInfo info;
+        if (!h2yio::dpx_probe(argv[2], &info, &err)) { printf("%s\n", err.c_str()); return 1; }
+        std::vector<uint16_t> v((size_t)info.width * info.height * 2);
+        if (!h2yio::dpx_read_words(argv[2], reinterpret_cast<uint32_t *>(v.data()), &info, &err)) { printf("%s\n", err.c_str()); return 1; }
+        printf("%d %d %d %d\n", info.width, info.height, info.bits, info.big_endian ? 1 : 0);
+        return dump(argv[3], v) ? 0 : 1;
+    }
     printf("usage: see the header of h2y_iotool.cpp\n");
     return 2;
 }

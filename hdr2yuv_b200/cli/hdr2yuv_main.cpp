@@ -26,10 +26,10 @@ namespace {
 
 enum FileType { FT_UNDEFINED = 0, FT_YUV, FT_TIFF, FT_EXR, FT_Y4M, FT_DPX, FT_RGB };
 struct TypeInfo { int idx; const char *name; int supported; };
-// hdr.h:48-68; DPX and the .exr/.dpx/.rgb destinations are outside the accelerated path; a .tiff destination is
+// hdr.h:48-68; the .exr/.dpx/.rgb destinations are outside the accelerated path; a .tiff destination is
 // served for .yuv sources (matrix_inverse + write_tiff, hdr2yuv.cpp:818-819, 930-933)
 const TypeInfo kInputTypes[] = {{FT_UNDEFINED, "UNDEFINED", 0}, {FT_YUV, "yuv", 1}, {FT_TIFF, "tiff", 1}, {FT_EXR, "exr", 1},
-                                {FT_Y4M, "y4m", 0}, {FT_DPX, "dpx", 0}, {FT_RGB, "rgb", 1}};
+                                {FT_Y4M, "y4m", 0}, {FT_DPX, "dpx", 1}, {FT_RGB, "rgb", 1}};
 const TypeInfo kOutputTypes[] = {{FT_UNDEFINED, "UNDEFINED", 0}, {FT_YUV, "yuv", 1}, {FT_TIFF, "tiff", 1}, {FT_EXR, "exr", 0},
                                  {FT_Y4M, "y4m", 0}, {FT_DPX, "dpx", 0}, {FT_RGB, "rgb", 0}};
 // hdr.h:140-166 (index = transfer_characteristics code)
@@ -236,6 +236,13 @@ bool read_frame(const Args &a, const Source &s, int frame, uint8_t *dst, std::st
         if (info.width != s.width || info.height != s.height) { *err = name + ": geometry differs from the first frame"; return false; }
         return true;
     }
+    case FT_DPX: {
+        const std::string name = h2yio::sequence_name(a.src_filename, a.src_start_frame + frame);
+        if (!h2yio::dpx_read_words(name, reinterpret_cast<uint32_t *>(dst), &info, err)) return false;
+        if (info.width != s.width || info.height != s.height) { *err = name + ": geometry differs from the first frame"; return false; }
+        if ((info.big_endian ? H2Y_LAYOUT_DPX10_BE : H2Y_LAYOUT_DPX10_LE) != s.layout) { *err = name + ": byte order differs from the first frame"; return false; }
+        return true;
+    }
     case FT_RGB:
         return h2yio::rgb_planar_read(a.src_filename, d16, s.width, s.height, a.src_start_frame + frame, err);
     default:   // .yuv 4:4:4: the three planes are the picture (hdr2yuv.cpp:641-643)
@@ -292,6 +299,17 @@ int main(int argc, char *argv[])
         if (in.matrix_coeffs != H2Y_MATRIX_GBR) printf("read_exr(): overriding matrix_coeffs(%d) to MATRIX_GBR(%d)\n", in.matrix_coeffs, H2Y_MATRIX_GBR);
         if (in.video_full_range_flag != 1) printf("reading .exr file (%s):  setting input picture video_full_range_flag to 1", a.src_filename);
         in.bit_depth = 32; in.matrix_coeffs = H2Y_MATRIX_GBR; in.video_full_range_flag = 1; in.chroma_format_idc = H2Y_CHROMA_444;
+    } else if (s.type == FT_DPX) {
+        // hdr2yuv.cpp:700-737: a float picture (code / 1023.0), GBR, 4:4:4, 32 bits; the full-range flag is only reported
+        const std::string first = h2yio::sequence_name(a.src_filename, a.src_start_frame);
+        if (!h2yio::dpx_probe(first, &info, &err)) { printf(" %s, aborting\n", err.c_str()); return 1; }
+        printf(" reading file %s width = %d, height = %d, cineon = 0\n", first.c_str(), info.width, info.height);
+        s.width = info.width; s.height = info.height; s.channels = 3;
+        s.layout = info.big_endian ? H2Y_LAYOUT_DPX10_BE : H2Y_LAYOUT_DPX10_LE;
+        if (in.matrix_coeffs != H2Y_MATRIX_GBR) printf("reading .dpx file (%s):  setting input picture matrix_coef=%d (MATRIX_GBR)", a.src_filename, H2Y_MATRIX_GBR);
+        if (in.chroma_format_idc != H2Y_CHROMA_444) printf("reading .dpx file (%s):  setting input picture chroma_format_idc=%d (CHROMA_444)", a.src_filename, H2Y_CHROMA_444);
+        if (in.video_full_range_flag != 1) printf("reading .dpx file (%s):  setting input picture video_full_range_flag to 1", a.src_filename);
+        in.bit_depth = 32; in.matrix_coeffs = H2Y_MATRIX_GBR; in.chroma_format_idc = H2Y_CHROMA_444;
     } else if (s.type == FT_RGB) {
         s.width = in.width; s.height = in.height; s.channels = 3; s.layout = H2Y_LAYOUT_RGB16;
         if (in.matrix_coeffs != H2Y_MATRIX_GBR) {
@@ -317,7 +335,7 @@ int main(int argc, char *argv[])
     fp.src.transfer_characteristics = in.transfer_characteristics; fp.src.colour_primaries = in.colour_primaries;
     fp.src.matrix_coeffs = in.matrix_coeffs; fp.src.bit_depth = in.bit_depth;
     fp.src.video_full_range_flag = in.video_full_range_flag;
-    fp.src.pic_buffer_type = s.type == FT_EXR ? H2Y_PIC_TYPE_F32 : H2Y_PIC_TYPE_U16;
+    fp.src.pic_buffer_type = (s.type == FT_EXR || s.type == FT_DPX) ? H2Y_PIC_TYPE_F32 : H2Y_PIC_TYPE_U16;
     fp.src.layout = s.layout;
     fp.dst.width = out.width; fp.dst.height = out.height; fp.dst.chroma_format_idc = out.chroma_format_idc;
     fp.dst.transfer_characteristics = out.transfer_characteristics; fp.dst.colour_primaries = out.colour_primaries;

@@ -259,6 +259,7 @@ size_t h2y_src_frame_bytes(const h2y_pic_desc *s)
     case H2Y_LAYOUT_PLANAR_U16: case H2Y_LAYOUT_RGB16: case H2Y_LAYOUT_HALF_RGB: return n * 6;
     case H2Y_LAYOUT_PLANAR_F32: return n * 12;
     case H2Y_LAYOUT_RGBA16: case H2Y_LAYOUT_HALF_RGBA: return n * 8;
+    case H2Y_LAYOUT_DPX10_BE: case H2Y_LAYOUT_DPX10_LE: return n * 4;
     }
     return 0;
 }
@@ -467,7 +468,7 @@ static h2y_status forward_validate(const h2y_forward_params *p, h2y_pic_desc *tm
 {
     const h2y_pic_desc &s = p->src, &d = p->dst;
     if (s.width < 2 || s.height < 2 || s.width > 16384 || s.height > 16384) return H2Y_ERR_ARG;
-    if (s.layout < H2Y_LAYOUT_PLANAR_U16 || s.layout > H2Y_LAYOUT_HALF_RGBA) return H2Y_ERR_ARG;
+    if (s.layout < H2Y_LAYOUT_PLANAR_U16 || s.layout > H2Y_LAYOUT_DPX10_LE) return H2Y_ERR_ARG;
     if (s.chroma_format_idc != H2Y_CHROMA_444) return H2Y_ERR_PRECONDITION;        // convert.cpp:886-890
     if (d.chroma_format_idc != H2Y_CHROMA_444 && d.chroma_format_idc != H2Y_CHROMA_420 &&
         d.chroma_format_idc != H2Y_CHROMA_422) return H2Y_ERR_ARG;

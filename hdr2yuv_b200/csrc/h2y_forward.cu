@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_fused(const FwdArgs a)
 bool fused_forward_supported(const h2y_forward_params &p)
 {
     const int w = p.src.width, h = p.src.height;
-    if (p.src.layout == H2Y_LAYOUT_PLANAR_F32) return false;
+    if (p.src.layout == H2Y_LAYOUT_PLANAR_F32 || layout_is_dpx(p.src.layout)) return false;   // staged route
     if (w < 8 || (w & 7) || h < 2) return false;
     if ((p.dst.chroma_format_idc == H2Y_CHROMA_420) && (h & 1)) return false;
     if (p.dst.chroma_format_idc == H2Y_CHROMA_420 && p.chroma_resampler_type == 0 && ((w & 3) || (h & 3))) return false;

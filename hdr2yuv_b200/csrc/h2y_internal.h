@@ -65,6 +65,7 @@ void clip_of(int bit_depth, int full_range, h2y_clip_limits *c);
 
 inline bool layout_is_planar(int l) { return l == H2Y_LAYOUT_PLANAR_U16 || l == H2Y_LAYOUT_PLANAR_F32; }
 inline bool layout_is_half(int l) { return l == H2Y_LAYOUT_HALF_RGB || l == H2Y_LAYOUT_HALF_RGBA; }
+inline bool layout_is_dpx(int l) { return l == H2Y_LAYOUT_DPX10_BE || l == H2Y_LAYOUT_DPX10_LE; }
 inline int layout_channels(int l) { return (l == H2Y_LAYOUT_RGBA16 || l == H2Y_LAYOUT_HALF_RGBA) ? 4 : 3; }
 
 // ---- launchers (h2y_stats.cu) ----------------------------------------------------------------

@@ -130,10 +130,33 @@ k_unpack(int layout, long npix, const uint16_t *__restrict__ src, void *o0, void
     }
 }
 
+// 10-bit packed DPX words -> three float planes G,B,R with sample = code / 1023.0, the double division rounded to
+// float as dpx_read's assignment does (dpx.cpp:506-531; muxed_dpx_to_planar_float_buf, common.cpp:12-28)
+__global__ void __launch_bounds__(256)
+k_unpack_dpx10(long npix, const unsigned *__restrict__ src, int big_endian, float *__restrict__ g, float *__restrict__ b,
+               float *__restrict__ r)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    unsigned w = __ldg(src + i);
+    if (big_endian) w = __byte_perm(w, 0, 0x0123);
+    const unsigned rr = w >> 22, gg = (w >> 12) & 1023u, bb = (w >> 2) & 1023u;
+    r[i] = __double2float_rn(__ddiv_rn((double)rr, 1023.0));
+    g[i] = __double2float_rn(__ddiv_rn((double)gg, 1023.0));
+    b[i] = __double2float_rn(__ddiv_rn((double)bb, 1023.0));
+}
+
 h2y_status launch_unpack(h2y_ctx_impl *c, int layout, int w, int h, const void *d_src, void *const d_planes[3],
                          int clip_on_load, unsigned lo, unsigned hi, cudaStream_t st)
 {
     const long npix = (long)w * h;
+    if (layout_is_dpx(layout)) {
+        k_unpack_dpx10<<<(int)((npix + 255) / 256), 256, 0, st>>>(npix, (const unsigned *)d_src, layout == H2Y_LAYOUT_DPX10_BE,
+                                                                   (float *)d_planes[0], (float *)d_planes[1], (float *)d_planes[2]);
+        c->launches++;
+        H2Y_CUDA(c, cudaGetLastError());
+        return H2Y_OK;
+    }
     k_unpack<<<(int)((npix + 255) / 256), 256, 0, st>>>(layout, npix, (const uint16_t *)d_src, d_planes[0], d_planes[1],
                                                          d_planes[2], clip_on_load, lo, hi);
     c->launches++;

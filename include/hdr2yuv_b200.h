@@ -64,7 +64,11 @@ typedef enum h2y_layout {
     H2Y_LAYOUT_RGB16 = 2,      /* interleaved R,G,B u16: a TIFF strip row (tiff.cpp:276-278) */
     H2Y_LAYOUT_RGBA16 = 3,     /* interleaved R,G,B,A u16 (--alpha_channel, tiff.cpp:281-282) */
     H2Y_LAYOUT_HALF_RGB = 4,   /* interleaved r,g,b IEEE half */
-    H2Y_LAYOUT_HALF_RGBA = 5   /* interleaved Imf::Rgba {half r,g,b,a} (exr.cpp:143-192) */
+    H2Y_LAYOUT_HALF_RGBA = 5,  /* interleaved Imf::Rgba {half r,g,b,a} (exr.cpp:143-192) */
+    /* one 32-bit word per pixel as a 10-bit DPX file stores it, R[31:22] G[21:12] B[11:2] (dpx.cpp:506-531), in the
+     * file's byte order (big-endian "SDPX", little-endian "XPDS").  The picture is F32: sample = code / 1023.0 */
+    H2Y_LAYOUT_DPX10_BE = 6,
+    H2Y_LAYOUT_DPX10_LE = 7
 } h2y_layout;
 
 /* The fields of pic_t (hdr.h:359-392) the hot path reads. */

@@ -240,6 +240,14 @@ def load_half(px):
     return planes
 
 
+def load_dpx10(words, big_endian):
+    """What dpx_read + muxed_dpx_to_planar_float_buf leave in in_pic->fbuf for a 10-bit packed DPX (dpx.cpp:506-531,
+    common.cpp:12-28): (H,W) stored 32-bit words -> (3,H,W) float32 planes G,B,R with sample = code / 1023.0."""
+    w = np.ascontiguousarray(words).view(np.dtype(">u4") if big_endian else np.dtype("<u4")).astype(np.uint32)
+    rr, gg, bb = w >> 22, (w >> 12) & 1023, (w >> 2) & 1023
+    return np.stack([(c.astype(np.float64) / 1023.0).astype(np.float32) for c in (gg, bb, rr)], 0)
+
+
 def yuv2tiff(yuv, w, h, bit_depth=12, matrix=INV_YDZDX, fir=True, full_range=False, alpha=False, backend="port", ybar=False):
     """One 4:2:0 frame (flat u16 Y,Cb,Cr) -> (H,W,3|4) interleaved RGB16.  Returns (rgb, invalid_pixels)."""
     yuv = np.ascontiguousarray(yuv, np.uint16)

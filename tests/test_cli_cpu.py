@@ -152,3 +152,34 @@ def test_option_errors_follow_the_reference(cli, tmp_path):
                     "--src_pic_width", "64", "--src_pic_height", "48", "--src_bit_depth", "16", "--src_chroma_format_idc", "3",
                     "--dst_chroma_format_idc", "1", "--dst_bit_depth", "10"], check=False)
     assert rc == 1 and "holds 0 frames" in text
+
+
+@pytest.mark.parametrize("big_endian", [1, 0])
+def test_dpx_10bit_reader_and_dump(cli, tmp_path, big_endian):
+    # 10-bit packed DPX (dpx.cpp:210-360, 506-531): the header fields dpx_read uses, both byte orders; the host hands
+    # the stored words to the GPU untouched, so --dump_input must return exactly the file's pixel words
+    w, h = 72, 40
+    rng = np.random.default_rng(3 + big_endian)
+    rgb10 = rng.integers(0, 1024, (h, w, 3), dtype=np.uint16)
+    rgb10.tofile(tmp_path / "c.raw")
+    dpx = tmp_path / "in.dpx"
+    run([cli["h2y_iotool"], "write-dpx", str(dpx), str(w), str(h), str(big_endian), str(tmp_path / "c.raw")])
+    raw = np.fromfile(dpx, np.uint8)
+    assert raw.size == 2048 + w * h * 4 and bytes(raw[:4]) == (b"SDPX" if big_endian else b"XPDS")
+    _, text = run([cli["h2y_iotool"], "read-dpx", str(dpx), str(tmp_path / "w.raw")])
+    assert text.split() == [str(w), str(h), "10", str(big_endian)]
+    words = np.fromfile(tmp_path / "w.raw", np.dtype(">u4") if big_endian else np.dtype("<u4")).reshape(h, w)
+    assert np.array_equal(words >> 22, rgb10[..., 0]) and np.array_equal((words >> 12) & 1023, rgb10[..., 1])
+    assert np.array_equal((words >> 2) & 1023, rgb10[..., 2])
+    dump = tmp_path / "dump.raw"
+    size = ["--src_pic_width", str(w), "--src_pic_height", str(h), "--src_bit_depth", "10"]
+    _, text = run([cli["hdr2yuv"], "--src_filename", str(dpx), "--dst_filename", str(tmp_path / "o.yuv"),
+                   "--src_transfer_characteristics", "8", "--dst_transfer_characteristics", "16", "--dump_input", str(dump)] + size + BASE)
+    assert np.array_equal(np.fromfile(dump, np.uint8), raw[2048:]), text
+    assert "layout %d" % (6 if big_endian else 7) in text
+    # a 16-bit DPX is refused with a message, like every packing dpx_read does not know
+    bad = raw.copy(); bad[803] = 12
+    bad.tofile(tmp_path / "bad.dpx")
+    rc, text = run([cli["hdr2yuv"], "--src_filename", str(tmp_path / "bad.dpx"), "--dst_filename", str(tmp_path / "o.yuv"),
+                    "--dump_input", str(dump)] + size + BASE, check=False)
+    assert rc != 0 and "12-bits" in text

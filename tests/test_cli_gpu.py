@@ -118,3 +118,33 @@ def test_yuv444_to_tiff_uses_matrix_inverse(cli, tmp_path):
     got = np.fromfile(tmp_path / "o.raw", np.uint16).reshape(cases.MH, cases.MW, 3)
     assert np.array_equal(got, want)
     assert "invalid pixels %d" % invalid in text
+
+
+def test_dpx_sequence_to_yuv(cli, tmp_path):
+    # 10-bit packed DPX frames (both byte orders in one sequence is refused; here big-endian, as film scanners write):
+    # reader on the host, unpack + /1023.0 + the whole chain on the GPU
+    w, h, n = 256, 96, 3
+    rng = np.random.default_rng(5)
+    stored = []
+    for i in range(n):
+        c = rng.integers(0, 1024, (h, w, 3), dtype=np.uint16)
+        c[2, 3] = 1023
+        c[4, 5] = 0
+        c.tofile(tmp_path / "c.raw")
+        run([cli["h2y_iotool"], "write-dpx", str(tmp_path / ("scan_%04d.dpx" % i)), str(w), str(h), "1", str(tmp_path / "c.raw")])
+        c = c.astype(np.uint32)
+        stored.append(((c[..., 0] << 22) | (c[..., 1] << 12) | (c[..., 2] << 2)).astype(">u4"))
+    out = tmp_path / "out.yuv"
+    run([cli["hdr2yuv"], "--src_filename", str(tmp_path / "scan_0000.dpx"), "--dst_filename", str(out), "--src_pic_width", str(w),
+         "--src_pic_height", str(h), "--src_bit_depth", "10", "--dst_bit_depth", "10", "--src_chroma_format_idc", "3",
+         "--dst_chroma_format_idc", "1", "--src_matrix_coeffs", "0", "--dst_matrix_coeffs", "9",
+         "--src_transfer_characteristics", "8", "--dst_transfer_characteristics", "16", "--src_colour_primaries", "1",
+         "--dst_colour_primaries", "9", "--src_video_full_range_flag", "1", "--dst_video_full_range_flag", "0",       # dst would inherit 1
+         "--chroma_resampler_type", "1", "--n_frames", str(n)])
+    src = dict(bit_depth=32, full_range=1, transfer=8, primaries=1, matrix=0)
+    dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+    got = np.fromfile(out, np.uint16).reshape(n, -1)
+    for i in range(n):
+        want = O.forward(O.load_dpx10(stored[i], True), src, dst, backend="port")
+        d = np.abs(got[i].astype(int) - want.astype(int))
+        assert d.max() <= 1 and (d != 0).sum() <= max(2, d.size // 2000), (i, int(d.max()), int((d != 0).sum()), got[i][:8], want[:8])

@@ -307,3 +307,34 @@ def test_wide_and_short_pictures(ctx, monkeypatch, which):
         got = G.gpu_forward(ctx, frames, _HALF, dst)
         for f, g in zip(frames, got):
             G.compare_codes(g, G.oracle_forward(f, _HALF, dst), True, "%s %dx%d" % (which, w, h))
+
+
+@pytest.mark.parametrize("big_endian", [True, False])
+def test_dpx10_layout_unpacks_on_the_gpu_and_matches_oracle(ctx, big_endian):
+    # H2Y_LAYOUT_DPX10_BE / _LE: the file's packed words go to the device as stored; the unpack and the /1023.0 of
+    # dpx_read (dpx.cpp:506-531) happen there and the picture continues as an F32 source (hdr2yuv.cpp:700-737).
+    # Code 1023 and code 0 are present, so (int)max - (int)min = 1 (a DPX without a full-scale sample has range 0 in
+    # the reference, common.cpp:135-136).
+    w, h = 136, 52
+    rng = np.random.default_rng(21)
+    codes = rng.integers(0, 1024, (2, h, w, 3), dtype=np.uint32)
+    codes[:, 3, 5] = 1023
+    codes[:, 7, 9] = 0
+    words = (codes[..., 0] << 22) | (codes[..., 1] << 12) | (codes[..., 2] << 2)
+    stored = words.astype(">u4" if big_endian else "<u4")
+    src = dict(kind="dpx", bit_depth=32, full_range=1, transfer=8, primaries=1, matrix=0)
+    layout = cabi.LAYOUT_DPX10_BE if big_endian else cabi.LAYOUT_DPX10_LE
+    for dst in (dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1),
+                dict(bit_depth=12, full_range=1, transfer=18, primaries=9, matrix=11, chroma=3, resampler=1),
+                dict(bit_depth=10, full_range=0, transfer=8, primaries=1, matrix=1, chroma=1, resampler=0)):
+        params = api.forward_params(w, h, layout, src, dst, resampler=dst["resampler"])
+        assert api.src_frame_bytes(params.src) == w * h * 4
+        d_src = G.to_dev(stored.view(np.uint8))
+        nbytes = api.yuv_frame_bytes(w, h, dst["chroma"])
+        d_dst = torch.zeros(nbytes * 2, dtype=torch.uint8, device="cuda")
+        ctx.forward(params, d_src, d_dst, 2)
+        torch.cuda.synchronize()
+        got = d_dst.cpu().numpy().view(np.uint16).reshape(2, -1)
+        for i in range(2):
+            want = O.forward(O.load_dpx10(stored[i], big_endian), cases.oracle_src(src), dst, backend="port")
+            G.compare_codes(got[i], want, src["transfer"] != dst["transfer"], "dpx frame %d" % i)
