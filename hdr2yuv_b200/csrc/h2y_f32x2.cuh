@@ -69,12 +69,5 @@ __device__ __forceinline__ unsigned clamp_s16x2(unsigned v, unsigned lo, unsigne
     asm("min.s16x2 %0, %0, %1;" : "+r"(v) : "r"(hi));
     return v;
 }
-// 1.0f when x < 0, else 0.0f (FSET.BF)
-__device__ __forceinline__ float fset_lt0(float x)
-{
-    float r;
-    asm("set.lt.f32.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
-    return r;
-}
 
 }   // namespace h2y

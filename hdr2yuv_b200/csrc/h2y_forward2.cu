@@ -11,9 +11,12 @@
 //  * Per-pixel arithmetic runs on Blackwell's packed fp32x2 pipe (FFMA2 / FADD2: two lanes of fp32 per issue slot).
 //    The colour-difference stage is evaluated in fp32 with a guard band: every truncation is taken twice, at x-G and
 //    x+G, with a round-down add of 1.5*2^23 (the integer falls out of the mantissa, no F2I); when both agree the
-//    truncated integer is certain, because the fp32 evaluation is within G/2 of the reference's double evaluation.
-//    The rare pixel whose two truncations differ is redone with the general kernel's FP64 routine (inlined: an
-//    out-of-line call cost ~2900 cycles per 16-row step through ABI spills).
+//    truncated integer is certain, because the fp32 evaluation is within 7.2/8 G of the reference's double evaluation
+//    (G = 2^(depth-22) = 8 half-ulps of the largest values; the terms of the bound are listed in DESIGN.md 4).
+//    The rare pixel whose two truncations differ (0.15 % at 10 bits) is redone with the general kernel's FP64 routine,
+//    inlined (an out-of-line call cost ~2900 cycles per 16-row step through ABI spills); four pixels share a branch.
+//  * Frames whose LUT extremes prove that Cb/Cr stay clear of matrix_convert's clamp (two_lut_frame) take the TWO
+//    instantiation: two pre-scaled LUT copies, chroma truncated with FRND.TRUNC, Half-1 added by the filter constant.
 //  * The range scale (convert.cpp:1139-1144) keeps its two separately rounded fp32 operations, so the values entering
 //    the matrix are the reference's own floats.
 //  * Chroma stays in float from the truncation to the .yuv store; the u16 quantisation of the reference's `dst422`
@@ -34,6 +37,7 @@
 #ifndef H2Y_GUARD_SHIFT
 #define H2Y_GUARD_SHIFT 22
 #endif
+// Pixel pairs per guard-band branch (1, 2 or 4): 2 measured fastest (profiles/r01/variants.md).
 #ifndef H2Y_PAIRS_PER_BRANCH
 #define H2Y_PAIRS_PER_BRANCH 2
 #endif
