@@ -646,6 +646,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
             const int xload = lane_in_pic ? xl : (xl < 0 ? 0 : w - 8);          // halo lanes outside the picture read a valid
                                                                                  // address; their values are replaced below
             const bool left_edge = xl == 0, right_edge = xl + 8 >= w;
+            const bool strip_edge = __any_sync(0xffffffffu, left_edge || right_edge);
             u64 acc[6][4];
 #pragma unroll
             for (int i = 0; i < 6; i++)
@@ -677,8 +678,10 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                 float n1x = __shfl_down_sync(0xffffffffu, plo(ch[1]), 1), n1y = __shfl_down_sync(0xffffffffu, phi(ch[1]), 1);
                 float n3x = __shfl_down_sync(0xffffffffu, plo(ch[3]), 1), n3y = __shfl_down_sync(0xffffffffu, phi(ch[3]), 1);
                 u64 l3 = pk(l3x, l3y), l5 = pk(l5x, l5y), l7 = pk(l7x, l7y), n1 = pk(n1x, n1y), n3 = pk(n3x, n3y);
-                if (left_edge) l3 = l5 = l7 = ch[0];                // replicate s[0]     (convert.cpp:295-300)
-                if (right_edge) n1 = n3 = ch[7];                    // replicate s[W-1]
+                if (strip_edge) {                                   // warp-uniform (from a vote): inner strips skip 10 selects
+                    if (left_edge) l3 = l5 = l7 = ch[0];            // replicate s[0]     (convert.cpp:295-300)
+                    if (right_edge) n1 = n3 = ch[7];                // replicate s[W-1]
+                }
                 o[0] = fir_h7_pair(l3, l5, l7, ch[0], ch[1], ch[3], ch[5], hi_bits, hc0);
                 o[1] = fir_h7_pair(l5, l7, ch[1], ch[2], ch[3], ch[5], ch[7], hi_bits, hc0);
                 o[2] = fir_h7_pair(l7, ch[1], ch[3], ch[4], ch[5], ch[7], n1, hi_bits, hc0);
