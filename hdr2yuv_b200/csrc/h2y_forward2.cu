@@ -349,6 +349,39 @@ __device__ __forceinline__ u64 fir_h7_pair_ref(u64 m5, u64 m3, u64 m1, u64 c, u6
               fir_h7_f(phi(m5), phi(m3), phi(m1), phi(c), phi(p1), phi(p3), phi(p5), maxCVf));
 }
 
+// The same two filters for the warp-autonomous integer kernel: reference operation order on both planes of a {Cb,Cr}
+// pair at once.  Sums and differences are packed (FADD2); every product is a scalar FMUL because ptxas contracts a
+// packed multiply feeding a packed add into one FFMA2 (see h2y_f32x2.cuh), which would drop the product's rounding.
+// The reference clamps the float to [0, maxCV] and truncates; flooring first (round-down add of 1.5*2^23) and
+// clamping the integers gives the same code for every t, and leaves the bit pattern the callers want.
+__device__ __forceinline__ u64 fmulk2(float kf, u64 v) { return pk(__fmul_rn(kf, plo(v)), __fmul_rn(kf, phi(v))); }
+
+// convert.cpp:305-317; returns the clamped, truncated samples as floats
+__device__ __forceinline__ u64 fir_h7_pair_ord(u64 m5, u64 m3, u64 m1, u64 c, u64 p1, u64 p3, u64 p5, int hi_bits)
+{
+    u64 t = fmulk2(21.0f / 512.0f, fadd2(m5, p5));
+    t = fsub2(t, fmulk2(52.0f / 512.0f, fadd2(m3, p3)));
+    t = fadd2(t, fmulk2(159.0f / 512.0f, fadd2(m1, p1)));
+    t = fadd2(t, fmulk2(256.0f / 512.0f, c));
+    t = fadd2(t, pk(0.5f, 0.5f));
+    const u64 fl = fadd2_rm(t, pk(MAGIC, MAGIC));
+    const int a = clamp3(ilo(fl), MAGIC_BITS, hi_bits), b = clamp3(ihi(fl), MAGIC_BITS, hi_bits);
+    return fadd2(pk(__int_as_float(a), __int_as_float(b)), pk(-MAGIC, -MAGIC));
+}
+
+// convert.cpp:365-374, r[0..11] = rows y-5 .. y+6; returns the floor as MAGIC_BITS + n in both halves (not yet clamped)
+__device__ __forceinline__ u64 fir_v12_pair_ord(const u64 r[12])
+{
+    u64 t = fmulk2(228.0f / 512.0f, fadd2(r[5], r[6]));
+    t = fadd2(t, fmulk2(70.0f / 512.0f, fadd2(r[4], r[7])));
+    t = fsub2(t, fmulk2(37.0f / 512.0f, fadd2(r[3], r[8])));
+    t = fsub2(t, fmulk2(21.0f / 512.0f, fadd2(r[2], r[9])));
+    t = fadd2(t, fmulk2(11.0f / 512.0f, fadd2(r[1], r[10])));
+    t = fadd2(t, fmulk2(5.0f / 512.0f, fadd2(r[0], r[11])));
+    t = fadd2(t, pk(0.5f, 0.5f));
+    return fadd2_rm(t, pk(MAGIC, MAGIC));
+}
+
 template <int MK, int NCH, int SRC = 0>     // SRC: 0 = half source through the LUT (fp32 guard band), 1 = integer source (reference arithmetic)
 __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
 {
@@ -752,6 +785,132 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
     }
 }
 
+// =================================================================================================
+// Integer rows (TIFF), 4:2:0 FIR, large batches: the warp-autonomous layout of k_forward_exr420_rows with the
+// reference's arithmetic.  At 16-bit scale the vertical filter's operation order is observable (SURVEY.md Appendix
+// A.7), so its twelve input rows are kept, not folded into running sums: each warp owns a 12-slot ring of horizontally
+// filtered rows in shared memory ([slot][half][lane] float4, only its own lanes touch it, no barrier), and every second
+// row it reads the window back and evaluates convert.cpp:365-374 in order.
+constexpr int VSLOTS = 12;
+
+template <int MK, int NCH>
+__global__ void __launch_bounds__(THREADS3, 1) k_forward_u16_420_rows(const Fwd3Args A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Fwd2Args &a = A.b;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 *ring = reinterpret_cast<float4 *>(smem_raw) + (size_t)warp * VSLOTS * 64 + lane;      // [slot][half][lane]
+    const PixK &k = a.k;
+    const int w = a.w, h = a.h, wh = w >> 1;
+    const int hi_bits = MAGIC_BITS + (int)k.maxCV;
+    const int shift = k.down_shift;
+    const int clo = (int)k.loC + (MAGIC_BITS >> shift), chi = (int)k.hiC + (MAGIC_BITS >> shift);
+    unsigned fallbacks = 0;
+
+    const int wk = warp / A.wps, sfirst = warp - wk * A.wps;
+    if (wk >= A.sub) return;
+    const long K = (long)gridDim.x * A.sub, kid = (long)blockIdx.x * A.sub + wk;
+    const long g0 = ((kid * A.total_rows) / K) & ~1L, g1 = kid + 1 == K ? A.total_rows : (((kid + 1) * A.total_rows) / K) & ~1L;
+    if (g1 <= g0) return;
+
+    for (int frame = (int)(g0 / h); frame <= (int)((g1 - 1) / h); frame++) {
+        const long fbase = (long)frame * h;
+        const int ys = (int)(max(g0, fbase) - fbase), ye = (int)(min(g1, fbase + h) - fbase);
+        if (ys >= ye) continue;
+        const uint8_t *fsrc = a.src + (size_t)frame * a.src_stride;
+        uint16_t *fY = reinterpret_cast<uint16_t *>(a.dst + (size_t)frame * a.dst_stride);
+        uint16_t *fCb = fY + (size_t)w * h;
+        uint16_t *fCr = fCb + (size_t)wh * (h >> 1);
+
+        for (int strip = sfirst; strip < a.nstrips; strip += A.wps) {
+            const int x0 = strip * a.strip_w;
+            const int xl = x0 + 8 * (lane - 1);
+            const bool lane_in_pic = xl >= 0 && xl < w;
+            const bool lane_interior = lane >= 1 && lane < 31 && xl < min(x0 + a.strip_w, w);
+            const int xload = lane_in_pic ? xl : (xl < 0 ? 0 : w - 8);
+            const bool left_edge = xl == 0, right_edge = xl + 8 >= w;
+            const int rfirst = ys - 6, rlast = ye + 4;              // rows feeding outputs ys/2 .. ye/2-1 (rfirst even)
+            const unsigned spitch = (unsigned)w * (2 * NCH);
+            const uint8_t *sp = fsrc + (size_t)min(max(rfirst, 0), h - 1) * spitch + (size_t)xload * (2 * NCH);
+            uint16_t *yp = fY + (ptrdiff_t)rfirst * w + xl;
+            uint16_t *cbp = fCb + ((ptrdiff_t)(rfirst >> 1) - 3) * wh + (xl >> 1);
+            const int crd = (int)(fCr - fCb);
+            int slot = 0;                                            // ring slot of row r; row r - t sits t slots back
+
+            RawPx<NCH> raw, cur;
+            load_px8<NCH>(raw, sp, 0, 0, 0);
+#pragma unroll 1
+            for (int r = rfirst; r <= rlast; r++) {
+                cur = raw;
+                sp += ((unsigned)r < (unsigned)(h - 1)) ? spitch : 0;               // clamped rows = edge replicate
+                if (r < rlast) load_px8<NCH>(raw, sp, 0, 0, 0);                     // prefetch the next row
+                if (k.clip_on_load) {                                               // read_tiff's clip (tiff.cpp:296-304)
+                    const unsigned lo2 = k.loadLo * 0x10001u, hi2 = k.loadHi * 0x10001u;
+#pragma unroll
+                    for (int i = 0; i < NCH; i++) {
+                        unsigned *wv = reinterpret_cast<unsigned *>(&cur.v[i]);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) wv[j] = clamp_u16x2(wv[j], lo2, hi2);
+                    }
+                }
+                unsigned g[8], b[8], rr[8];
+                split_codes<NCH>(cur, g, b, rr);
+                uint4 ypack;
+                u64 ch[8];
+                pixels8_u16<MK>(a, g, b, rr, ypack, ch, fallbacks);
+                if (lane_interior && r >= ys && r < ye) *reinterpret_cast<uint4 *>(yp) = ypack;
+                yp += w;
+                float l3x = __shfl_up_sync(0xffffffffu, plo(ch[3]), 1), l3y = __shfl_up_sync(0xffffffffu, phi(ch[3]), 1);
+                float l5x = __shfl_up_sync(0xffffffffu, plo(ch[5]), 1), l5y = __shfl_up_sync(0xffffffffu, phi(ch[5]), 1);
+                float l7x = __shfl_up_sync(0xffffffffu, plo(ch[7]), 1), l7y = __shfl_up_sync(0xffffffffu, phi(ch[7]), 1);
+                float n1x = __shfl_down_sync(0xffffffffu, plo(ch[1]), 1), n1y = __shfl_down_sync(0xffffffffu, phi(ch[1]), 1);
+                float n3x = __shfl_down_sync(0xffffffffu, plo(ch[3]), 1), n3y = __shfl_down_sync(0xffffffffu, phi(ch[3]), 1);
+                u64 l3 = pk(l3x, l3y), l5 = pk(l5x, l5y), l7 = pk(l7x, l7y), n1 = pk(n1x, n1y), n3 = pk(n3x, n3y);
+                if (left_edge) l3 = l5 = l7 = ch[0];                // replicate s[0]     (convert.cpp:295-300)
+                if (right_edge) n1 = n3 = ch[7];                    // replicate s[W-1]
+                const u64 o0 = fir_h7_pair_ord(l3, l5, l7, ch[0], ch[1], ch[3], ch[5], hi_bits);
+                const u64 o1 = fir_h7_pair_ord(l5, l7, ch[1], ch[2], ch[3], ch[5], ch[7], hi_bits);
+                const u64 o2 = fir_h7_pair_ord(l7, ch[1], ch[3], ch[4], ch[5], ch[7], n1, hi_bits);
+                const u64 o3 = fir_h7_pair_ord(ch[1], ch[3], ch[5], ch[6], ch[7], n1, n3, hi_bits);
+                ring[slot * 64] = make_float4(plo(o0), phi(o0), plo(o1), phi(o1));
+                ring[slot * 64 + 32] = make_float4(plo(o2), phi(o2), plo(o3), phi(o3));
+                __syncwarp();
+                const int j = (r >> 1) - 3;                         // even row r = 2j+6 completes output row j
+                if ((r & 1) == 0 && j >= (ys >> 1) && j < (ye >> 1)) {
+                    unsigned cbv[4], crv[4];
+#pragma unroll
+                    for (int half = 0; half < 2; half++) {
+                        u64 win[2][12];                             // rows 2j-5 .. 2j+6 of this lane's columns 2*half, 2*half+1
+#pragma unroll
+                        for (int t = 0; t < 12; t++) {
+                            int sl = slot - 11 + t;                 // row r-11+t
+                            sl += sl < 0 ? VSLOTS : 0;
+                            const float4 v = ring[sl * 64 + 32 * half];
+                            win[0][t] = pk(v.x, v.y); win[1][t] = pk(v.z, v.w);
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < 2; cc++) {
+                            // clamp [0,maxCV] + truncation + write_yuv's shift and range clamp: one integer clamp of the floor
+                            int lo_, hi_;
+                            unpk(fir_v12_pair_ord(win[cc]), lo_, hi_);
+                            cbv[2 * half + cc] = (unsigned)clamp3(lo_ >> shift, clo, chi);
+                            crv[2 * half + cc] = (unsigned)clamp3(hi_ >> shift, clo, chi);
+                        }
+                    }
+                    if (lane_interior) {
+                        *reinterpret_cast<uint2 *>(cbp) = make_uint2(__byte_perm(cbv[0], cbv[1], 0x5410), __byte_perm(cbv[2], cbv[3], 0x5410));
+                        *reinterpret_cast<uint2 *>(cbp + crd) = make_uint2(__byte_perm(crv[0], crv[1], 0x5410), __byte_perm(crv[2], crv[3], 0x5410));
+                    }
+                }
+                if ((r & 1) == 0) cbp += wh;
+                slot = slot + 1 == VSLOTS ? 0 : slot + 1;
+            }
+            __syncwarp();
+        }
+    }
+    if (a.fallback_count && fallbacks) atomicAdd(a.fallback_count, (unsigned long long)fallbacks);
+}
+
 // ---- integer source, 4:4:4 output: a pure streaming map (no filter), one 8-pixel group per thread step ---------
 template <int MK, int NCH>
 __global__ void __launch_bounds__(256) k_forward_u16_444(const Fwd2Args a, long groups_per_frame)
@@ -850,10 +1009,41 @@ h2y_status launch_forward_u16_420(h2y_ctx_impl *c, const h2y_forward_params &p, 
         H2Y_CUDA(c, cudaGetLastError());
         return H2Y_OK;
     }
+    const int nch = layout_channels(p.src.layout);
+    {
+        // large batches: the warp-autonomous kernel (rows of the whole batch split evenly over all warps)
+        a.strip_w = 240;
+        a.nstrips = (a.w + a.strip_w - 1) / a.strip_w;
+        Fwd3Args A3;
+        memset(&A3, 0, sizeof(A3));
+        A3.wps = 1;
+        for (int d = 1; d <= WARPS3; d++) if (WARPS3 % d == 0 && a.nstrips % d == 0) A3.wps = d;
+        A3.sub = WARPS3 / A3.wps;
+        A3.total_rows = (long)nframes * a.h;
+        const long rows_per_worker = A3.total_rows / ((long)c->sm_count * A3.sub);
+        const char *force = getenv("H2Y_FORWARD_KERNEL");             // "ring" / "rows": tests and experiments
+        const bool want_rows = force ? force[1] == 'o' : rows_per_worker >= 128;
+        if (want_rows && A3.total_rows >= 2) {
+            int g3 = c->sm_count;
+            while (g3 > 1 && A3.total_rows / ((long)g3 * A3.sub) < 16) g3 >>= 1;   // forced on a tiny batch
+            A3.b = a;
+            const size_t smem3 = (size_t)WARPS3 * VSLOTS * 64 * sizeof(float4);
+#define LR(MKV, NC)                                                                                                        \
+    do {                                                                                                                   \
+        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_u16_420_rows<MKV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
+        k_forward_u16_420_rows<MKV, NC><<<g3, THREADS3, smem3, st>>>(A3);                                                 \
+    } while (0)
+            if (k.mat_kind == MK_YCBCR) { if (nch == 3) LR(MK_YCBCR, 3); else LR(MK_YCBCR, 4); }
+            else { if (nch == 3) LR(MK_YDZDX, 3); else LR(MK_YDZDX, 4); }
+#undef LR
+            c->launches++;
+            H2Y_CUDA(c, cudaGetLastError());
+            return H2Y_OK;
+        }
+    }
     ring_items(a, nframes, c->sm_count);
     const size_t smem = (size_t)RING_ROWS * RING_PITCH * sizeof(float);
     const int grid = a.nitems < c->sm_count ? a.nitems : c->sm_count;
-    const int nch = layout_channels(p.src.layout);
 #define LU(MKV, NC)                                                                                                        \
     do {                                                                                                                   \
         H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420<MKV, NC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

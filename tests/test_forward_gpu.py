@@ -338,3 +338,34 @@ def test_dpx10_layout_unpacks_on_the_gpu_and_matches_oracle(ctx, big_endian):
         for i in range(2):
             want = O.forward(O.load_dpx10(stored[i], big_endian), cases.oracle_src(src), dst, backend="port")
             G.compare_codes(got[i], want, src["transfer"] != dst["transfer"], "dpx frame %d" % i)
+
+
+@pytest.mark.parametrize("which", ["ring", "rows"])
+@pytest.mark.parametrize("matrix,depth,full,channels", [(9, 10, 0, 3), (11, 10, 0, 3), (9, 12, 0, 4), (9, 16, 0, 3), (11, 12, 1, 4), (9, 10, 1, 3)])
+def test_tiff_420_kernels_match_oracle(ctx, monkeypatch, which, matrix, depth, full, channels):
+    # the two kernels behind the integer 4:2:0 FIR route (CTA ring / warp-autonomous with a private row ring), forced in
+    # turn; 16-bit tmp depth, reference operation order in both filters -> bit exact.  Widths that are and are not
+    # multiples of the 240-pixel strip, several frames so that row ranges cross frame boundaries, RGB and RGBA rows.
+    _force_kernel(monkeypatch, which)
+    src = dict(_TIFF, full_range=full)
+    for (w, h) in ((240, 66), (488, 130), (1000, 34), (8, 2), (3848, 4)):
+        dst = dict(bit_depth=depth, full_range=full, transfer=16, primaries=9, matrix=matrix, chroma=1, resampler=1)
+        frames = [synth.tiff16_frame(w, h, seed=300 + s, channels=channels, smooth=bool(s & 1)) for s in range(3)]
+        got = G.gpu_forward(ctx, frames, src, dst)
+        for f, g in zip(frames, got):
+            G.compare_codes(g, G.oracle_forward(f, src, dst), False, "%s %dx%d m%d b%d" % (which, w, h, matrix, depth))
+
+
+def test_large_1080p_tiff_batch_takes_rows_kernel_and_matches_oracle(ctx):
+    # 40 frames of 1920x1080: the batch size at which the integer route picks the warp-autonomous kernel by itself
+    w, h, n = 1920, 1080, 40
+    dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+    base = [synth.tiff16_frame(w, h, seed=s, smooth=bool(s & 1)) for s in (0, 1, 2)]
+    frames = [base[i % 3] for i in range(n)]
+    before = ctx.kernel_launches
+    got = G.gpu_forward(ctx, frames, _TIFF, dst)
+    assert ctx.kernel_launches - before == 1
+    for i in range(3):
+        G.compare_codes(got[i], G.oracle_forward(base[i], _TIFF, dst), False, "1080p frame %d" % i)
+    for i in range(3, n):
+        assert np.array_equal(got[i], got[i % 3]), i
