@@ -336,10 +336,17 @@ __device__ __forceinline__ void pixels8_u16(const Fwd2Args &a, const unsigned g[
             px_matrix_exact<MK>((float)gg, (float)bb, (float)rr, k, Y, Cb, Cr);
             fallbacks++;
         }
-        yv[q] = out_clamp(Y, k.down_shift, k.loY, k.hiY);
-        chroma[q] = pk(u2f(Cb), u2f(Cr));
+        yv[q] = Y;
+        // u2f on both planes at once: 2^23 + code as a bit pattern, minus 2^23 (exact)
+        chroma[q] = fadd2(pk(__uint_as_float(0x4B000000u | Cb), __uint_as_float(0x4B000000u | Cr)), pk(-8388608.0f, -8388608.0f));
     }
-    ypack = make_uint4(yv[0] | (yv[1] << 16), yv[2] | (yv[3] << 16), yv[4] | (yv[5] << 16), yv[6] | (yv[7] << 16));
+    // write_yuv on luma: >> shift and the range clamp on two packed codes per instruction (Y <= maxCV < 2^16)
+    const unsigned keep = (0xffffu >> k.down_shift) * 0x10001u, lo2 = k.loY * 0x10001u, hi2 = k.hiY * 0x10001u;
+    unsigned wv[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        wv[i] = clamp_u16x2((__byte_perm(yv[2 * i], yv[2 * i + 1], 0x5410) >> k.down_shift) & keep, lo2, hi2);
+    ypack = make_uint4(wv[0], wv[1], wv[2], wv[3]);
 }
 
 // horizontal 7-tap in the reference's operation order (convert.cpp:305-317), both planes of a {Cb,Cr} pair
