@@ -323,10 +323,9 @@ __device__ __forceinline__ u64 fir_h7_pair(u64 m5, u64 m3, u64 m1, u64 c, u64 p1
 // (reciprocal multiply with 14 guard bits, exact division when unsure) and the reference's float operation order
 // in both filters; it shares the ring / register-blocked vertical stage of k_forward_exr420.
 template <int MK>
-__device__ __forceinline__ void pixels8_u16(const Fwd2Args &a, const unsigned g[8], const unsigned b[8], const unsigned r[8],
+__device__ __forceinline__ void pixels8_u16(const PixK &k, const unsigned g[8], const unsigned b[8], const unsigned r[8],
                                             uint4 &ypack, u64 chroma[8], unsigned &fallbacks)
 {
-    const PixK &k = a.k;
     unsigned yv[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) {
@@ -466,7 +465,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
                 split_codes<NCH>(raw, g, b, r);
                 uint4 ypack;
                 if (SRC == 0) { unsigned yb[8]; pixels8<MK>(a, lut_sa, g, b, r, yb, ch); ypack = pack_luma<0>(a, yb); }
-                else pixels8_u16<MK>(a, g, b, r, ypack, ch, fallbacks);
+                else pixels8_u16<MK>(a.k, g, b, r, ypack, ch, fallbacks);
                 if (lane_interior && row >= ys && row < ye) *reinterpret_cast<uint4 *>(fY + (size_t)row * w + xl) = ypack;
             }
             {   // prefetch the next step's row
@@ -864,7 +863,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_u16_420_rows(const Fwd3
                 split_codes<NCH>(cur, g, b, rr);
                 uint4 ypack;
                 u64 ch[8];
-                pixels8_u16<MK>(a, g, b, rr, ypack, ch, fallbacks);
+                pixels8_u16<MK>(k, g, b, rr, ypack, ch, fallbacks);
                 if (lane_interior && r >= ys && r < ye) *reinterpret_cast<uint4 *>(yp) = ypack;
                 yp += w;
                 float l3x = __shfl_up_sync(0xffffffffu, plo(ch[3]), 1), l3y = __shfl_up_sync(0xffffffffu, phi(ch[3]), 1);
