@@ -87,6 +87,8 @@ def make_frame(wl, index):
     if wl["kind"] == "inverse":
         raise RuntimeError("inverse inputs are produced by the forward path")
     if wl["src_kind"] == "half":
+        if wl.get("content") == "natural" and ch == 3:
+            return synth.exr_half_frame_smooth_fast(wl["w"], wl["h"], seed=index)
         return synth.exr_half_frame_fast(wl["w"], wl["h"], seed=index, channels=ch)
     return synth.tiff16_frame(wl["w"], wl["h"], seed=index + 1, channels=ch)
 
@@ -326,6 +328,8 @@ def bench_config(wl, name, frames_per_step):
     if wl["kind"] == "forward":
         cfg["layout"] = wl["layout"] + " (%d B/px in)" % LAYOUT_BPP[wl["layout"]]
         cfg["content"] = "iid log-uniform samples (SURVEY.md 8d config 2)" if wl["src_kind"] == "half" else "iid uniform codes"
+        if wl.get("content") == "natural" and wl["src_kind"] == "half":
+            cfg["content"] = "spatially correlated luminance field with colour cast and 2 % noise (--forward-content natural)"
     return cfg
 
 
@@ -553,6 +557,9 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the workload's)")
     ap.add_argument("--layout", choices=sorted(LAYOUT_BPP), default=None, help="override the source layout")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
+    ap.add_argument("--forward-content", choices=["iid", "natural"], default=None,
+                    help="forward EXR workloads: iid log-uniform samples (default, the headline; worst case for the LUT "
+                         "gather) or a spatially correlated field, as a second data point")
     ap.add_argument("--content", choices=["smooth", "iid"], default="smooth",
                     help="inverse workload only: the .yuv frames come from spatially correlated (default) or iid-random sources")
     args = ap.parse_args()
@@ -561,6 +568,8 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.layout and wl["kind"] == "forward":
         wl["layout"] = args.layout
+    if args.forward_content and wl["kind"] == "forward":
+        wl["content"] = args.forward_content
     if args.impl == "reference":
         return run_reference(args, wl, args.workload)
     return run_gpu(args, wl, args.workload)
