@@ -581,8 +581,9 @@ h2y_status h2y_forward(h2y_ctx *c, const h2y_forward_params *p, const void *d_sr
         // EXR route: the v2 kernel converts every "clean" frame, v1 then takes what v2 left (usually nothing)
         int skip_clean = 0;
         if (k.convert_transfer && forward_exr420_supported(*p, k, tmp.bit_depth) && !getenv("H2Y_FORCE_V1")) {
-            if ((s = launch_forward_exr420(c, *p, k, tmp.bit_depth, src, src_stride, dst, dst_stride, nf, dfk, dl, st)) != H2Y_OK) return s;
-            skip_clean = 1;
+            int three = 0;
+            if ((s = launch_forward_exr420(c, *p, k, tmp.bit_depth, src, src_stride, dst, dst_stride, nf, dfk, dl, st, &three)) != H2Y_OK) return s;
+            skip_clean = three ? 2 : 1;
         }
         if ((s = launch_forward_fused(c, *p, k, src, src_stride, dst, dst_stride, nf, dfk, dl, st, skip_clean)) != H2Y_OK) return s;
         if (c->profile_on) { cudaEventRecord(pev[2], st); c->profile_count++; }

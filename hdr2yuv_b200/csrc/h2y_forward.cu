@@ -43,7 +43,7 @@ struct FwdArgs {
     int layout;
     int use_lut;             // transfer changes: per-frame LUT gather
     int exact_math;          // force the reference-order FP64 path for every pixel (debug / tests)
-    int skip_clean;          // frames flagged clean were converted by the v2 kernel (h2y_forward2.cu)
+    int skip_clean;          // 1: frames flagged clean were converted by the fast kernels (h2y_forward2.cu); 2: clean3 frames too
     int strip_w, nstrips, seg_rows, nsegs, nitems;
     PixK k;
     const FrameK *framek;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_fused(const FwdArgs a)
         const int strip = item % a.nstrips;
         const int seg = (item / a.nstrips) % a.nsegs;
         const int frame = item / (a.nstrips * a.nsegs);
-        if (a.skip_clean && a.framek[frame].clean) continue;          // uniform per CTA
+        if (a.skip_clean && (a.framek[frame].clean || (a.skip_clean > 1 && a.framek[frame].clean3))) continue;   // uniform per CTA
         const uint8_t *fsrc = a.src + (size_t)frame * a.src_stride;
         uint16_t *fY = reinterpret_cast<uint16_t *>(a.dst + (size_t)frame * a.dst_stride);
         uint16_t *fCb = fY + (size_t)w * h;

@@ -172,9 +172,11 @@ __device__ __forceinline__ float lds_lut(unsigned lut, unsigned code)
 // ---- per-lane: 8 pixels -> luma (floor bits, not yet clamped) and chroma as floats ---------------------------
 // TWO:   `lut` holds two pre-scaled copies (luma scale, then chroma scale at +LUT2_CODES); chroma comes without
 //        Half-1 and without matrix_convert's clamp (two_lut_frame() has checked that it cannot bind).
+// lutB / lutR: table bases of the B and R channels when each channel has its own table (three-table frames); the
+// callers with one table pass `lut` three times and the compiler sees one value.
 template <int MK, int CFG = 0, bool TWO = false>
-__device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, const unsigned g[8], const unsigned b[8],
-                                            const unsigned r[8], unsigned ybits[8], u64 chroma[8])
+__device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, unsigned lutB, unsigned lutR, const unsigned g[8],
+                                            const unsigned b[8], const unsigned r[8], unsigned ybits[8], u64 chroma[8])
 {
     typedef KC<CFG> C;
     const PixK &k = a.k;
@@ -206,8 +208,8 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, const u
                 R2[p] = pk(lds_lut<LUT2_CODES * 4>(lut, r[q]), lds_lut<LUT2_CODES * 4>(lut, r[q + 1]));
             } else {
                 G2[p] = fadd2(fmul2s(lds_lut<0>(lut, g[q]), lds_lut<0>(lut, g[q + 1]), C::mulY(a)), addY2);
-                B2[p] = fadd2(fmul2s(lds_lut<0>(lut, b[q]), lds_lut<0>(lut, b[q + 1]), C::mulC(a)), addC2);
-                R2[p] = fadd2(fmul2s(lds_lut<0>(lut, r[q]), lds_lut<0>(lut, r[q + 1]), C::mulC(a)), addC2);
+                B2[p] = fadd2(fmul2s(lds_lut<0>(lutB, b[q]), lds_lut<0>(lutB, b[q + 1]), C::mulC(a)), addC2);
+                R2[p] = fadd2(fmul2s(lds_lut<0>(lutR, r[q]), lds_lut<0>(lutR, r[q + 1]), C::mulC(a)), addC2);
             }
             u64 y1, y2, base;
             if (MK == MK_YCBCR) {
@@ -260,8 +262,8 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, const u
                         Gs = lds_lut<0>(lut, g[q0 + i]); Bs = lds_lut<LUT2_CODES * 4>(lut, b[q0 + i]); Rs = lds_lut<LUT2_CODES * 4>(lut, r[q0 + i]);
                     } else {
                         Gs = __fadd_rn(__fmul_rn(lds_lut<0>(lut, g[q0 + i]), C::mulY(a)), C::addY(a));
-                        Bs = __fadd_rn(__fmul_rn(lds_lut<0>(lut, b[q0 + i]), C::mulC(a)), C::addC(a));
-                        Rs = __fadd_rn(__fmul_rn(lds_lut<0>(lut, r[q0 + i]), C::mulC(a)), C::addC(a));
+                        Bs = __fadd_rn(__fmul_rn(lds_lut<0>(lutB, b[q0 + i]), C::mulC(a)), C::addC(a));
+                        Rs = __fadd_rn(__fmul_rn(lds_lut<0>(lutR, r[q0 + i]), C::mulC(a)), C::addC(a));
                     }
                     unsigned Ye, Cbe, Cre;
                     pixel_exact<MK>(Gs, Bs, Rs, k, Ye, Cbe, Cre);
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
                 }
                 split_codes<NCH>(raw, g, b, r);
                 uint4 ypack;
-                if (SRC == 0) { unsigned yb[8]; pixels8<MK>(a, lut_sa, g, b, r, yb, ch); ypack = pack_luma<0>(a, yb); }
+                if (SRC == 0) { unsigned yb[8]; pixels8<MK>(a, lut_sa, lut_sa, lut_sa, g, b, r, yb, ch); ypack = pack_luma<0>(a, yb); }
                 else pixels8_u16<MK>(a.k, g, b, r, ypack, ch, fallbacks);
                 if (lane_interior && row >= ys && row < ye) *reinterpret_cast<uint4 *>(fY + (size_t)row * w + xl) = ypack;
             }
@@ -604,7 +606,8 @@ struct Fwd3Args {
 
 constexpr int THREADS3 = 512, WARPS3 = THREADS3 / 32;     // 16 warps (12 x 168 registers measured 6 % slower: latency hiding wins)
 
-template <int MK, int NCH, int CFG = 0, bool TWO = false>
+// THREE: the instantiation for frames whose channels need a table each (FrameK::clean3); TWO must be false
+template <int MK, int NCH, int CFG = 0, bool TWO = false, bool THREE = false>
 __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3Args A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -637,6 +640,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
     const int f_first = (int)(c0 / h), f_last = (int)((c1 - 1) / h);
     int cur_slot = -1;
     unsigned cur_lo = 1, cur_hi = 0;
+    unsigned lut3G = lut_sa, lut3B = lut_sa, lut3R = lut_sa;     // per-channel table bases (THREE); one table otherwise
 
     const u64 kv[12] = {pk(5.0f / 512.0f, 5.0f / 512.0f), pk(11.0f / 512.0f, 11.0f / 512.0f),
                         pk(-21.0f / 512.0f, -21.0f / 512.0f), pk(-37.0f / 512.0f, -37.0f / 512.0f),
@@ -647,10 +651,27 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
 
     for (int frame = f_first; frame <= f_last; frame++) {
         const FrameK &fk = a.framek[frame];
-        if (!fk.clean) continue;                         // uniform per CTA: v1 converts this frame
-        if (A.split_by_lut2 && TWO != two_lut_frame<CFG>(a, fk)) continue;   // the other instantiation converts this frame
+        if (THREE ? !fk.clean3 : !fk.clean) continue;    // uniform per CTA: another launch converts this frame
+        if (!THREE && A.split_by_lut2 && TWO != two_lut_frame<CFG>(a, fk)) continue;   // the other instantiation converts this frame
         // ---- LUT for this frame (CTA-wide) ----
-        {
+        if (THREE) {
+            // three tables back to back, channel c holding codes ch_lo[c] .. ch_hi[c]; the base handed to the gathers is
+            // moved down by ch_lo[c] entries so that they index with the raw code
+            if (frame != cur_slot) {
+                __syncthreads();
+                unsigned off = 0;
+                for (int ch3 = 0; ch3 < 3; ch3++) {
+                    const float *gl = a.luts + (size_t)fk.lut_slot[ch3] * 65536;
+                    const unsigned lo = fk.ch_lo[ch3], hi = fk.ch_hi[ch3];
+                    for (unsigned c = lo + threadIdx.x; c <= hi; c += THREADS3) lut_s[off + c - lo] = __ldg(gl + c);
+                    const unsigned base = lut_sa + 4u * off - 4u * lo;
+                    if (ch3 == 0) lut3G = base; else if (ch3 == 1) lut3B = base; else lut3R = base;
+                    off += hi - lo + 1;
+                }
+                cur_slot = frame;
+                __syncthreads();
+            }
+        } else {
             const unsigned lo = fk.code_lo, hi = fk.code_hi;
             if (fk.lut_slot[0] != cur_slot || lo < cur_lo || hi > cur_hi) {
                 __syncthreads();                         // every warp is done with the previous LUT
@@ -708,7 +729,8 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                 split_codes<NCH>(raw, g, b, rr);
                 unsigned yb[8];
                 u64 ch[8];
-                pixels8<MK, CFG, TWO>(a, lut_sa, g, b, rr, yb, ch);
+                if (THREE) pixels8<MK, CFG, false>(a, lut3G, lut3B, lut3R, g, b, rr, yb, ch);
+                else pixels8<MK, CFG, TWO>(a, lut_sa, lut_sa, lut_sa, g, b, rr, yb, ch);
                 const uint4 ypack = pack_luma<CFG>(a, yb);
                 if (lane_interior && r >= ys && r < ye) *reinterpret_cast<uint4 *>(yp) = ypack;
                 float l3x = __shfl_up_sync(0xffffffffu, plo(ch[3]), 1), l3y = __shfl_up_sync(0xffffffffu, phi(ch[3]), 1);
@@ -1087,7 +1109,7 @@ static h2y_status launch_v2(h2y_ctx_impl *c, const Fwd2Args &a, int grid, size_t
 
 h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, int tmp_bit_depth,
                                  const void *d_src, size_t src_stride, void *d_dst, size_t dst_stride, int nframes,
-                                 const FrameK *d_framek, const float *d_luts, cudaStream_t st)
+                                 const FrameK *d_framek, const float *d_luts, cudaStream_t st, int *took_three_table_frames)
 {
     Fwd2Args a;
     a.src = (const uint8_t *)d_src; a.src_stride = src_stride;
@@ -1139,10 +1161,16 @@ h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, c
             const size_t smem3 = (size_t)LUT_MAX_CODES * sizeof(float);
             int g3 = grid_max;
             while (g3 > 1 && A3.total_rows / ((long)g3 * A3.sub) < 16) g3 >>= 1;   // forced on a tiny batch
+            // frames that need a table per channel (FrameK::clean3) get a third launch of the same kernel
+            const size_t smemT = (size_t)LUT3_FLOATS * sizeof(float);
+            if (took_three_table_frames) *took_three_table_frames = 1;
 #define L3(MKV, NC)                                                                                                        \
     do {                                                                                                                   \
         H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MKV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
         k_forward_exr420_rows<MKV, NC><<<g3, THREADS3, smem3, st>>>(A3);                                                  \
+        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MKV, NC, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT)); \
+        k_forward_exr420_rows<MKV, NC, 0, false, true><<<g3, THREADS3, smemT, st>>>(A3);                                  \
+        c->launches++;                                                                                                     \
     } while (0)
             // the headline configurations get their constants as immediates (KC<10>, KC<12>)
             const int sc = 1 << (tmp_bit_depth - 8);
@@ -1163,7 +1191,9 @@ h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, c
         k_forward_exr420_rows<MK_YCBCR, NC, DD, true><<<g3, THREADS3, smem2, st>>>(A3);                                   \
         H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
         k_forward_exr420_rows<MK_YCBCR, NC, DD, false><<<g3, THREADS3, smem3, st>>>(A3);                                  \
-        c->launches++;                                                                                                     \
+        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT)); \
+        k_forward_exr420_rows<MK_YCBCR, NC, DD, false, true><<<g3, THREADS3, smemT, st>>>(A3);                            \
+        c->launches += 2;                                                                                                  \
     } while (0)
                 if (tmp_bit_depth == 10) { if (nch == 3) L3C(3, 10); else L3C(4, 10); }
                 else { if (nch == 3) L3C(3, 12); else L3C(4, 12); }

@@ -23,7 +23,12 @@ struct FrameK {
     int clean;
     unsigned code_lo, code_hi;
     int lut2_ok;                // clean and code_hi < LUT2_CODES: two pre-scaled LUT copies fit in shared memory
+    // same preconditions but a table per channel (the channels' floor / ceiling differ, as in real footage): the rows
+    // kernel keeps three range-restricted tables, channel c indexed by code - ch_lo[c]; clean3 also says that they fit
+    int clean3;
+    unsigned ch_lo[3], ch_hi[3];
 };
+constexpr unsigned LUT3_FLOATS = 58000;  // three tables together: 232 000 B
 constexpr unsigned LUT2_CODES = 29000;   // 2 x 29000 floats = 232 000 B of the 232 448 B a CTA may use (half code 0x7148 ~ 10 800)
 
 struct h2y_ctx_impl {
@@ -107,7 +112,7 @@ h2y_status launch_forward_u16_420(h2y_ctx_impl *c, const h2y_forward_params &p, 
 bool forward_exr420_supported(const h2y_forward_params &p, const PixK &k, int tmp_bit_depth);
 h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, int tmp_bit_depth,
                                  const void *d_src, size_t src_stride, void *d_dst, size_t dst_stride, int nframes,
-                                 const FrameK *d_framek, const float *d_luts, cudaStream_t st);
+                                 const FrameK *d_framek, const float *d_luts, cudaStream_t st, int *took_three_table_frames = nullptr);
 h2y_status launch_forward_fused(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, const void *d_src,
                                 size_t src_stride, void *d_dst, size_t dst_stride, int nframes,
                                 const FrameK *d_framek, const float *d_luts, cudaStream_t st, int skip_clean = 0);

@@ -350,7 +350,7 @@ k_stats_u16_planes(const uint16_t *__restrict__ p0, const uint16_t *__restrict__
 }
 
 // Turn extrema into estimated floor / ceiling, offset / range and LUT slots.  One block.
-__global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_float, int bit_depth)
+__global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_float, int bit_depth, int is_half)
 {
     const int n = nframes * 3;
     for (int p = threadIdx.x; p < n; p += blockDim.x) {
@@ -404,6 +404,15 @@ __global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_fl
         f.clean = is_float && f.same_lut && ulo <= uhi && uhi < 0x7C00u && f.range[0] > 0.0f && f.range[1] > 0.0f &&
                   f.range[2] > 0.0f;
         f.lut2_ok = f.clean && uhi < LUT2_CODES;
+        // a table per channel: the extrema are half values here, so their bit patterns bound the channel's codes
+        unsigned need = 0;
+        for (int c = 0; c < 3; c++) {
+            f.ch_lo[c] = __half_as_ushort(__float2half_rn(f.fmin[c]));
+            f.ch_hi[c] = __half_as_ushort(__float2half_rn(f.fmax[c]));
+            need += f.ch_hi[c] >= f.ch_lo[c] ? f.ch_hi[c] - f.ch_lo[c] + 1 : LUT3_FLOATS + 1;
+        }
+        f.clean3 = is_half && !f.same_lut && ulo <= uhi && uhi < 0x7C00u && f.range[0] > 0.0f && f.range[1] > 0.0f &&
+                   f.range[2] > 0.0f && need <= LUT3_FLOATS;
     }
 }
 
@@ -467,7 +476,7 @@ h2y_status launch_stats_and_luts(h2y_ctx_impl *c, const h2y_forward_params &p, c
     else
         k_stats_codes<false><<<grid, 256, 0, st>>>((const uint16_t *)d_src, src_stride / 2, p.src.layout, npix,
                                                    k.clip_on_load, k.loadLo, k.loadHi, (unsigned *)slots);
-    k_plan<<<1, 256, 0, st>>>((const unsigned *)slots, (FrameK *)fk, nframes, half ? 1 : 0, p.src.bit_depth);
+    k_plan<<<1, 256, 0, st>>>((const unsigned *)slots, (FrameK *)fk, nframes, half ? 1 : 0, p.src.bit_depth, half ? 1 : 0);
     k_build_lut<<<dim3(256, nframes * 3), 256, 0, st>>>((const FrameK *)fk, (float *)luts, half ? 1 : 0, k.tf_linearise,
                                                          k.tf_encode, k.clip_on_load, k.loadLo, k.loadHi);
     c->launches += 4;
@@ -496,7 +505,7 @@ h2y_status launch_stats_planar(h2y_ctx_impl *c, const h2y_pic_desc &pic, const v
     else
         k_stats_u16_planes<<<blocks, 256, 0, st>>>((const uint16_t *)d_planes[0], (const uint16_t *)d_planes[1],
                                                    (const uint16_t *)d_planes[2], n0, n12, (unsigned *)slots);
-    k_plan<<<1, 256, 0, st>>>((const unsigned *)slots, (FrameK *)fk, 1, isf ? 1 : 0, pic.bit_depth);
+    k_plan<<<1, 256, 0, st>>>((const unsigned *)slots, (FrameK *)fk, 1, isf ? 1 : 0, pic.bit_depth, 0);
     c->launches += 3;
     H2Y_CUDA(c, cudaGetLastError());
     *d_framek = (FrameK *)fk;

@@ -233,8 +233,8 @@ def test_large_4k_batch_takes_rows_kernel_and_matches_oracle(ctx):
     frames = [base[i % 2] for i in range(n)]
     before = ctx.kernel_launches
     got = G.gpu_forward(ctx, frames, _HALF, dst)
-    # init, stats, plan, LUT, rows kernel (two-LUT instantiation + single-LUT instantiation), general-kernel sweep
-    assert ctx.kernel_launches - before == 7
+    # init, stats, plan, LUT, rows kernel (two-LUT, single-LUT and three-table instantiations), general-kernel sweep
+    assert ctx.kernel_launches - before == 8
     for i in (0, 1):
         G.compare_codes(got[i], G.oracle_forward(base[i], _HALF, dst), True, "4K frame %d" % i)
     for i in range(2, n):
@@ -369,3 +369,29 @@ def test_large_1080p_tiff_batch_takes_rows_kernel_and_matches_oracle(ctx):
         G.compare_codes(got[i], G.oracle_forward(base[i], _TIFF, dst), False, "1080p frame %d" % i)
     for i in range(3, n):
         assert np.array_equal(got[i], got[i % 3]), i
+
+
+@pytest.mark.parametrize("depth,matrix", [(10, 9), (12, 9), (10, 11), (10, 1)])
+def test_rows_kernel_three_table_frames(ctx, monkeypatch, depth, matrix):
+    # Real footage: the channels' (int)min / (int)max differ, so the reference normalises each channel on its own
+    # (common.cpp:135-136, convert.cpp:936-940) and a frame needs three transfer tables.  The rows kernel keeps three
+    # range-restricted tables in shared memory when they fit (FrameK::clean3); other frames of the same call still go
+    # to the single-table instantiations or, when nothing fits, to the general kernel.
+    monkeypatch.setenv("H2Y_FORWARD_KERNEL", "rows")
+    w, h = 480, 130
+    dst = dict(bit_depth=depth, full_range=0, transfer=16, primaries=9, matrix=matrix, chroma=1, resampler=1)
+    rng = np.random.default_rng(7)
+
+    def footage(seed, top=(900.0, 650.0, 400.0), bottom=0.02):
+        v = np.exp(rng.uniform(np.log(bottom), np.log(1.0), (h, w, 3))) * np.array(top)
+        v = v.astype(np.float16)
+        for c in range(3):
+            v[seed % h, (seed * 7 + c) % w, c] = np.float16(top[c])      # pin each channel's maximum
+        return np.ascontiguousarray(v).view(np.uint16)
+
+    frames = [footage(1), synth.exr_half_frame(w, h, seed=2, channels=3),            # three tables; one table
+              footage(3, top=(4000.0, 3000.5, 1999.0)), footage(4, top=(100.0, 100.9, 100.2)),   # three; one (same ints)
+              footage(5, top=(4000.0, 2500.0, 1200.0), bottom=1e-5)]                  # code ranges too wide: general kernel
+    got = G.gpu_forward(ctx, frames, _HALF, dst)
+    for i, f in enumerate(frames):
+        G.compare_codes(got[i], G.oracle_forward(f, _HALF, dst), True, "frame %d" % i)
