@@ -641,6 +641,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
     int cur_slot = -1;
     unsigned cur_lo = 1, cur_hi = 0;
     unsigned lut3G = lut_sa, lut3B = lut_sa, lut3R = lut_sa;     // per-channel table bases (THREE); one table otherwise
+    unsigned floor_rg = 0, floor_br = 0, floor_gb = 0;           // THREE: codes are raised to the table's first entry
 
     const u64 kv[12] = {pk(5.0f / 512.0f, 5.0f / 512.0f), pk(11.0f / 512.0f, 11.0f / 512.0f),
                         pk(-21.0f / 512.0f, -21.0f / 512.0f), pk(-37.0f / 512.0f, -37.0f / 512.0f),
@@ -663,11 +664,16 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                 for (int ch3 = 0; ch3 < 3; ch3++) {
                     const float *gl = a.luts + (size_t)fk.lut_slot[ch3] * 65536;
                     const unsigned lo = fk.ch_lo[ch3], hi = fk.ch_hi[ch3];
-                    for (unsigned c = lo + threadIdx.x; c <= hi; c += THREADS3) lut_s[off + c - lo] = __ldg(gl + c);
+                    for (unsigned c = lo + threadIdx.x; c <= hi; c += THREADS3)
+                        lut_s[off + c - lo] = __ldg(gl + (c == lo && fk.zero_entry[ch3] ? 0u : c));
                     const unsigned base = lut_sa + 4u * off - 4u * lo;
                     if (ch3 == 0) lut3G = base; else if (ch3 == 1) lut3B = base; else lut3R = base;
                     off += hi - lo + 1;
                 }
+                // packed floors for the three word kinds of an RGB row, (R,G) (B,R) (G,B); RGBA rows have (R,G) (B,A)
+                floor_rg = fk.ch_lo[2] | (fk.ch_lo[0] << 16);
+                floor_br = fk.ch_lo[1] | (NCH == 3 ? fk.ch_lo[2] << 16 : 0u);
+                floor_gb = fk.ch_lo[0] | (fk.ch_lo[1] << 16);
                 cur_slot = frame;
                 __syncthreads();
             }
@@ -726,6 +732,21 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
             auto next_src = [&](int r) { sp += ((unsigned)r < (unsigned)(h - 1)) ? spitch : 0; };
             auto row_front = [&](const RawPx<NCH> &raw, int r, u64 o[4]) {
                 unsigned g[8], b[8], rr[8];
+                if (THREE) {
+                    // raise every code to its table's first entry (only exact zeros move: FrameK::zero_entry)
+                    RawPx<NCH> cl = raw;
+#pragma unroll
+                    for (int i = 0; i < NCH; i++) {
+                        unsigned *wv = reinterpret_cast<unsigned *>(&cl.v[i]);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int kind = NCH == 3 ? (4 * i + j) % 3 : (j & 1);
+                            const unsigned fl = NCH == 3 ? (kind == 0 ? floor_rg : (kind == 1 ? floor_br : floor_gb)) : (kind == 0 ? floor_rg : floor_br);
+                            asm("max.u16x2 %0, %0, %1;" : "+r"(wv[j]) : "r"(fl));
+                        }
+                    }
+                    split_codes<NCH>(cl, g, b, rr);
+                } else
                 split_codes<NCH>(raw, g, b, rr);
                 unsigned yb[8];
                 u64 ch[8];

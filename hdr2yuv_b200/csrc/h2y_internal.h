@@ -27,6 +27,7 @@ struct FrameK {
     // kernel keeps three range-restricted tables, channel c indexed by code - ch_lo[c]; clean3 also says that they fit
     int clean3;
     unsigned ch_lo[3], ch_hi[3];
+    int zero_entry[3];          // table entry ch_lo[c] holds the value of code 0 (see k_plan)
 };
 constexpr unsigned LUT3_FLOATS = 58000;  // three tables together: 232 000 B
 constexpr unsigned LUT2_CODES = 29000;   // 2 x 29000 floats = 232 000 B of the 232 448 B a CTA may use (half code 0x7148 ~ 10 800)

@@ -25,12 +25,25 @@ __device__ __forceinline__ float fkey_inv(unsigned k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// stats slots: [frame][8] = {min key, max key} x 3 channels, then min and max RAW 16-bit code
-constexpr int SLOTS = 8;
+// stats slots: [frame][12] = {min key, max key} x 3 channels, then min and max RAW 16-bit code, then (half sources,
+// vector kernel) per channel G,B,R the smallest NONZERO raw code minus one (0xffffffff: not collected)
+constexpr int SLOTS = 12;
 __global__ void k_stats_init(unsigned *slots, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) slots[i] = (i & 1) ? 0u : 0xffffffffu;
+    if (i < n) {
+        const int j = i % SLOTS;
+        slots[i] = j >= 8 ? 0xffffffffu : ((j & 1) ? 0u : 0xffffffffu);
+    }
+}
+
+// min(acc, w - 1) on both 16-bit halves, one VIADDMNMX: zero codes wrap to 0xffff and drop out of the minimum
+__device__ __forceinline__ unsigned nzmin(unsigned acc, unsigned w)
+{
+    unsigned t;
+    asm("add.u16x2 %0, %1, %2;" : "=r"(t) : "r"(w), "r"(0xffffffffu));
+    asm("min.u16x2 %0, %0, %1;" : "+r"(acc) : "r"(t));
+    return acc;
 }
 
 // One block-strided pass over a frame; 16-bit code layouts.  grid = (blocks, nframes).
@@ -142,6 +155,7 @@ k_stats_vec(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int
     const uint8_t *f = src + (size_t)blockIdx.y * frame_stride;
     unsigned mnv[3], mxv[3];        // per word kind (interleaved) or per plane (planar), two lanes each
     unsigned umn = 0xFFFFFFFFu, umx = 0u;   // half input: extrema of the RAW codes of the colour channels (packed)
+    unsigned nzv[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};     // half input, 3 channels: smallest nonzero code - 1, per word kind
 #pragma unroll
     for (int i = 0; i < 3; i++) { mnv[i] = P::MIN_INIT; mxv[i] = P::MAX_INIT; }
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long)gridDim.x * blockDim.x;
@@ -150,9 +164,9 @@ k_stats_vec(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int
         // (n + w) mod 3 at position w, kinds 0 = (R,G), 1 = (B,R), 2 = (G,B); the grid stride is a multiple of
         // 3 vectors, so a thread's phase n mod 3 never changes and it can accumulate per word POSITION.
         const long nvec = npix * 6 / 16;
-        unsigned pmn[4], pmx[4];
+        unsigned pmn[4], pmx[4], pnz[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { pmn[i] = P::MIN_INIT; pmx[i] = P::MAX_INIT; }
+        for (int i = 0; i < 4; i++) { pmn[i] = P::MIN_INIT; pmx[i] = P::MAX_INIT; pnz[i] = 0xFFFFFFFFu; }
         const uint4 *p = reinterpret_cast<const uint4 *>(f);
         long n = tid;
         for (; n + 3 * nthr < nvec; n += 4 * nthr) {
@@ -170,6 +184,8 @@ k_stats_vec(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int
                     typedef Pk<false> U;
                     umx = U::mx(umx, U::mx(U::mx(v[j].x, v[j].y), U::mx(v[j].z, v[j].w)));
                     umn = U::mn(umn, U::mn(U::mn(v[j].x, v[j].y), U::mn(v[j].z, v[j].w)));
+                    pnz[0] = nzmin(pnz[0], v[j].x); pnz[1] = nzmin(pnz[1], v[j].y);
+                    pnz[2] = nzmin(pnz[2], v[j].z); pnz[3] = nzmin(pnz[3], v[j].w);
                 }
             }
         }
@@ -183,6 +199,7 @@ k_stats_vec(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int
                 typedef Pk<false> U;
                 umx = U::mx(umx, U::mx(U::mx(v.x, v.y), U::mx(v.z, v.w)));
                 umn = U::mn(umn, U::mn(U::mn(v.x, v.y), U::mn(v.z, v.w)));
+                pnz[0] = nzmin(pnz[0], v.x); pnz[1] = nzmin(pnz[1], v.y); pnz[2] = nzmin(pnz[2], v.z); pnz[3] = nzmin(pnz[3], v.w);
             }
         }
         const int ph = (int)(tid % 3);                        // kind of word w is (ph + w) % 3
@@ -191,7 +208,10 @@ k_stats_vec(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int
             const int kind = (ph + wd) % 3;
 #pragma unroll
             for (int kk = 0; kk < 3; kk++)
-                if (kind == kk) { mnv[kk] = P::mn(mnv[kk], pmn[wd]); mxv[kk] = P::mx(mxv[kk], pmx[wd]); }
+                if (kind == kk) {
+                    mnv[kk] = P::mn(mnv[kk], pmn[wd]); mxv[kk] = P::mx(mxv[kk], pmx[wd]);
+                    nzv[kk] = Pk<false>::mn(nzv[kk], pnz[wd]);
+                }
         }
     } else if (NCH == 4) {
         const long nvec = npix / 2;                           // 2 pixels per uint4: (R,G)(B,A)(R,G)(B,A)
@@ -232,12 +252,15 @@ k_stats_vec(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int
         for (int o = 16; o > 0; o >>= 1) {
             umn = U::mn(umn, __shfl_xor_sync(0xffffffffu, umn, o));
             umx = U::mx(umx, __shfl_xor_sync(0xffffffffu, umx, o));
+#pragma unroll
+            for (int i = 0; i < 3; i++) nzv[i] = U::mn(nzv[i], __shfl_xor_sync(0xffffffffu, nzv[i], o));
         }
     }
-    __shared__ unsigned red[8][8];
+    __shared__ unsigned red[8][12];
     if ((threadIdx.x & 31) == 0) {
         unsigned *r = red[threadIdx.x >> 5];
         r[0] = mnv[0]; r[1] = mnv[1]; r[2] = mnv[2]; r[3] = mxv[0]; r[4] = mxv[1]; r[5] = mxv[2]; r[6] = umn; r[7] = umx;
+        r[8] = nzv[0]; r[9] = nzv[1]; r[10] = nzv[2];
     }
     __syncthreads();
     if (threadIdx.x >= 32) return;
@@ -253,11 +276,22 @@ k_stats_vec(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int
             c0 = U::mn(c0, __shfl_xor_sync(0xffffffffu, c0, o)); c1 = U::mx(c1, __shfl_xor_sync(0xffffffffu, c1, o));
         }
         mnv[0] = a0; mnv[1] = a1; mnv[2] = a2; mxv[0] = b0; mxv[1] = b1; mxv[2] = b2; umn = c0; umx = c1;
+        unsigned z0 = red[wsrc][8], z1 = red[wsrc][9], z2 = red[wsrc][10];
+        for (int o = 4; o > 0; o >>= 1) {
+            z0 = U::mn(z0, __shfl_xor_sync(0xffffffffu, z0, o)); z1 = U::mn(z1, __shfl_xor_sync(0xffffffffu, z1, o));
+            z2 = U::mn(z2, __shfl_xor_sync(0xffffffffu, z2, o));
+        }
+        nzv[0] = z0; nzv[1] = z1; nzv[2] = z2;
     }
     if (HALF) {
         if (threadIdx.x == 0) {
             atomicMin(&slots[blockIdx.y * SLOTS + 6], min(umn & 0xffffu, umn >> 16));
             atomicMax(&slots[blockIdx.y * SLOTS + 7], max(umx & 0xffffu, umx >> 16));
+            if (NCH == 3) {     // the (word kind, half) pairs of G, B, R: as for the extrema below
+                atomicMin(&slots[blockIdx.y * SLOTS + 8], min(nzv[0] >> 16, nzv[2] & 0xffffu));
+                atomicMin(&slots[blockIdx.y * SLOTS + 9], min(nzv[1] & 0xffffu, nzv[2] >> 16));
+                atomicMin(&slots[blockIdx.y * SLOTS + 10], min(nzv[0] & 0xffffu, nzv[1] >> 16));
+            }
         }
     } else if (threadIdx.x == 0 && blockIdx.x == 0) {
         slots[blockIdx.y * SLOTS + 6] = 0u; slots[blockIdx.y * SLOTS + 7] = 0xffffu;     // integer codes: not the v2 route
@@ -409,6 +443,12 @@ __global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_fl
         for (int c = 0; c < 3; c++) {
             f.ch_lo[c] = __half_as_ushort(__float2half_rn(f.fmin[c]));
             f.ch_hi[c] = __half_as_ushort(__float2half_rn(f.fmax[c]));
+            // exact zeros (black bars) would stretch the table down to code 0: when the pass collected the smallest
+            // nonzero code, the table starts one entry below it and that entry holds the value of code 0; the kernel
+            // raises every code to ch_lo first, which only moves the zeros
+            const unsigned nzm1 = slots[fi * SLOTS + 8 + c];
+            f.zero_entry[c] = 0;
+            if (f.ch_lo[c] == 0 && nzm1 < 0xffffu && nzm1 + 1 <= f.ch_hi[c]) { f.ch_lo[c] = nzm1; f.zero_entry[c] = 1; }
             need += f.ch_hi[c] >= f.ch_lo[c] ? f.ch_hi[c] - f.ch_lo[c] + 1 : LUT3_FLOATS + 1;
         }
         f.clean3 = is_half && !f.same_lut && ulo <= uhi && uhi < 0x7C00u && f.range[0] > 0.0f && f.range[1] > 0.0f &&

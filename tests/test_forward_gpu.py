@@ -392,6 +392,9 @@ def test_rows_kernel_three_table_frames(ctx, monkeypatch, depth, matrix):
     frames = [footage(1), synth.exr_half_frame(w, h, seed=2, channels=3),            # three tables; one table
               footage(3, top=(4000.0, 3000.5, 1999.0)), footage(4, top=(100.0, 100.9, 100.2)),   # three; one (same ints)
               footage(5, top=(4000.0, 2500.0, 1200.0), bottom=1e-5)]                  # code ranges too wide: general kernel
+    # exact zeros (black bars) in some or all channels: the tables start one entry below the smallest nonzero code
+    z = footage(6).copy(); z[:9] = 0; z[-7:, :, 1] = 0; frames.append(z)
+    z = footage(7, top=(3000.0, 2000.0, 1000.0)).copy(); z[40:50, 100:300, 2] = 0; z[3, 5, 0] = 1; frames.append(z)   # and a denormal
     got = G.gpu_forward(ctx, frames, _HALF, dst)
     for i, f in enumerate(frames):
         G.compare_codes(got[i], G.oracle_forward(f, _HALF, dst), True, "frame %d" % i)
