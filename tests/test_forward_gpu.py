@@ -398,3 +398,8 @@ def test_rows_kernel_three_table_frames(ctx, monkeypatch, depth, matrix):
     got = G.gpu_forward(ctx, frames, _HALF, dst)
     for i, f in enumerate(frames):
         G.compare_codes(got[i], G.oracle_forward(f, _HALF, dst), True, "frame %d" % i)
+    # Imf::Rgba rows (alpha = 1.0 rides along and must not enter any table index)
+    rgba = [np.concatenate([f, np.full((h, w, 1), 0x3C00, np.uint16)], -1) for f in frames[:3]]
+    got = G.gpu_forward(ctx, rgba, _HALF, dst)
+    for i, f in enumerate(rgba):
+        G.compare_codes(got[i], G.oracle_forward(f, _HALF, dst), True, "rgba frame %d" % i)
