@@ -174,7 +174,9 @@ __device__ __forceinline__ float lds_lut(unsigned lut, unsigned code)
 //        Half-1 and without matrix_convert's clamp (two_lut_frame() has checked that it cannot bind).
 // lutB / lutR: table bases of the B and R channels when each channel has its own table (three-table frames); the
 // callers with one table pass `lut` three times and the compiler sees one value.
-template <int MK, int CFG = 0, bool TWO = false>
+// PRESC (three-table frames): the per-channel tables already carry their range scale (G: luma, B/R: chroma), like TWO's
+// two copies, but the clamp and the integer chroma path stay.
+template <int MK, int CFG = 0, bool TWO = false, bool PRESC = false>
 __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, unsigned lutB, unsigned lutR, const unsigned g[8],
                                             const unsigned b[8], const unsigned r[8], unsigned ybits[8], u64 chroma[8])
 {
@@ -206,6 +208,10 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, unsigne
                 G2[p] = pk(lds_lut<0>(lut, g[q]), lds_lut<0>(lut, g[q + 1]));
                 B2[p] = pk(lds_lut<LUT2_CODES * 4>(lut, b[q]), lds_lut<LUT2_CODES * 4>(lut, b[q + 1]));
                 R2[p] = pk(lds_lut<LUT2_CODES * 4>(lut, r[q]), lds_lut<LUT2_CODES * 4>(lut, r[q + 1]));
+            } else if (PRESC) {
+                G2[p] = pk(lds_lut<0>(lut, g[q]), lds_lut<0>(lut, g[q + 1]));
+                B2[p] = pk(lds_lut<0>(lutB, b[q]), lds_lut<0>(lutB, b[q + 1]));
+                R2[p] = pk(lds_lut<0>(lutR, r[q]), lds_lut<0>(lutR, r[q + 1]));
             } else {
                 G2[p] = fadd2(fmul2s(lds_lut<0>(lut, g[q]), lds_lut<0>(lut, g[q + 1]), C::mulY(a)), addY2);
                 B2[p] = fadd2(fmul2s(lds_lut<0>(lutB, b[q]), lds_lut<0>(lutB, b[q + 1]), C::mulC(a)), addC2);
@@ -260,6 +266,8 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, unsigne
                     float Gs, Bs, Rs;
                     if (TWO) {
                         Gs = lds_lut<0>(lut, g[q0 + i]); Bs = lds_lut<LUT2_CODES * 4>(lut, b[q0 + i]); Rs = lds_lut<LUT2_CODES * 4>(lut, r[q0 + i]);
+                    } else if (PRESC) {
+                        Gs = lds_lut<0>(lut, g[q0 + i]); Bs = lds_lut<0>(lutB, b[q0 + i]); Rs = lds_lut<0>(lutR, r[q0 + i]);
                     } else {
                         Gs = __fadd_rn(__fmul_rn(lds_lut<0>(lut, g[q0 + i]), C::mulY(a)), C::addY(a));
                         Bs = __fadd_rn(__fmul_rn(lds_lut<0>(lutB, b[q0 + i]), C::mulC(a)), C::addC(a));
@@ -664,8 +672,10 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                 for (int ch3 = 0; ch3 < 3; ch3++) {
                     const float *gl = a.luts + (size_t)fk.lut_slot[ch3] * 65536;
                     const unsigned lo = fk.ch_lo[ch3], hi = fk.ch_hi[ch3];
+                    // with the range scale applied exactly as convert.cpp:1141-1143 rounds it (G: luma, B and R: chroma)
+                    const float mul = ch3 == 0 ? C::mulY(a) : C::mulC(a), add = ch3 == 0 ? C::addY(a) : C::addC(a);
                     for (unsigned c = lo + threadIdx.x; c <= hi; c += THREADS3)
-                        lut_s[off + c - lo] = __ldg(gl + (c == lo && fk.zero_entry[ch3] ? 0u : c));
+                        lut_s[off + c - lo] = __fadd_rn(__fmul_rn(__ldg(gl + (c == lo && fk.zero_entry[ch3] ? 0u : c)), mul), add);
                     const unsigned base = lut_sa + 4u * off - 4u * lo;
                     if (ch3 == 0) lut3G = base; else if (ch3 == 1) lut3B = base; else lut3R = base;
                     off += hi - lo + 1;
@@ -750,7 +760,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                 split_codes<NCH>(raw, g, b, rr);
                 unsigned yb[8];
                 u64 ch[8];
-                if (THREE) pixels8<MK, CFG, false>(a, lut3G, lut3B, lut3R, g, b, rr, yb, ch);
+                if (THREE) pixels8<MK, CFG, false, true>(a, lut3G, lut3B, lut3R, g, b, rr, yb, ch);
                 else pixels8<MK, CFG, TWO>(a, lut_sa, lut_sa, lut_sa, g, b, rr, yb, ch);
                 const uint4 ypack = pack_luma<CFG>(a, yb);
                 if (lane_interior && r >= ys && r < ye) *reinterpret_cast<uint4 *>(yp) = ypack;
