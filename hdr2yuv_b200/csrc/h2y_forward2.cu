@@ -37,6 +37,9 @@
 #ifndef H2Y_GUARD_SHIFT
 #define H2Y_GUARD_SHIFT 22
 #endif
+#ifndef H2Y_PAIRS_PER_BRANCH_THREE
+#define H2Y_PAIRS_PER_BRANCH_THREE 1
+#endif
 // Pixel pairs per guard-band branch (1, 2 or 4): 2 measured fastest (profiles/r01/variants.md).
 #ifndef H2Y_PAIRS_PER_BRANCH
 #define H2Y_PAIRS_PER_BRANCH 2
@@ -193,7 +196,7 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, unsigne
     const unsigned maxCV = (unsigned)C::maxCV(a);
     // PG pixel pairs share one guard-band branch: fewer, larger basic blocks for the scheduler at the price of keeping
     // the scaled samples of PG pairs alive until the branch
-    constexpr int PG = H2Y_PAIRS_PER_BRANCH;
+    constexpr int PG = PRESC ? H2Y_PAIRS_PER_BRANCH_THREE : H2Y_PAIRS_PER_BRANCH;
 #pragma unroll
     for (int q0 = 0; q0 < 8; q0 += 2 * PG) {
         u64 G2[PG], B2[PG], R2[PG];
