@@ -87,8 +87,8 @@ def make_frame(wl, index):
     if wl["kind"] == "inverse":
         raise RuntimeError("inverse inputs are produced by the forward path")
     if wl["src_kind"] == "half":
-        if wl.get("content") == "natural" and ch == 3:
-            return synth.exr_half_frame_smooth_fast(wl["w"], wl["h"], seed=index)
+        if wl.get("content") in ("natural", "graded") and ch == 3:
+            return synth.exr_half_frame_smooth_fast(wl["w"], wl["h"], seed=index, peak_white=wl["content"] == "graded")
         return synth.exr_half_frame_fast(wl["w"], wl["h"], seed=index, channels=ch)
     return synth.tiff16_frame(wl["w"], wl["h"], seed=index + 1, channels=ch)
 
@@ -330,6 +330,9 @@ def bench_config(wl, name, frames_per_step):
         cfg["content"] = "iid log-uniform samples (SURVEY.md 8d config 2)" if wl["src_kind"] == "half" else "iid uniform codes"
         if wl.get("content") == "natural" and wl["src_kind"] == "half":
             cfg["content"] = "spatially correlated luminance field with colour cast and 2 % noise (--forward-content natural)"
+        if wl.get("content") == "graded" and wl["src_kind"] == "half":
+            cfg["content"] = ("the natural field plus one peak-white and one near-black pixel per frame, so the channels share "
+                              "floor and ceiling (--forward-content graded)")
     return cfg
 
 
@@ -557,7 +560,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the workload's)")
     ap.add_argument("--layout", choices=sorted(LAYOUT_BPP), default=None, help="override the source layout")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
-    ap.add_argument("--forward-content", choices=["iid", "natural"], default=None,
+    ap.add_argument("--forward-content", choices=["iid", "natural", "graded"], default=None,
                     help="forward EXR workloads: iid log-uniform samples (default, the headline; worst case for the LUT "
                          "gather) or a spatially correlated field, as a second data point")
     ap.add_argument("--content", choices=["smooth", "iid"], default="smooth",

@@ -41,6 +41,9 @@
 #define H2Y_PAIRS_PER_BRANCH_THREE 1
 #endif
 // Pixel pairs per guard-band branch (1, 2 or 4): 2 measured fastest (profiles/r01/variants.md).
+#ifndef H2Y_PAIRS_PER_BRANCH_THREE_NC
+#define H2Y_PAIRS_PER_BRANCH_THREE_NC 1
+#endif
 #ifndef H2Y_PAIRS_PER_BRANCH
 #define H2Y_PAIRS_PER_BRANCH 2
 #endif
@@ -160,6 +163,30 @@ __device__ __forceinline__ bool two_lut_frame(const Fwd2Args &a, const FrameK &f
     return vlo >= 0.0f && cb_hi < top && cr_hi < top && cb_lo > bot && cr_lo > bot && yhi < (float)C::maxCV(a);
 }
 
+// The same proof for a three-table frame (FrameK::clean3): each channel has its own table and code range, so the box
+// of scaled samples has a side per channel.  The table entry that stands for code 0 (FrameK::zero_entry) is the
+// channel's smallest value.  Evaluated identically by every CTA of both three-table instantiations.
+template <int CFG>
+__device__ __forceinline__ bool three_nc_frame(const Fwd2Args &a, const FrameK &fk)
+{
+    typedef KC<CFG> C;
+    float lo[3], hi[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float *gl = a.luts + (size_t)fk.lut_slot[c] * 65536;
+        const float vlo = __ldg(gl + (fk.zero_entry[c] ? 0u : fk.ch_lo[c])), vhi = __ldg(gl + fk.ch_hi[c]);
+        if (!(vlo >= 0.0f)) return false;
+        const float mul = c == 0 ? C::mulY(a) : C::mulC(a), add = c == 0 ? C::addY(a) : C::addC(a);
+        lo[c] = vlo * mul + add; hi[c] = vhi * mul + add;
+    }
+    // planes 0/1/2 = G/B/R; extremes of (B - Y')/db and (R - Y')/dr over the box, with Y' = wr R + wg G + wb B + 0.5
+    const float wr = C::wr(a), wg = C::wg(a), wb = C::wb(a);
+    const float cb_hi = (hi[1] - (wr * lo[2] + wg * lo[0] + wb * hi[1])) * C::rdb(a), cb_lo = (lo[1] - (wr * hi[2] + wg * hi[0] + wb * lo[1]) - 1.0f) * C::rdb(a);
+    const float cr_hi = (hi[2] - (wr * hi[2] + wg * lo[0] + wb * lo[1])) * C::rdr(a), cr_lo = (lo[2] - (wr * lo[2] + wg * hi[0] + wb * hi[1]) - 1.0f) * C::rdr(a);
+    const float top = (float)(C::maxCV(a) - C::half_m1(a)) - 2.0f, bot = 2.0f - (float)C::half_m1(a);
+    return cb_hi < top && cr_hi < top && cb_lo > bot && cr_lo > bot && hi[0] < (float)C::maxCV(a);
+}
+
 // LUT entry `code` of the table at shared-window address `lut` (+OFS bytes).  An explicit shared-space load: the
 // generic form makes ptxas rebuild the window base (S2UR + UMOV + ULEA) in front of every group of gathers.
 template <int OFS>
@@ -178,7 +205,7 @@ __device__ __forceinline__ float lds_lut(unsigned lut, unsigned code)
 // lutB / lutR: table bases of the B and R channels when each channel has its own table (three-table frames); the
 // callers with one table pass `lut` three times and the compiler sees one value.
 // PRESC (three-table frames): the per-channel tables already carry their range scale (G: luma, B/R: chroma), like TWO's
-// two copies, but the clamp and the integer chroma path stay.
+// two copies; the clamp and the integer chroma path stay unless TWO is set as well (three_nc_frame() has checked it).
 template <int MK, int CFG = 0, bool TWO = false, bool PRESC = false>
 __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, unsigned lutB, unsigned lutR, const unsigned g[8],
                                             const unsigned b[8], const unsigned r[8], unsigned ybits[8], u64 chroma[8])
@@ -196,7 +223,7 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, unsigne
     const unsigned maxCV = (unsigned)C::maxCV(a);
     // PG pixel pairs share one guard-band branch: fewer, larger basic blocks for the scheduler at the price of keeping
     // the scaled samples of PG pairs alive until the branch
-    constexpr int PG = PRESC ? H2Y_PAIRS_PER_BRANCH_THREE : H2Y_PAIRS_PER_BRANCH;
+    constexpr int PG = PRESC ? (TWO ? H2Y_PAIRS_PER_BRANCH_THREE_NC : H2Y_PAIRS_PER_BRANCH_THREE) : H2Y_PAIRS_PER_BRANCH;
 #pragma unroll
     for (int q0 = 0; q0 < 8; q0 += 2 * PG) {
         u64 G2[PG], B2[PG], R2[PG];
@@ -207,14 +234,14 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, unsigne
         for (int p = 0; p < PG; p++) {
             const int q = q0 + 2 * p;
             // LUT gather + range scale (two rounded operations each, convert.cpp:1141-1143)
-            if (TWO) {
-                G2[p] = pk(lds_lut<0>(lut, g[q]), lds_lut<0>(lut, g[q + 1]));
-                B2[p] = pk(lds_lut<LUT2_CODES * 4>(lut, b[q]), lds_lut<LUT2_CODES * 4>(lut, b[q + 1]));
-                R2[p] = pk(lds_lut<LUT2_CODES * 4>(lut, r[q]), lds_lut<LUT2_CODES * 4>(lut, r[q + 1]));
-            } else if (PRESC) {
+            if (PRESC) {
                 G2[p] = pk(lds_lut<0>(lut, g[q]), lds_lut<0>(lut, g[q + 1]));
                 B2[p] = pk(lds_lut<0>(lutB, b[q]), lds_lut<0>(lutB, b[q + 1]));
                 R2[p] = pk(lds_lut<0>(lutR, r[q]), lds_lut<0>(lutR, r[q + 1]));
+            } else if (TWO) {
+                G2[p] = pk(lds_lut<0>(lut, g[q]), lds_lut<0>(lut, g[q + 1]));
+                B2[p] = pk(lds_lut<LUT2_CODES * 4>(lut, b[q]), lds_lut<LUT2_CODES * 4>(lut, b[q + 1]));
+                R2[p] = pk(lds_lut<LUT2_CODES * 4>(lut, r[q]), lds_lut<LUT2_CODES * 4>(lut, r[q + 1]));
             } else {
                 G2[p] = fadd2(fmul2s(lds_lut<0>(lut, g[q]), lds_lut<0>(lut, g[q + 1]), C::mulY(a)), addY2);
                 B2[p] = fadd2(fmul2s(lds_lut<0>(lutB, b[q]), lds_lut<0>(lutB, b[q + 1]), C::mulC(a)), addC2);
@@ -267,10 +294,10 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, unsigne
                 if (flag[i]) {
                     // gathered again rather than kept alive across the branch (registers are the scarce resource here)
                     float Gs, Bs, Rs;
-                    if (TWO) {
-                        Gs = lds_lut<0>(lut, g[q0 + i]); Bs = lds_lut<LUT2_CODES * 4>(lut, b[q0 + i]); Rs = lds_lut<LUT2_CODES * 4>(lut, r[q0 + i]);
-                    } else if (PRESC) {
+                    if (PRESC) {
                         Gs = lds_lut<0>(lut, g[q0 + i]); Bs = lds_lut<0>(lutB, b[q0 + i]); Rs = lds_lut<0>(lutR, r[q0 + i]);
+                    } else if (TWO) {
+                        Gs = lds_lut<0>(lut, g[q0 + i]); Bs = lds_lut<LUT2_CODES * 4>(lut, b[q0 + i]); Rs = lds_lut<LUT2_CODES * 4>(lut, r[q0 + i]);
                     } else {
                         Gs = __fadd_rn(__fmul_rn(lds_lut<0>(lut, g[q0 + i]), C::mulY(a)), C::addY(a));
                         Bs = __fadd_rn(__fmul_rn(lds_lut<0>(lutB, b[q0 + i]), C::mulC(a)), C::addC(a));
@@ -612,12 +639,14 @@ struct Fwd3Args {
     int sub;                 // row workers per CTA (16 / strips when a picture has fewer than 16 strips)
     int wps;                 // warps per row worker = strips handled side by side
     int split_by_lut2;       // two instantiations share the frames: TWO takes those with lut2_ok, the other the rest
+    int split_three_nc;      // likewise for three-table frames: TWO (clamp-free) takes those three_nc_frame() accepts
     long total_rows;         // nframes * h
 };
 
 constexpr int THREADS3 = 512, WARPS3 = THREADS3 / 32;     // 16 warps (12 x 168 registers measured 6 % slower: latency hiding wins)
 
-// THREE: the instantiation for frames whose channels need a table each (FrameK::clean3); TWO must be false
+// THREE: the instantiation for frames whose channels need a table each (FrameK::clean3); with TWO as well: the
+// clamp-free chroma path on those three tables (frames that three_nc_frame() accepts)
 template <int MK, int NCH, int CFG = 0, bool TWO = false, bool THREE = false>
 __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3Args A)
 {
@@ -665,6 +694,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
         const FrameK &fk = a.framek[frame];
         if (THREE ? !fk.clean3 : !fk.clean) continue;    // uniform per CTA: another launch converts this frame
         if (!THREE && A.split_by_lut2 && TWO != two_lut_frame<CFG>(a, fk)) continue;   // the other instantiation converts this frame
+        if (THREE && A.split_three_nc && TWO != three_nc_frame<CFG>(a, fk)) continue;
         // ---- LUT for this frame (CTA-wide) ----
         if (THREE) {
             // three tables back to back, channel c holding codes ch_lo[c] .. ch_hi[c]; the base handed to the gathers is
@@ -763,7 +793,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                 split_codes<NCH>(raw, g, b, rr);
                 unsigned yb[8];
                 u64 ch[8];
-                if (THREE) pixels8<MK, CFG, false, true>(a, lut3G, lut3B, lut3R, g, b, rr, yb, ch);
+                if (THREE) pixels8<MK, CFG, TWO, true>(a, lut3G, lut3B, lut3R, g, b, rr, yb, ch);
                 else pixels8<MK, CFG, TWO>(a, lut_sa, lut_sa, lut_sa, g, b, rr, yb, ch);
                 const uint4 ypack = pack_luma<CFG>(a, yb);
                 if (lane_interior && r >= ys && r < ye) *reinterpret_cast<uint4 *>(yp) = ypack;
@@ -1188,6 +1218,7 @@ h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, c
         A3.sub = WARPS3 / A3.wps;
         A3.total_rows = (long)nframes * a.h;
         A3.split_by_lut2 = 0;
+        A3.split_three_nc = 0;
         const long rows_per_worker = A3.total_rows / ((long)grid_max * A3.sub);
         const char *force = getenv("H2Y_FORWARD_KERNEL");             // "ring" / "rows": tests and experiments
         const bool want_rows = force ? force[0] == 'r' && force[1] == 'o' : rows_per_worker >= 128;
@@ -1221,13 +1252,17 @@ h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, c
         /* frames whose code range allows two pre-scaled LUT copies, then the rest */                                      \
         const size_t smem2 = (size_t)2 * LUT2_CODES * sizeof(float);                                                       \
         A3.split_by_lut2 = 1;                                                                                              \
+        A3.split_three_nc = 1;                                                                                             \
         H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
         k_forward_exr420_rows<MK_YCBCR, NC, DD, true><<<g3, THREADS3, smem2, st>>>(A3);                                   \
         H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
         k_forward_exr420_rows<MK_YCBCR, NC, DD, false><<<g3, THREADS3, smem3, st>>>(A3);                                  \
         H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT)); \
         k_forward_exr420_rows<MK_YCBCR, NC, DD, false, true><<<g3, THREADS3, smemT, st>>>(A3);                            \
-        c->launches += 2;                                                                                                  \
+        /* three-table frames that provably stay inside matrix_convert's chroma clamp */                                   \
+        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT)); \
+        k_forward_exr420_rows<MK_YCBCR, NC, DD, true, true><<<g3, THREADS3, smemT, st>>>(A3);                             \
+        c->launches += 3;                                                                                                  \
     } while (0)
                 if (tmp_bit_depth == 10) { if (nch == 3) L3C(3, 10); else L3C(4, 10); }
                 else { if (nch == 3) L3C(3, 12); else L3C(4, 12); }

@@ -80,10 +80,12 @@ def exr_half_frame_fast(width, height, seed=0, channels=3):
     return px
 
 
-def exr_half_frame_smooth_fast(width, height, seed=0, block=16):
+def exr_half_frame_smooth_fast(width, height, seed=0, block=16, peak_white=False):
     """Spatially correlated linear-light frame (what decoded video looks like to the inverse path): a log-uniform
     luminance field at 1/block resolution, bilinearly smooth through a separable box blur, with a mild colour cast
-    per channel and 2 % pixel noise.  (H, W, 3) uint16 half bit patterns, all >= 0, max pinned to 4000."""
+    per channel and 2 % pixel noise.  (H, W, 3) uint16 half bit patterns, all >= 0, max pinned to 4000.
+    peak_white: one peak-white (4000, 4000, 4000) and one near-black pixel per frame, as in a graded master: the three
+    channels then share pic_stats' floor and ceiling (common.cpp:135-136) and the frame takes the single-table kernels."""
     rng = np.random.default_rng(seed)
     bh, bw = height // block + 2, width // block + 2
     low = np.exp(rng.uniform(np.log(0.05), np.log(2000.0), (bh, bw))).astype(np.float32)
@@ -98,4 +100,7 @@ def exr_half_frame_smooth_fast(width, height, seed=0, block=16):
     v = (lum[..., None] * cast * noise).astype(np.float16)
     flat = v.reshape(-1)
     flat[int(rng.integers(0, flat.size))] = np.float16(4000.0)
+    if peak_white:
+        v[int(rng.integers(0, height)), int(rng.integers(0, width))] = np.float16(4000.0)
+        v[int(rng.integers(0, height)), int(rng.integers(0, width))] = np.float16(0.01)
     return np.ascontiguousarray(v).view(np.uint16)

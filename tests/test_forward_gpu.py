@@ -233,8 +233,8 @@ def test_large_4k_batch_takes_rows_kernel_and_matches_oracle(ctx):
     frames = [base[i % 2] for i in range(n)]
     before = ctx.kernel_launches
     got = G.gpu_forward(ctx, frames, _HALF, dst)
-    # init, stats, plan, LUT, rows kernel (two-LUT, single-LUT and three-table instantiations), general-kernel sweep
-    assert ctx.kernel_launches - before == 8
+    # init, stats, plan, LUT, rows kernel (two-LUT, single-LUT and the two three-table instantiations), general-kernel sweep
+    assert ctx.kernel_launches - before == 9
     for i in (0, 1):
         G.compare_codes(got[i], G.oracle_forward(base[i], _HALF, dst), True, "4K frame %d" % i)
     for i in range(2, n):
@@ -395,6 +395,14 @@ def test_rows_kernel_three_table_frames(ctx, monkeypatch, depth, matrix):
     # exact zeros (black bars) in some or all channels: the tables start one entry below the smallest nonzero code
     z = footage(6).copy(); z[:9] = 0; z[-7:, :, 1] = 0; frames.append(z)
     z = footage(7, top=(3000.0, 2000.0, 1000.0)).copy(); z[40:50, 100:300, 2] = 0; z[3, 5, 0] = 1; frames.append(z)   # and a denormal
+    # Three-table frames that can reach matrix_convert's chroma clamp (convert.cpp:1207-1213) must keep it: channel
+    # maxima in [1, 4) give ranges of 1..3, normalised samples up to ~1.9 and PQ values above 1.  The clamp-free
+    # three-table instantiation (three_nc_frame) has to decline them; saturated primaries make the clamp bind.
+    frames.append(footage(8, top=(1.9, 2.5, 3.7)))
+    sat = footage(9, top=(1.9, 2.9, 3.9)).copy()
+    sat[::2, ::3, 0] = np.float16(1.9).view(np.uint16); sat[::2, ::3, 1:] = np.float16(0.05).view(np.uint16)
+    sat[1::2, 1::3, 2] = np.float16(3.9).view(np.uint16); sat[1::2, 1::3, :2] = np.float16(0.05).view(np.uint16)
+    frames.append(sat)
     got = G.gpu_forward(ctx, frames, _HALF, dst)
     for i, f in enumerate(frames):
         G.compare_codes(got[i], G.oracle_forward(f, _HALF, dst), True, "frame %d" % i)
