@@ -50,7 +50,7 @@ struct TiffReader {
     bool values(uint16_t type, uint32_t count, const uint8_t *field, std::vector<uint32_t> *out)
     {
         const size_t esz = type == 3 ? 2 : (type == 4 ? 4 : (type == 1 ? 1 : 0));
-        if (!esz) return false;
+        if (!esz || count > (1u << 24)) return false;              // a strip table never needs more than one entry per row
         std::vector<uint8_t> buf(esz * count);
         if (esz * count <= 4) memcpy(buf.data(), field, esz * count);
         else if (!file.read_at(buf.data(), buf.size(), u32(field))) return false;
@@ -97,6 +97,7 @@ struct TiffReader {
             }
         }
         if (!d.width || !d.height) return fail(err, "TIFF without dimensions");
+        if (d.width > 65535u || d.height > 65535u) return fail(err, "TIFF dimensions out of range");
         if (d.compression != 1) return fail(err, "compressed TIFF is not supported (baseline raw strips only)");
         if (d.bits != 16) return fail(err, "TIFF BitsPerSample must be 16");
         if (d.spp != 3 && d.spp != 4) return fail(err, "TIFF SamplesPerPixel must be 3 or 4");
@@ -175,7 +176,8 @@ bool exr_parse(File &f, ExrHeader *h, std::string *err)
         p += (size_t)asz;
     }
     h->table_offset = p;
-    if (h->width() < 1 || h->height() < 1) return fail(err, "EXR without a data window");
+    if (h->xmax < h->xmin || h->ymax < h->ymin) return fail(err, "EXR without a data window");
+    if ((int64_t)h->xmax - h->xmin >= 65535 || (int64_t)h->ymax - h->ymin >= 65535) return fail(err, "EXR data window out of range");
     if (h->compression != 0 && h->compression != 2 && h->compression != 3)
         return fail(err, "EXR compression must be NONE, ZIPS or ZIP");
     for (const auto &c : h->ch) {
@@ -367,6 +369,8 @@ bool exr_read_half(const std::string &path, uint16_t *dst, int out_channels, Ima
         const int nl = std::min(lpb, ht - y0);
         if (y0 < 0 || nl <= 0 || psize < 0) return fail(err, "bad EXR chunk");
         const size_t want = line_bytes * nl;
+        // a chunk is stored raw when compression does not make it smaller, so it is never larger than the lines it holds
+        if ((size_t)psize > want || (h.compression == 0 && (size_t)psize != want)) return fail(err, "bad EXR chunk size");
         packed.resize((size_t)psize);
         if (!f.read_at(packed.data(), packed.size(), table[b] + 8)) return fail(err, "short EXR chunk");
         const uint8_t *data;

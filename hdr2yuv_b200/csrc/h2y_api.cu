@@ -634,11 +634,19 @@ static h2y_status run_pipeline(h2y_ctx *c, const uint8_t *h_in, size_t in_stride
     void *din, *dout;
     if ((s = scratch_reserve(c, SCR_RING_IN, in_pitch * per * NB, &din)) != H2Y_OK) return s;
     if ((s = scratch_reserve(c, SCR_RING_OUT, out_pitch * per * NB, &dout)) != H2Y_OK) return s;
-    cudaEvent_t ev_h2d[NB], ev_comp[NB], ev_d2h[NB];
+    cudaEvent_t ev_h2d[NB] = {}, ev_comp[NB] = {}, ev_d2h[NB] = {};
+    auto drop_events = [&]() {
+        for (int i = 0; i < NB; i++) {
+            if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]);
+            if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
+            if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]);
+        }
+    };
     for (int i = 0; i < NB; i++) {
-        H2Y_CUDA(c, cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
-        H2Y_CUDA(c, cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
-        H2Y_CUDA(c, cudaEventCreateWithFlags(&ev_d2h[i], cudaEventDisableTiming));
+        cudaError_t e = cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_d2h[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) { drop_events(); return cuda_fail(c, e); }
     }
     h2y_status rs = H2Y_OK;
     int chunk = 0;
@@ -668,7 +676,7 @@ static h2y_status run_pipeline(h2y_ctx *c, const uint8_t *h_in, size_t in_stride
         cudaEventRecord(ev_d2h[slot], c->s_d2h);
     }
     cudaError_t e1 = cudaStreamSynchronize(c->s_h2d), e2 = cudaStreamSynchronize(c->s_compute), e3 = cudaStreamSynchronize(c->s_d2h);
-    for (int i = 0; i < NB; i++) { cudaEventDestroy(ev_h2d[i]); cudaEventDestroy(ev_comp[i]); cudaEventDestroy(ev_d2h[i]); }
+    drop_events();
     if (rs != H2Y_OK) return rs;
     if (e1 != cudaSuccess) return cuda_fail(c, e1);
     if (e2 != cudaSuccess) return cuda_fail(c, e2);

@@ -183,3 +183,60 @@ def test_dpx_10bit_reader_and_dump(cli, tmp_path, big_endian):
     rc, text = run([cli["hdr2yuv"], "--src_filename", str(tmp_path / "bad.dpx"), "--dst_filename", str(tmp_path / "o.yuv"),
                     "--dump_input", str(dump)] + size + BASE, check=False)
     assert rc != 0 and "12-bits" in text
+
+
+def test_readers_reject_damaged_files(cli, tmp_path):
+    # Damaged inputs must come back as an error message and exit status 1, never as a crash or an out-of-bounds read:
+    # a raw EXR chunk that claims fewer bytes than its lines need, a chunk size beyond the block, a truncated file,
+    # an inverted data window, and a TIFF whose strip table claims 2^31 entries.
+    rng = np.random.default_rng(5)
+    w, h = 24, 18
+    px = _halfs(rng, h, w, 3)
+    raw, exr, out = tmp_path / "in.raw", tmp_path / "a.exr", tmp_path / "o.raw"
+    px.tofile(raw)
+    run([cli["h2y_iotool"], "write-exr", str(exr), str(w), str(h), "3", "0", str(raw)])
+    good = bytearray(exr.read_bytes())
+    line = w * 3 * 2
+    first_chunk = len(good) - h * (8 + line)            # uncompressed: h chunks of (y, size, line)
+    assert int.from_bytes(good[first_chunk + 4:first_chunk + 8], "little") == line
+
+    def damaged(name, edit):
+        b = bytearray(good)
+        b = edit(b) or b
+        p = tmp_path / name
+        p.write_bytes(bytes(b))
+        rc, text = run([cli["h2y_iotool"], "read-exr", str(p), str(out)], check=False)
+        assert rc == 1, (name, rc, text)
+        return text
+
+    def chunk_size(v):
+        def edit(b):
+            b[first_chunk + 4:first_chunk + 8] = int(v).to_bytes(4, "little", signed=True)
+        return edit
+
+    assert "chunk" in damaged("short_chunk.exr", chunk_size(line - 2))
+    assert "chunk" in damaged("huge_chunk.exr", chunk_size(0x7fffffff))
+    assert "chunk" in damaged("negative_chunk.exr", chunk_size(-4))
+    damaged("truncated.exr", lambda b: b[:len(b) - line // 2])
+    i = bytes(good).index(b"dataWindow\0box2i\0") + len(b"dataWindow\0box2i\0") + 4
+    def flip_window(b):
+        b[i + 8:i + 12] = (-5).to_bytes(4, "little", signed=True)          # xmax < xmin
+    assert "data window" in damaged("window.exr", flip_window)
+
+    tif = tmp_path / "a.tiff"
+    synth.tiff16_frame(w, h, seed=2).tofile(raw)
+    run([cli["h2y_iotool"], "write-tiff", str(tif), str(w), str(h), "3", str(raw)])
+    b = bytearray(tif.read_bytes())
+    ifd = int.from_bytes(b[4:8], "little")
+    n = int.from_bytes(b[ifd:ifd + 2], "little")
+    for k in range(n):
+        e = ifd + 2 + 12 * k
+        if int.from_bytes(b[e:e + 2], "little") == 273:                     # StripOffsets: count = 2^31
+            b[e + 4:e + 8] = (1 << 31).to_bytes(4, "little")
+    bad = tmp_path / "bad.tiff"
+    bad.write_bytes(bytes(b))
+    rc, text = run([cli["h2y_iotool"], "read-tiff", str(bad), str(out)], check=False)
+    assert rc == 1 and "strips" in text, text
+    (tmp_path / "cut.tiff").write_bytes(bytes(tif.read_bytes()[:200]))
+    rc, text = run([cli["h2y_iotool"], "read-tiff", str(tmp_path / "cut.tiff"), str(out)], check=False)
+    assert rc == 1, text
