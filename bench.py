@@ -87,6 +87,8 @@ def make_frame(wl, index):
     if wl["kind"] == "inverse":
         raise RuntimeError("inverse inputs are produced by the forward path")
     if wl["src_kind"] == "half":
+        if wl.get("content") == "flat" and ch == 3:
+            return synth.exr_half_frame_flat(wl["w"], wl["h"], seed=index)
         if wl.get("content") in ("natural", "graded") and ch == 3:
             return synth.exr_half_frame_smooth_fast(wl["w"], wl["h"], seed=index, peak_white=wl["content"] == "graded")
         return synth.exr_half_frame_fast(wl["w"], wl["h"], seed=index, channels=ch)
@@ -330,6 +332,8 @@ def bench_config(wl, name, frames_per_step):
         cfg["content"] = "iid log-uniform samples (SURVEY.md 8d config 2)" if wl["src_kind"] == "half" else "iid uniform codes"
         if wl.get("content") == "natural" and wl["src_kind"] == "half":
             cfg["content"] = "spatially correlated luminance field with colour cast and 2 % noise (--forward-content natural)"
+        if wl.get("content") == "flat" and wl["src_kind"] == "half":
+            cfg["content"] = "diagnostic: 64x64 tiles of constant colour, broadcast LUT gathers (--forward-content flat)"
         if wl.get("content") == "graded" and wl["src_kind"] == "half":
             cfg["content"] = ("the natural field plus one peak-white and one near-black pixel per frame, so the channels share "
                               "floor and ceiling (--forward-content graded)")
@@ -560,7 +564,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the workload's)")
     ap.add_argument("--layout", choices=sorted(LAYOUT_BPP), default=None, help="override the source layout")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
-    ap.add_argument("--forward-content", choices=["iid", "natural", "graded"], default=None,
+    ap.add_argument("--forward-content", choices=["iid", "natural", "graded", "flat"], default=None,
                     help="forward EXR workloads: iid log-uniform samples (default, the headline; worst case for the LUT "
                          "gather) or a spatially correlated field, as a second data point")
     ap.add_argument("--content", choices=["smooth", "iid"], default="smooth",

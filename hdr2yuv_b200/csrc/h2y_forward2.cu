@@ -212,6 +212,15 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, unsigne
 {
     typedef KC<CFG> C;
     const PixK &k = a.k;
+#ifdef H2Y_EXPERIMENT_NO_MATH
+    // timing diagnostic only (wrong output): keeps the loads, filters and stores, drops the gathers and the matrix
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        ybits[i] = (unsigned)MAGIC_BITS + (g[i] & 1023u);
+        chroma[i] = pk((float)(b[i] & 511u), (float)(r[i] & 511u));
+    }
+    return;
+#endif
     const u64 addY2 = pk(C::addY(a), C::addY(a)), addC2 = pk(C::addC(a), C::addC(a));
     const u64 magic2 = pk(MAGIC, MAGIC), twoG2 = pk(C::twoG(a), C::twoG(a));
     const float wr = C::wr(a), wg = C::wg(a), wb = C::wb(a), rdb = C::rdb(a), rdr = C::rdr(a);
@@ -773,8 +782,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
             // one row: 8 pixels -> Y store, chroma, horizontal 7-tap -> o[4]
             // advance the source pointer from (clamped) row r to (clamped) row r+1
             auto next_src = [&](int r) { sp += ((unsigned)r < (unsigned)(h - 1)) ? spitch : 0; };
-            auto row_front = [&](const RawPx<NCH> &raw, int r, u64 o[4]) {
-                unsigned g[8], b[8], rr[8];
+            auto row_split = [&](const RawPx<NCH> &raw, unsigned g[8], unsigned b[8], unsigned rr[8]) {
                 if (THREE) {
                     // raise every code to its table's first entry (only exact zeros move: FrameK::zero_entry)
                     RawPx<NCH> cl = raw;
@@ -791,6 +799,8 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
                     split_codes<NCH>(cl, g, b, rr);
                 } else
                 split_codes<NCH>(raw, g, b, rr);
+            };
+            auto row_front = [&](const unsigned g[8], const unsigned b[8], const unsigned rr[8], int r, u64 o[4]) {
                 unsigned yb[8];
                 u64 ch[8];
                 if (THREE) pixels8<MK, CFG, TWO, true>(a, lut3G, lut3B, lut3R, g, b, rr, yb, ch);
@@ -861,15 +871,32 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
 
             // one row body for both parities (measured: a two-row trip with two sample buffers spills and is 20 % slower,
             // loading the next row only after the pixel stage exposes the load latency: profiles/r01/variants.md)
-            RawPx<NCH> raw, cur;
+            RawPx<NCH> raw;
             load_px8<NCH>(raw, sp, 0, 0, 0);
 #pragma unroll 1
             for (int r = rfirst; r <= rlast; r++) {
-                cur = raw;
+                unsigned g[8], b[8], rr[8];
+#ifdef H2Y_LOAD_BEFORE_SPLIT
+                RawPx<NCH> cur = raw;
                 next_src(r);
                 if (r < rlast) load_px8<NCH>(raw, sp, 0, 0, 0);                 // prefetch the next row
+                row_split(cur, g, b, rr);
+#else
+                // the codes leave the sample registers first, then the next row is loaded into the same registers: no copy
+                row_split(raw, g, b, rr);
+                next_src(r);
+                if (r < rlast) load_px8<NCH>(raw, sp, 0, 0, 0);                 // prefetch the next row
+#endif
+#ifdef H2Y_EXPERIMENT_L2_PREFETCH_ROWS
+                // timing experiment: pull the row H2Y_EXPERIMENT_L2_PREFETCH_ROWS further down into L2
+                if (r + 1 + H2Y_EXPERIMENT_L2_PREFETCH_ROWS < h && r + 1 >= 0) {
+                    const uint8_t *pf = sp + (size_t)H2Y_EXPERIMENT_L2_PREFETCH_ROWS * spitch;
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(pf));
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(pf + 16 * (NCH - 1)));
+                }
+#endif
                 u64 o[4];
-                row_front(cur, r, o);
+                row_front(g, b, rr, r, o);
                 yp += w;
                 if ((r & 1) == 0) row_even(o, r); else row_odd(o);
             }

@@ -104,3 +104,16 @@ def exr_half_frame_smooth_fast(width, height, seed=0, block=16, peak_white=False
         v[int(rng.integers(0, height)), int(rng.integers(0, width))] = np.float16(4000.0)
         v[int(rng.integers(0, height)), int(rng.integers(0, width))] = np.float16(0.01)
     return np.ascontiguousarray(v).view(np.uint16)
+
+
+def exr_half_frame_flat(width, height, seed=0):
+    """Diagnostic content: 64 x 64 tiles of constant colour (so the 32 lanes of a warp, 8 pixels apart, gather at most a
+    handful of distinct table entries and shared memory serves them by broadcast), plus one peak-white and one near-black
+    pixel so that the channels share floor and ceiling.  (H, W, 3) uint16 half bit patterns."""
+    rng = np.random.default_rng(seed)
+    t = 64
+    low = np.exp(rng.uniform(np.log(0.05), np.log(2000.0), (height // t + 1, width // t + 1, 3))).astype(np.float16)
+    v = np.repeat(np.repeat(low, t, 0), t, 1)[:height, :width].copy()
+    v[int(rng.integers(0, height)), int(rng.integers(0, width))] = np.float16(4000.0)
+    v[int(rng.integers(0, height)), int(rng.integers(0, width))] = np.float16(0.01)
+    return np.ascontiguousarray(v).view(np.uint16)
