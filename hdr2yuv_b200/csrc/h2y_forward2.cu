@@ -41,6 +41,9 @@
 #define H2Y_PAIRS_PER_BRANCH_THREE 1
 #endif
 // Pixel pairs per guard-band branch (1, 2 or 4): 2 measured fastest (profiles/r01/variants.md).
+#ifndef H2Y_ROWS_PDL
+#define H2Y_ROWS_PDL 1
+#endif
 #ifndef H2Y_PAIRS_PER_BRANCH_THREE_NC
 #define H2Y_PAIRS_PER_BRANCH_THREE_NC 1
 #endif
@@ -656,8 +659,8 @@ constexpr int THREADS3 = 512, WARPS3 = THREADS3 / 32;     // 16 warps (12 x 168 
 
 // THREE: the instantiation for frames whose channels need a table each (FrameK::clean3); with TWO as well: the
 // clamp-free chroma path on those three tables (frames that three_nc_frame() accepts)
-template <int MK, int NCH, int CFG = 0, bool TWO = false, bool THREE = false>
-__global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3Args A)
+template <int MK, int NCH, int CFG, bool TWO, bool THREE>
+__device__ __forceinline__ void rows_body(const Fwd3Args &A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *lut_s = reinterpret_cast<float *>(smem_raw);
@@ -902,6 +905,39 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3A
             }
         }
     }
+}
+
+template <int MK, int NCH, int CFG = 0, bool TWO = false, bool THREE = false>
+__global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3Args A)
+{
+#if H2Y_ROWS_PDL
+    // The instantiations of one call convert disjoint frames and read only what the statistics pass wrote, so the next
+    // one may move onto SMs as this one's CTAs leave them (programmatic dependent launch; measured 14 us per call).
+    // No griddepcontrol.wait anywhere: nothing here consumes a predecessor's output, and the next ordinary operation in
+    // the stream (the general-kernel sweep, a copy, an event) is ordered behind ALL of these launches, not only the last
+    // one -- tests/test_forward_gpu.py::test_stream_order_behind_the_overlapped_rows_launches checks exactly that.  (A
+    // wait at the end of every instantiation, to make completion transitive by hand, cost 0.2 ms per call.)
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
+    rows_body<MK, NCH, CFG, TWO, THREE>(A);
+}
+
+// launch an instantiation that may overlap the tail of the previous one (see above)
+template <class K>
+static cudaError_t launch_rows_overlapped(K kernel, int grid, size_t smem, cudaStream_t st, const Fwd3Args &A)
+{
+#if H2Y_ROWS_PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS3); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, A);
+#else
+    kernel<<<grid, THREADS3, smem, st>>>(A);
+    return cudaSuccess;
+#endif
 }
 
 // =================================================================================================
@@ -1283,12 +1319,12 @@ h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, c
         H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
         k_forward_exr420_rows<MK_YCBCR, NC, DD, true><<<g3, THREADS3, smem2, st>>>(A3);                                   \
         H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
-        k_forward_exr420_rows<MK_YCBCR, NC, DD, false><<<g3, THREADS3, smem3, st>>>(A3);                                  \
+        H2Y_CUDA(c, launch_rows_overlapped(k_forward_exr420_rows<MK_YCBCR, NC, DD, false>, g3, smem3, st, A3));            \
         H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT)); \
-        k_forward_exr420_rows<MK_YCBCR, NC, DD, false, true><<<g3, THREADS3, smemT, st>>>(A3);                            \
+        H2Y_CUDA(c, launch_rows_overlapped(k_forward_exr420_rows<MK_YCBCR, NC, DD, false, true>, g3, smemT, st, A3));      \
         /* three-table frames that provably stay inside matrix_convert's chroma clamp */                                   \
         H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT)); \
-        k_forward_exr420_rows<MK_YCBCR, NC, DD, true, true><<<g3, THREADS3, smemT, st>>>(A3);                             \
+        H2Y_CUDA(c, launch_rows_overlapped(k_forward_exr420_rows<MK_YCBCR, NC, DD, true, true>, g3, smemT, st, A3));       \
         c->launches += 3;                                                                                                  \
     } while (0)
                 if (tmp_bit_depth == 10) { if (nch == 3) L3C(3, 10); else L3C(4, 10); }

@@ -411,3 +411,33 @@ def test_rows_kernel_three_table_frames(ctx, monkeypatch, depth, matrix):
     got = G.gpu_forward(ctx, rgba, _HALF, dst)
     for i, f in enumerate(rgba):
         G.compare_codes(got[i], G.oracle_forward(f, _HALF, dst), True, "rgba frame %d" % i)
+
+
+@pytest.mark.gpu
+def test_stream_order_behind_the_overlapped_rows_launches(ctx, monkeypatch):
+    # The rows-kernel instantiations of one call are launched so that each may start while its predecessor drains
+    # (programmatic dependent launch).  Work queued behind h2y_forward on the same stream must still see every frame
+    # converted: a device-to-host copy queued on that stream right after the call, with no device-wide synchronise in
+    # between, has to return the same bytes as a synchronised run.  Single-table frames are converted by the FIRST
+    # launch (the long one, the later launches find nothing to do), three-table frames by the last ones.
+    monkeypatch.setenv("H2Y_FORWARD_KERNEL", "rows")
+    w, h, n = 1920, 1080, 12
+    dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+    single = synth.exr_half_frame_fast(w, h, seed=3, channels=3)
+    three = synth.exr_half_frame_smooth_fast(w, h, seed=4)
+    for frames in ([single] * n, [three] * n, [single, three] * (n // 2)):
+        want = np.stack(G.gpu_forward(ctx, frames, _HALF, dst))
+        params = api.forward_params(w, h, cabi.LAYOUT_HALF_RGB, _HALF, dst, resampler=1, clip_on_load=0)
+        d_src = G.to_dev(np.stack(frames, 0))
+        nbytes = api.yuv_frame_bytes(w, h, 1)
+        host = torch.empty(nbytes * n, dtype=torch.uint8).pin_memory()
+        st = torch.cuda.Stream()
+        for _ in range(3):
+            d_dst = torch.zeros(nbytes * n, dtype=torch.uint8, device="cuda")
+            host.zero_()
+            torch.cuda.synchronize()
+            with torch.cuda.stream(st):
+                ctx.forward(params, d_src, d_dst, n, stream=st.cuda_stream)
+                host.copy_(d_dst, non_blocking=True)
+            st.synchronize()
+            assert np.array_equal(host.numpy().view(np.uint16).reshape(n, -1), want)
