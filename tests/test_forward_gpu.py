@@ -441,3 +441,24 @@ def test_stream_order_behind_the_overlapped_rows_launches(ctx, monkeypatch):
                 host.copy_(d_dst, non_blocking=True)
             st.synchronize()
             assert np.array_equal(host.numpy().view(np.uint16).reshape(n, -1), want)
+
+
+@pytest.mark.gpu
+def test_host_pipeline_with_the_rows_kernels(ctx, monkeypatch):
+    # h2y_forward_host with the warp-autonomous kernels forced: per chunk the compute stream runs the overlapped rows
+    # launches and the general-kernel sweep, records an event, and the copy stream drains the chunk behind that event.
+    # Single-table and three-table frames alternate, so both the first and the last launch of a call do real work.
+    monkeypatch.setenv("H2Y_FORWARD_KERNEL", "rows")
+    w, h, n = 1920, 1080, 20
+    dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+    base = [synth.exr_half_frame_fast(w, h, seed=11, channels=3), synth.exr_half_frame_smooth_fast(w, h, seed=12)]
+    frames = [base[(i // 3) % 2] for i in range(n)]
+    want = [G.gpu_forward(ctx, [f], _HALF, dst)[0] for f in base]
+    params = api.forward_params(w, h, cabi.LAYOUT_HALF_RGB, _HALF, dst, resampler=1, clip_on_load=0)
+    src = np.ascontiguousarray(np.stack(frames, 0))
+    out = np.zeros((n, api.yuv_frame_bytes(w, h, 1) // 2), np.uint16)
+    for _ in range(2):
+        out[:] = 0
+        ctx.forward_host(params, src, out, n)
+        for i in range(n):
+            assert np.array_equal(out[i], want[(i // 3) % 2]), i
