@@ -410,6 +410,20 @@ template <int MK, int CM>
 static h2y_status launch_one(h2y_ctx_impl *c, const FwdArgs &a, int grid, size_t smem, cudaStream_t st)
 {
     H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_fused<MK, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#ifndef H2Y_NO_SWEEP_OVERLAP
+    if (a.skip_clean) {
+        // The sweep behind the fast kernels converts only the frames they left (disjoint output, inputs older than
+        // both): it need not wait for the fast kernel to drain (programmatic stream serialization, as between the
+        // rows-kernel instantiations in h2y_forward2.cu).
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        H2Y_CUDA(c, cudaLaunchKernelEx(&cfg, k_forward_fused<MK, CM>, a));
+    } else
+#endif
     k_forward_fused<MK, CM><<<grid, THREADS, smem, st>>>(a);
     c->launches++;
     H2Y_CUDA(c, cudaGetLastError());
