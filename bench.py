@@ -170,8 +170,11 @@ class CpuPool:
         self.kind = _cpu_init()
 
     def run(self, fn, tasks):
+        """One task per worker, all at once.  Returns (seconds per frame per core, outputs): the mean of the workers' own
+        conversion times, so the stagger of the workers' frame synthesis in front of the timed part is not charged to the
+        reference."""
         res = list(self.ex.map(fn, tasks))
-        wall = max(r[1] for r in res) - min(r[0] for r in res)
+        wall = sum(r[1] - r[0] for r in res) / len(res)
         return wall, [r[2] for r in res]
 
     def close(self):
@@ -303,7 +306,7 @@ def run_reference(args, wl, name):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64->u16",
         "data": "synthetic", "frames_per_s": mpx * 1e6 / (wl["w"] * wl["h"]),
-        "config": bench_config(wl, name, pool.cores),
+        "config": bench_config(wl, name), "frames_per_step": pool.cores,
         "cpu_baseline": {"value": mpx, "unit": "Mpixel/s", "cores": pool.cores,
                          "kind": pool.kind if wl["kind"] == "forward" else "port", "sample": sample},
         "e2e": {"value": mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -323,9 +326,9 @@ def reference_inverse_input(wl, index):
     return np.concatenate([y.reshape(-1), c.reshape(-1)])
 
 
-def bench_config(wl, name, frames_per_step):
+def bench_config(wl, name):
+    """The workload, identical in both arms (how many frames an arm takes per step is a top-level key of its line)."""
     cfg = {"workload": name, "what": wl["text"], "width": wl["w"], "height": wl["h"],
-           "frames_per_step_per_gpu": frames_per_step,
            "l2": "inputs larger than L2 (batch >> 126 MB); no flush needed"}
     if wl["kind"] == "forward":
         cfg["layout"] = wl["layout"] + " (%d B/px in)" % LAYOUT_BPP[wl["layout"]]
@@ -369,9 +372,13 @@ def run_gpu(args, wl, name):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     ctx = api.Context(local)
+    if args.plan_reuse != "auto":
+        ctx.set_option("H2Y_PLAN_REUSE", args.plan_reuse)
     w, h, nf = wl["w"], wl["h"], min(args.frames or wl["frames"], 256)   # one profiling bracket per step (<= 256 frames)
     px_per_frame = w * h
-    first = rank * nf                                      # this rank's contiguous frame range
+    from hdr2yuv_b200 import sharding
+    first, last = sharding.frame_range(rank, world, nf * world)    # this rank's contiguous frame range (weak scaling)
+    assert last - first == nf
     stream = torch.cuda.current_stream()
 
     # ---- inputs: pinned host batch -> HBM -------------------------------------------------------
@@ -445,6 +452,12 @@ def run_gpu(args, wl, name):
     launches = ctx.kernel_launches - launches0
     kern_ms, prologue_ms = ctx.profile_last_ms()           # per call, averaged over the last <=16 steps
     ctx.profile_enable(False)
+    plan_reuse = None
+    if wl["kind"] == "forward":
+        attempted, pr_n, pr_redone = ctx.forward_last_plan_reuse()
+        plan_reuse = {"single_pass": attempted, "frames": pr_n, "frames_converted_again": pr_redone,
+                      "what": "last timed step: frames converted with the previous plan while their extrema were gathered, "
+                              "and how many the verify step handed back (h2y_forward, include/hdr2yuv_b200.h)"}
     gpu_ref_out = d_out.cpu().numpy().view(np.uint16).reshape(nf, -1) if rank == 0 and world == 1 else None
 
     # ---- end to end through the host API: pinned host in, pinned host out --------------------------
@@ -502,8 +515,8 @@ def run_gpu(args, wl, name):
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32/f64->u16", "data": "synthetic",
         "frames_per_s": mpx * 1e6 / px_per_frame,
-        "config": bench_config(wl, name, nf),
-        "roofline": {"bound": "hbm", "kernel": fused_kernel_name(wl),
+        "config": bench_config(wl, name), "frames_per_step": nf * world, "plan_reuse": plan_reuse,
+        "roofline": {"bound": "hbm", "kernel": fused_kernel_name(wl) + (" <SPEC>: conversion + statistics in one pass" if plan_reuse and plan_reuse["single_pass"] else ""),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic,
                      "algorithmic_bytes_per_px": bpp, "algorithmic_bytes_per_launch": bpp * px_per_frame * nf,
@@ -534,7 +547,7 @@ def run_gpu(args, wl, name):
         kind = pool.kind if wl["kind"] == "forward" else "port"    # the reference's yuv2tiff is a file-to-file program
         line["cpu_baseline"] = {
             "value": px_per_frame * n / wall / 1e6, "unit": "Mpixel/s", "cores": n, "kind": kind,
-            "sample": "frames 0..%d of this workload (%dx%d), one per host core, %.1f s wall" % (n - 1, w, h, wall)}
+            "sample": "frames 0..%d of this workload (%dx%d), one per host core at once, %.1f s per frame per core" % (n - 1, w, h, wall)}
         differ, max_abs, total = 0, 0, 0
         for i, o in enumerate(outs):
             d = np.abs(gpu_ref_out[i].astype(np.int32) - np.asarray(o).reshape(-1).astype(np.int32))
@@ -564,6 +577,8 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the workload's)")
     ap.add_argument("--layout", choices=sorted(LAYOUT_BPP), default=None, help="override the source layout")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
+    ap.add_argument("--plan-reuse", choices=["auto", "0", "1"], default="auto",
+                    help="h2y_forward's single-pass route: library policy (default), never, or whenever a seed exists")
     ap.add_argument("--forward-content", choices=["iid", "natural", "graded", "flat"], default=None,
                     help="forward EXR workloads: iid log-uniform samples (default, the headline; worst case for the LUT "
                          "gather) or a spatially correlated field, as a second data point")

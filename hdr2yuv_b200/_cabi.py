@@ -56,6 +56,7 @@ SYMBOLS = {
     "h2y_abi_version": (C.c_int, []),
     "h2y_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "h2y_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "h2y_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "h2y_status_string": (C.c_char_p, [C.c_int]),
     "h2y_last_cuda_error": (C.c_int, [C.c_void_p]),
     "h2y_host_alloc": (C.c_void_p, [C.c_size_t]),
@@ -65,6 +66,7 @@ SYMBOLS = {
     "h2y_profile_last_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "h2y_set_pic_clip": (C.c_int, [C.c_int, C.c_int, C.POINTER(ClipLimits)]),
     "h2y_plane_dims": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int * 3), C.POINTER(C.c_int * 3)]),
+    "h2y_frame_range": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "h2y_src_frame_bytes": (C.c_size_t, [C.POINTER(PicDesc)]),
     "h2y_yuv_frame_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "h2y_tmp_bit_depth": (C.c_int, [C.POINTER(PicDesc), C.POINTER(PicDesc)]),
@@ -86,6 +88,7 @@ SYMBOLS = {
     "h2y_forward_host": (C.c_int, [C.c_void_p, C.POINTER(ForwardParams), C.c_void_p, C.c_size_t, C.c_void_p,
                                    C.c_size_t, C.c_int]),
     "h2y_forward_last_stats": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PicStats)]),
+    "h2y_forward_last_plan_reuse": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "h2y_rgb_frame_bytes": (C.c_size_t, [C.POINTER(InverseParams)]),
     "h2y_inverse": (C.c_int, [C.c_void_p, C.POINTER(InverseParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                               C.c_int, C.c_void_p, C.c_void_p]),

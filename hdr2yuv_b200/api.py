@@ -81,6 +81,11 @@ class Context:
         except Exception:
             pass
 
+    def set_option(self, name=None, value=None):
+        """h2y_ctx_set_option: a test / experiment switch of this context (name=None restores the defaults)."""
+        check(lib().h2y_ctx_set_option(self._h, None if name is None else name.encode(),
+                                       None if value is None else str(value).encode()), "h2y_ctx_set_option")
+
     @property
     def kernel_launches(self):
         return int(lib().h2y_kernel_launches(self._h))
@@ -161,6 +166,12 @@ class Context:
         ds = dst_stride or yuv_frame_bytes(params.src.width, params.src.height, params.dst.chroma_format_idc)
         check(lib().h2y_forward_host(self._h, C.byref(params), _addr(src), ss, _addr(dst), ds, int(nframes)),
               "h2y_forward_host")
+
+    def forward_last_plan_reuse(self):
+        """(attempted, nframes, nredone) of the last forward call's last group (h2y_forward_last_plan_reuse)."""
+        a, n, r = C.c_int(0), C.c_int(0), C.c_int(0)
+        check(lib().h2y_forward_last_plan_reuse(self._h, C.byref(a), C.byref(n), C.byref(r)), "h2y_forward_last_plan_reuse")
+        return bool(a.value), n.value, r.value
 
     def forward_last_stats(self, frame=0):
         out = PicStats()

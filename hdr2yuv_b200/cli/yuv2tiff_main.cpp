@@ -74,7 +74,8 @@ int main(int argc, char *argv[])
     std::vector<std::thread> workers;
     for (int d = 0; d < ndev; d++) {
         workers.emplace_back([&, d]() {
-            const int lo = (int)((long)nframes * d / ndev), hi = (int)((long)nframes * (d + 1) / ndev);
+            int lo = 0, hi = 0;
+            h2y_frame_range(d, ndev, nframes, &lo, &hi);
             h2y_ctx *ctx = nullptr;
             h2y_status st = h2y_ctx_create(d, &ctx);
             if (st != H2Y_OK) { printf("ERROR: device %d: %s\n", d, h2y_status_string(st)); rc[d] = 1; return; }

@@ -35,6 +35,109 @@ h2y_status scratch_reserve(h2y_ctx_impl *c, int slot, size_t bytes, void **out)
     return H2Y_OK;
 }
 
+// ---- test / experiment switches -------------------------------------------------------------------------------
+int switches_set(Switches *s, const char *name, const char *v)
+{
+    const bool on = v && v[0] && !(v[0] == '0' && !v[1]);
+    if (!strcmp(name, "H2Y_FORCE_STAGED")) s->force_staged = on;
+    else if (!strcmp(name, "H2Y_FORCE_V1")) s->force_v1 = on;
+    else if (!strcmp(name, "H2Y_NO_SPECIALISED")) s->no_specialised = on;
+    else if (!strcmp(name, "H2Y_EXACT_MATH")) s->exact_math = v && v[0] == '1';
+    else if (!strcmp(name, "H2Y_FORWARD_KERNEL")) s->fwd_kernel = !v || !v[0] ? 0 : (v[0] == 'r' && v[1] == 'o' ? 2 : 1);
+    else if (!strcmp(name, "H2Y_INVERSE_KERNEL")) s->inv_kernel = !v || !v[0] ? 0 : (v[0] == 'r' ? 2 : 1);
+    else if (!strcmp(name, "H2Y_STATS_GX")) s->stats_gx = v ? atoi(v) : 0;
+    else if (!strcmp(name, "H2Y_EXPERIMENT_GUARD_LOG2")) s->guard_log2 = v && v[0] ? atoi(v) : -1;
+    else if (!strcmp(name, "H2Y_PLAN_REUSE")) s->spec = !v || !v[0] ? -1 : atoi(v);
+    else return 0;
+    return 1;
+}
+
+void switches_from_env(Switches *s)
+{
+    memset(s, 0, sizeof(*s));
+    s->guard_log2 = -1;
+    s->spec = -1;
+    static const char *const names[] = {"H2Y_FORCE_STAGED", "H2Y_FORCE_V1", "H2Y_NO_SPECIALISED", "H2Y_EXACT_MATH", "H2Y_FORWARD_KERNEL",
+                                        "H2Y_INVERSE_KERNEL", "H2Y_STATS_GX", "H2Y_EXPERIMENT_GUARD_LOG2", "H2Y_PLAN_REUSE"};
+    for (const char *n : names)
+        if (const char *v = getenv(n)) switches_set(s, n, v);
+}
+
+// ---- auxiliary streams: kernels of one call that convert disjoint frames ----------------------------------------
+static h2y_status aux_init(h2y_ctx_impl *c)
+{
+    if (c->aux_ready) return H2Y_OK;
+    for (int i = 0; i < 4; i++) {
+        H2Y_CUDA(c, cudaStreamCreateWithFlags(&c->s_aux[i], cudaStreamNonBlocking));
+        H2Y_CUDA(c, cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+    H2Y_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    c->aux_ready = 1;
+    return H2Y_OK;
+}
+
+h2y_status aux_fork(h2y_ctx_impl *c, cudaStream_t st)
+{
+    h2y_status s = aux_init(c);
+    if (s != H2Y_OK) return s;
+    if (c->aux_forked) return H2Y_OK;                    // one fork point per call section
+    H2Y_CUDA(c, cudaEventRecord(c->ev_fork, st));
+    c->aux_forked = 1;
+    c->aux_used = 0;
+    return H2Y_OK;
+}
+
+cudaStream_t aux_stream(h2y_ctx_impl *c, int i)
+{
+    if (!(c->aux_used & (1 << i))) {
+        cudaStreamWaitEvent(c->s_aux[i], c->ev_fork, 0);
+        c->aux_used |= 1 << i;
+    }
+    return c->s_aux[i];
+}
+
+h2y_status aux_join(h2y_ctx_impl *c, cudaStream_t st)
+{
+    if (!c->aux_forked) return H2Y_OK;
+    for (int i = 0; i < 4; i++)
+        if (c->aux_used & (1 << i)) {
+            H2Y_CUDA(c, cudaEventRecord(c->ev_join[i], c->s_aux[i]));
+            H2Y_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[i], 0));
+        }
+    c->aux_forked = 0;
+    c->aux_used = 0;
+    return H2Y_OK;
+}
+
+// ---- every entry point runs on the context's device and restores the caller's; the context's scratch is owned by one
+// stream at a time: a call that arrives on another stream first waits (on the device) for the previous call's work ----
+struct DeviceGuard {
+    int prev, dev;
+    bool ok;
+    explicit DeviceGuard(h2y_ctx_impl *c) : prev(-1), dev(c->device), ok(true)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) { c->last_cuda_error = (int)cudaGetLastError(); ok = false; }
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+#define H2Y_ON_DEVICE(c) DeviceGuard guard__(c); if (!guard__.ok) return H2Y_ERR_CUDA
+
+static h2y_status stream_enter(h2y_ctx_impl *c, cudaStream_t st)
+{
+    if (c->busy_valid && c->busy_stream != st) H2Y_CUDA(c, cudaStreamWaitEvent(st, c->ev_busy, 0));
+    return H2Y_OK;
+}
+
+static h2y_status stream_leave(h2y_ctx_impl *c, cudaStream_t st)
+{
+    if (!c->ev_busy) H2Y_CUDA(c, cudaEventCreateWithFlags(&c->ev_busy, cudaEventDisableTiming));
+    H2Y_CUDA(c, cudaEventRecord(c->ev_busy, st));
+    c->busy_valid = 1;
+    c->busy_stream = st;
+    return H2Y_OK;
+}
+
 void clip_of(int bit_depth, int full_range, h2y_clip_limits *c)
 {
     c->minCV = 0;
@@ -176,6 +279,7 @@ h2y_status h2y_ctx_create(int device, h2y_ctx **out)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; cudaGetLastError(); return H2Y_ERR_CUDA; }
     c->sm_count = prop.multiProcessorCount;
+    switches_from_env(&c->sw);
     *out = c;
     return H2Y_OK;
 }
@@ -185,7 +289,14 @@ h2y_status h2y_ctx_destroy(h2y_ctx *c)
     if (!c) return H2Y_ERR_ARG;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 8; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
+    for (int i = 0; i < SCR_COUNT; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
+    if (c->aux_ready) {
+        for (int i = 0; i < 4; i++) { cudaStreamDestroy(c->s_aux[i]); cudaEventDestroy(c->ev_join[i]); }
+        cudaEventDestroy(c->ev_fork);
+    }
+    if (c->ev_busy) cudaEventDestroy(c->ev_busy);
+    if (c->spec_dev) cudaFree(c->spec_dev);
+    if (c->spec_fb) cudaFreeHost(c->spec_fb);
     if (c->pipeline_ready) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_d2h); }
     if (c->h_framek) cudaFreeHost(c->h_framek);
     if (c->ev[0][0]) for (int r = 0; r < PROFILE_RING; r++) for (int i = 0; i < 3; i++) cudaEventDestroy(c->ev[r][i]);
@@ -193,10 +304,17 @@ h2y_status h2y_ctx_destroy(h2y_ctx *c)
     return H2Y_OK;
 }
 
+h2y_status h2y_ctx_set_option(h2y_ctx *c, const char *name, const char *value)
+{
+    if (!c) return H2Y_ERR_ARG;
+    if (!name) { switches_from_env(&c->sw); return H2Y_OK; }       // back to the defaults of h2y_ctx_create
+    return switches_set(&c->sw, name, value) ? H2Y_OK : H2Y_ERR_ARG;
+}
+
 h2y_status h2y_profile_enable(h2y_ctx *c, int on)
 {
     if (!c) return H2Y_ERR_ARG;
-    H2Y_CUDA(c, cudaSetDevice(c->device));
+    H2Y_ON_DEVICE(c);
     if (on && !c->ev[0][0])
         for (int r = 0; r < PROFILE_RING; r++) for (int i = 0; i < 3; i++) H2Y_CUDA(c, cudaEventCreate(&c->ev[r][i]));
     c->profile_on = on != 0;
@@ -251,6 +369,15 @@ h2y_status h2y_plane_dims(int w, int h, int chroma, int pw[3], int ph[3])
     return H2Y_OK;
 }
 
+h2y_status h2y_frame_range(int rank, int world, int nframes, int *lo, int *hi)
+{
+    if (!lo || !hi || world < 1 || rank < 0 || rank >= world || nframes < 0) return H2Y_ERR_ARG;
+    const int base = nframes / world, extra = nframes % world;
+    *lo = rank * base + (rank < extra ? rank : extra);
+    *hi = *lo + base + (rank < extra ? 1 : 0);
+    return H2Y_OK;
+}
+
 size_t h2y_src_frame_bytes(const h2y_pic_desc *s)
 {
     if (!s) return 0;
@@ -301,7 +428,7 @@ h2y_status h2y_pic_stats(h2y_ctx *c, const h2y_pic_desc *pic, const void *const 
     if (pic->pic_buffer_type != H2Y_PIC_TYPE_U16 && pic->pic_buffer_type != H2Y_PIC_TYPE_F32) return H2Y_ERR_ARG;
     if (pic->pic_buffer_type == H2Y_PIC_TYPE_U16 && !depth_ok(pic->bit_depth)) return H2Y_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    H2Y_CUDA(c, cudaSetDevice(c->device));
+    H2Y_ON_DEVICE(c);
     FrameK *dfk;
     h2y_status s = launch_stats_planar(c, *pic, d_planes, &dfk, st);
     if (s != H2Y_OK) return s;
@@ -331,7 +458,7 @@ h2y_status h2y_matrix_convert(h2y_ctx *c, const h2y_pic_desc *out, void *const d
             nk.offset[ch] = (float)in_stats->estimated_floor[ch];
         }
     }
-    H2Y_CUDA(c, cudaSetDevice(c->device));
+    H2Y_ON_DEVICE(c);
     return launch_matrix_convert(c, k, nk, in->width, in->height, in_f32, d_in, out_f32, d_out, (cudaStream_t)stream);
 }
 
@@ -343,7 +470,7 @@ h2y_status h2y_convert(h2y_ctx *c, const h2y_pic_desc *out, void *const d_out[3]
     if (!depth_ok(in->bit_depth)) return H2Y_ERR_ARG;
     const int w = in->width, h = in->height;
     cudaStream_t st = (cudaStream_t)stream;
-    H2Y_CUDA(c, cudaSetDevice(c->device));
+    H2Y_ON_DEVICE(c);
     h2y_clip_limits clip;
     clip_of(in->bit_depth, in->video_full_range_flag, &clip);     // clip of the INPUT picture, convert.cpp:520
     h2y_status s = H2Y_OK;
@@ -387,7 +514,7 @@ h2y_status h2y_write_yuv_clamp(h2y_ctx *c, const h2y_pic_desc *pic, void *const 
     clip_of(pic->bit_depth, pic->video_full_range_flag, &oc);
     int pw[3], ph[3];
     h2y_plane_dims(pic->width, pic->height, pic->chroma_format_idc, pw, ph);
-    H2Y_CUDA(c, cudaSetDevice(c->device));
+    H2Y_ON_DEVICE(c);
     for (int p = 0; p < 3; p++) {
         unsigned lo, hi;
         if (pic->video_full_range_flag == 0) { lo = p ? oc.minVRC : oc.minVR; hi = p ? oc.maxVRC : oc.maxVR; }
@@ -402,7 +529,7 @@ h2y_status h2y_subsample_420_to_444(h2y_ctx *c, const void *d_src, void *d_dst, 
                                     uint16_t minCV, uint16_t maxCV, void *stream)
 {
     if (!c || !d_src || !d_dst || w < 2 || h < 2 || (w & 1) || (h & 1)) return H2Y_ERR_ARG;
-    H2Y_CUDA(c, cudaSetDevice(c->device));
+    H2Y_ON_DEVICE(c);
     void *mid = nullptr;
     h2y_status s;
     if (algorithm && (s = scratch_reserve(c, SCR_TMP444, (size_t)(w / 2) * h * 2, &mid)) != H2Y_OK) return s;
@@ -444,7 +571,7 @@ h2y_status h2y_matrix_inverse(h2y_ctx *c, const h2y_pic_desc *out, void *const d
     h2y_clip_limits clip;
     clip_of(in->bit_depth, in->video_full_range_flag, &clip);
     const int d = in->bit_depth - out->bit_depth;
-    H2Y_CUDA(c, cudaSetDevice(c->device));
+    H2Y_ON_DEVICE(c);
     cudaStream_t st = (cudaStream_t)stream;
     if (d_invalid) H2Y_CUDA(c, cudaMemsetAsync(d_invalid, 0, sizeof(uint32_t), st));
     return launch_matrix_inverse(c, family, clip.minVR, clip.maxVR, d > 0 ? d : 0, d < 0 ? -d : 0, npix, p0, 0, o0, 0, 1, 0,
@@ -457,7 +584,7 @@ h2y_status h2y_write_tiff_rows(h2y_ctx *c, const h2y_pic_desc *pic, const void *
     if (!c || !pic || !d_planes || !d_rgb || pic->width < 1 || pic->height < 1) return H2Y_ERR_ARG;
     const int sr = pic->bit_depth - src_bit_depth;
     if (sr < 0) return H2Y_ERR_BIT_DEPTH;
-    H2Y_CUDA(c, cudaSetDevice(c->device));
+    H2Y_ON_DEVICE(c);
     return launch_write_tiff_rows(c, (long)pic->width * pic->height, (const uint16_t *)d_planes[0], (const uint16_t *)d_planes[1],
                                   (const uint16_t *)d_planes[2], (uint16_t *)d_rgb, sr, (cudaStream_t)stream);
 }
@@ -534,6 +661,22 @@ static h2y_status forward_staged(h2y_ctx *c, const h2y_forward_params *p, const 
     return h2y_write_yuv_clamp(c, &od, opl, tmp.bit_depth, st);
 }
 
+// Should this group try the single-pass route?  The policy never waits for the GPU: it reads the feedback block of
+// whatever call finished last (a pinned copy of SpecCtl) and tries plan reuse when at most a quarter of that call's
+// frames differed from the plan a reuse pass would have predicted.  A wrong guess costs time, never correctness: the
+// SPEC pass hands every frame it cannot confirm back to the classic kernels of the same call.
+static bool spec_policy(h2y_ctx_impl *c, unsigned long long key)
+{
+    if (c->sw.spec == 0 || c->spec_key != key) return false;       // switched off, or no seed for these parameters yet
+    if (c->sw.spec == 1) return true;
+    const volatile SpecCtl *fb = c->spec_fb;
+    if (fb && fb->seq != c->spec_seen_seq) {
+        c->spec_seen_seq = fb->seq;
+        c->spec_hint = fb->nframes > 0 && fb->nflag * 4 <= fb->nframes;
+    }
+    return c->spec_hint != 0;
+}
+
 h2y_status h2y_forward(h2y_ctx *c, const h2y_forward_params *p, const void *d_src, size_t src_stride, void *d_dst,
                        size_t dst_stride, int nframes, void *stream)
 {
@@ -546,16 +689,24 @@ h2y_status h2y_forward(h2y_ctx *c, const h2y_forward_params *p, const void *d_sr
     if (src_stride < h2y_src_frame_bytes(&p->src) ||
         dst_stride < h2y_yuv_frame_bytes(p->src.width, p->src.height, p->dst.chroma_format_idc)) return H2Y_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    H2Y_CUDA(c, cudaSetDevice(c->device));
+    H2Y_ON_DEVICE(c);
+    if ((s = stream_enter(c, st)) != H2Y_OK) return s;
     c->last_nframes = 0;
+    c->last_groups = 0;
+    c->last_spec = 0;
+    c->last_is_float = pic_type_of_layout(p->src.layout) == H2Y_PIC_TYPE_F32;
     const bool fused = fused_forward_supported(*p) && k.mat_kind != MK_PRIME2 && aligned16(d_src, src_stride) &&
-                       aligned16(d_dst, dst_stride) && !getenv("H2Y_FORCE_STAGED");
+                       aligned16(d_dst, dst_stride) && !c->sw.force_staged;
     if (!fused) {
         for (int f = 0; f < nframes; f++)
             if ((s = forward_staged(c, p, tmp, k, (const uint8_t *)d_src + (size_t)f * src_stride,
                                     (uint8_t *)d_dst + (size_t)f * dst_stride, st)) != H2Y_OK) return s;
-        return H2Y_OK;
+        return stream_leave(c, st);
     }
+    const bool exr_route = k.convert_transfer && forward_exr420_supported(*p, k, tmp.bit_depth) && !c->sw.force_v1;
+    // what a seed (plan + LUT) depends on besides the frame's extrema: the two transfer functions and the sample type
+    const unsigned long long seed_key = (1ull << 40) | ((unsigned long long)(layout_is_half(p->src.layout) ? 1 : 0) << 16) |
+                                        ((unsigned long long)k.tf_linearise << 8) | (unsigned long long)k.tf_encode;
     // bounded groups keep the LUT scratch (768 KiB per frame) bounded
     const int GROUP = 256;
     for (int f0 = 0; f0 < nframes; f0 += GROUP) {
@@ -566,6 +717,36 @@ h2y_status h2y_forward(h2y_ctx *c, const h2y_forward_params *p, const void *d_sr
         float *dl = nullptr;
         cudaEvent_t *pev = c->ev[c->profile_count % PROFILE_RING];
         if (c->profile_on) cudaEventRecord(pev[0], st);
+        c->last_groups++;
+        const bool seedable = exr_route && c->sw.spec != 0 && forward_exr420_spec_supported(c, *p, k, tmp.bit_depth, nf);
+        if (seedable && spec_policy(c, seed_key)) {
+            // ---- single pass: convert with the previous plan, gather the extrema on the way, verify, redo what differs ----
+            const int seq = ++c->spec_seq;
+            c->last_spec = 1;
+            FrameK *pred;
+            unsigned *slots;
+            int *bail, *flag;
+            SpecDev sd;
+            if ((s = spec_dev(c, &sd)) != H2Y_OK) return s;
+            if ((s = launch_spec_prepare(c, nf, seq, &pred, &slots, &bail, &flag, st)) != H2Y_OK) return s;
+            if (c->profile_on) cudaEventRecord(pev[1], st);
+            SpecLaunch sl = {sd.ctl, flag, bail, slots, 1};
+            if ((s = launch_forward_exr420(c, *p, k, tmp.bit_depth, src, src_stride, dst, dst_stride, nf, pred, sd.seed_lut, st, nullptr, &sl)) != H2Y_OK) return s;
+            if ((s = aux_join(c, st)) != H2Y_OK) return s;
+            if ((s = launch_spec_verify_and_redo_prologue(c, *p, k, src, src_stride, nf, &dl, st)) != H2Y_OK) return s;
+            dfk = (FrameK *)c->scratch[SCR_FRAMEK];
+            sl.spec = 0;
+            int three = 0;
+            if ((s = launch_forward_exr420(c, *p, k, tmp.bit_depth, src, src_stride, dst, dst_stride, nf, dfk, dl, st, &three, &sl)) != H2Y_OK) return s;
+            if ((s = aux_fork(c, st)) != H2Y_OK) return s;
+            if ((s = launch_forward_fused(c, *p, k, src, src_stride, dst, dst_stride, nf, dfk, dl, st, three ? 2 : 1, &sl, aux_stream(c, 3))) != H2Y_OK) return s;
+            if ((s = aux_join(c, st)) != H2Y_OK) return s;
+            if ((s = launch_seed_update(c, dfk, dl, nf, seq, 1, 0, st)) != H2Y_OK) return s;
+            c->last_nframes = nf;
+            c->last_stream = st;
+            if (c->profile_on) { cudaEventRecord(pev[2], st); c->profile_count++; }
+            continue;
+        }
         if (k.convert_transfer) {
             if ((s = launch_stats_and_luts(c, *p, k, src, src_stride, nf, &dfk, &dl, st)) != H2Y_OK) return s;
             c->last_nframes = nf;
@@ -573,33 +754,58 @@ h2y_status h2y_forward(h2y_ctx *c, const h2y_forward_params *p, const void *d_sr
         }
         if (c->profile_on) cudaEventRecord(pev[1], st);
         // TIFF route (integer rows, no transfer change, 4:2:0 FIR): the ring kernel with the reference's arithmetic
-        if (!k.convert_transfer && forward_u16_420_supported(*p, k) && !getenv("H2Y_FORCE_V1")) {
+        if (!k.convert_transfer && forward_u16_420_supported(*p, k) && !c->sw.force_v1) {
             if ((s = launch_forward_u16_420(c, *p, k, src, src_stride, dst, dst_stride, nf, st)) != H2Y_OK) return s;
             if (c->profile_on) { cudaEventRecord(pev[2], st); c->profile_count++; }
             continue;
         }
         // EXR route: the v2 kernel converts every "clean" frame, v1 then takes what v2 left (usually nothing)
         int skip_clean = 0;
-        if (k.convert_transfer && forward_exr420_supported(*p, k, tmp.bit_depth) && !getenv("H2Y_FORCE_V1")) {
+        if (exr_route) {
             int three = 0;
             if ((s = launch_forward_exr420(c, *p, k, tmp.bit_depth, src, src_stride, dst, dst_stride, nf, dfk, dl, st, &three)) != H2Y_OK) return s;
             skip_clean = three ? 2 : 1;
         }
-        if ((s = launch_forward_fused(c, *p, k, src, src_stride, dst, dst_stride, nf, dfk, dl, st, skip_clean)) != H2Y_OK) return s;
+        // the sweep converts disjoint frames: it shares the fast kernels' fork point when there is one
+        cudaStream_t sweep = c->aux_forked ? aux_stream(c, 3) : nullptr;
+        if ((s = launch_forward_fused(c, *p, k, src, src_stride, dst, dst_stride, nf, dfk, dl, st, skip_clean, nullptr, sweep)) != H2Y_OK) return s;
+        if ((s = aux_join(c, st)) != H2Y_OK) return s;
+        if (seedable) {
+            // the last frame's plan seeds the next call; the feedback says how uniform this call's plans were
+            if ((s = launch_seed_update(c, dfk, dl, nf, ++c->spec_seq, 0, c->spec_key != seed_key, st)) != H2Y_OK) return s;
+            c->spec_key = seed_key;
+        }
         if (c->profile_on) { cudaEventRecord(pev[2], st); c->profile_count++; }
+    }
+    return stream_leave(c, st);
+}
+
+h2y_status h2y_forward_last_plan_reuse(h2y_ctx *c, int *attempted, int *nframes, int *nredone)
+{
+    if (!c) return H2Y_ERR_ARG;
+    H2Y_ON_DEVICE(c);
+    if (attempted) *attempted = c->last_spec;
+    if (nframes) *nframes = c->last_nframes;
+    if (nredone) *nredone = 0;
+    if (c->last_spec && c->spec_fb) {
+        H2Y_CUDA(c, cudaStreamSynchronize(c->last_stream));
+        if (nredone) *nredone = c->spec_fb->nflag;
     }
     return H2Y_OK;
 }
 
 h2y_status h2y_forward_last_stats(h2y_ctx *c, int frame, h2y_pic_stats_t *out)
 {
-    if (!c || !out || frame < 0 || frame >= c->last_nframes || !c->scratch[SCR_FRAMEK]) return H2Y_ERR_ARG;
-    H2Y_CUDA(c, cudaSetDevice(c->device));
+    if (!c || !out || frame < 0 || !c->scratch[SCR_FRAMEK]) return H2Y_ERR_ARG;
+    // the per-frame plans live in scratch that every 256-frame group of a call (and every chunk of the host pipeline)
+    // overwrites: only a call that was a single group can be asked afterwards
+    if (c->last_groups != 1) return H2Y_ERR_UNSUPPORTED;
+    if (frame >= c->last_nframes) return H2Y_ERR_ARG;
+    H2Y_ON_DEVICE(c);
     FrameK h;
     H2Y_CUDA(c, cudaStreamSynchronize(c->last_stream));
     H2Y_CUDA(c, cudaMemcpy(&h, (FrameK *)c->scratch[SCR_FRAMEK] + frame, sizeof(h), cudaMemcpyDeviceToHost));
-    framek_to_stats(h, 1, out);
-    for (int i = 0; i < 3; i++) { out->i_min[i] = (uint16_t)h.fmin[i]; out->i_max[i] = (uint16_t)h.fmax[i]; }
+    framek_to_stats(h, c->last_is_float, out);
     return H2Y_OK;
 }
 
@@ -697,11 +903,15 @@ h2y_status h2y_forward_host(h2y_ctx *c, const h2y_forward_params *p, const void 
     if (s != H2Y_OK) return s;
     const size_t inb = h2y_src_frame_bytes(&p->src), outb = h2y_yuv_frame_bytes(p->src.width, p->src.height, p->dst.chroma_format_idc);
     if (src_stride < inb || dst_stride < outb) return H2Y_ERR_ARG;
-    H2Y_CUDA(c, cudaSetDevice(c->device));
-    return run_pipeline(c, (const uint8_t *)h_src, src_stride, inb, (uint8_t *)h_dst, dst_stride, outb, nframes,
-                        [&](uint8_t *di, size_t ip, uint8_t *dob, size_t op, int nf, cudaStream_t st) {
-                            return h2y_forward(c, p, di, ip, dob, op, nf, st);
-                        });
+    H2Y_ON_DEVICE(c);
+    int chunks = 0;
+    s = run_pipeline(c, (const uint8_t *)h_src, src_stride, inb, (uint8_t *)h_dst, dst_stride, outb, nframes,
+                     [&](uint8_t *di, size_t ip, uint8_t *dob, size_t op, int nf, cudaStream_t st) {
+                         chunks++;
+                         return h2y_forward(c, p, di, ip, dob, op, nf, st);
+                     });
+    if (chunks > 1) c->last_groups = chunks;         // h2y_forward_last_stats: the scratch holds the last chunk only
+    return s;
 }
 
 // ---- inverse ------------------------------------------------------------------------------------------------
@@ -716,7 +926,7 @@ h2y_status h2y_inverse(h2y_ctx *c, const h2y_inverse_params *p, const void *d_yu
     if (s != H2Y_OK) return s;
     if (yuv_stride < h2y_yuv_frame_bytes(p->width, p->height, H2Y_CHROMA_420) || rgb_stride < h2y_rgb_frame_bytes(p)) return H2Y_ERR_ARG;
     if (!aligned16(d_yuv, yuv_stride) || !aligned16(d_rgb, rgb_stride)) return H2Y_ERR_ARG;
-    H2Y_CUDA(c, cudaSetDevice(c->device));
+    H2Y_ON_DEVICE(c);
     cudaStream_t st = (cudaStream_t)stream;
     if (d_invalid) H2Y_CUDA(c, cudaMemsetAsync(d_invalid, 0, sizeof(uint32_t) * nframes, st));
     cudaEvent_t *pev = c->ev[c->profile_count % PROFILE_RING];
@@ -736,7 +946,7 @@ h2y_status h2y_inverse_host(h2y_ctx *c, const h2y_inverse_params *p, const void 
     if (s != H2Y_OK) return s;
     const size_t inb = h2y_yuv_frame_bytes(p->width, p->height, H2Y_CHROMA_420), outb = h2y_rgb_frame_bytes(p);
     if (yuv_stride < inb || rgb_stride < outb) return H2Y_ERR_ARG;
-    H2Y_CUDA(c, cudaSetDevice(c->device));
+    H2Y_ON_DEVICE(c);
     uint32_t *d_inv = nullptr;
     if (h_invalid) {
         void *v;
@@ -772,7 +982,7 @@ h2y_status h2y_inverse444_host(h2y_ctx *c, const h2y_pic_desc *in, int out_bit_d
     if (yuv_stride < inb || rgb_stride < outb) return H2Y_ERR_ARG;
     h2y_clip_limits clip;
     clip_of(in->bit_depth, in->video_full_range_flag, &clip);
-    H2Y_CUDA(c, cudaSetDevice(c->device));
+    H2Y_ON_DEVICE(c);
     uint32_t *d_inv = nullptr;
     if (h_invalid) {
         void *v;

@@ -49,8 +49,13 @@ struct PixK {
 
 // ---- x86-64 conversion semantics -------------------------------------------------------------
 
-// (unsigned int)float on x86-64 is a 64-bit cvttss2si whose low half is kept.
-__device__ __forceinline__ unsigned f2u_x86(float x) { return (unsigned)__float2ll_rz(x); }
+// (unsigned int)float on x86-64 is a 64-bit cvttss2si whose low half is kept; NaN and values outside the int64 range
+// give the "integer indefinite" 0x8000000000000000, whose low half is 0 (CUDA's conversion would saturate instead).
+__device__ __forceinline__ unsigned f2u_x86(float x)
+{
+    if (!(x > -9.2233720e18f && x < 9.2233720e18f)) return 0u;
+    return (unsigned)__float2ll_rz(x);
+}
 
 // (int)double is a 32-bit cvttsd2si: NaN / out of range give INT_MIN.
 __device__ __forceinline__ int d2i_x86(double x)
@@ -212,24 +217,25 @@ __device__ __forceinline__ bool px_matrix_fast(float G, float B, float R, const 
         Y = min(__float2uint_rz(G), k.maxCV);
         Cb = min(__float2uint_rz(B), k.maxCV);
         Cr = min(__float2uint_rz(R), k.maxCV);
-        return G >= 0.0f && B >= 0.0f && R >= 0.0f;
+        // values of 2^32 and above wrap in the reference ((unsigned) keeps the low word): exact route
+        return G >= 0.0f && B >= 0.0f && R >= 0.0f && G < 4294967296.0f && B < 4294967296.0f && R < 4294967296.0f;
     } else if (MK == MK_YCBCR) {
         const double s = __dadd_rn(__dadd_rn(__dmul_rn(k.wr, (double)R), __dmul_rn(k.wg, (double)G)),
                                    __dmul_rn(k.wb, (double)B));
         const float tmpF = __double2float_rn(__dadd_rn(s, 0.5));
         Y = min(__float2uint_rz(tmpF), k.maxCV);
-        ok = tmpF >= 0.0f;
+        ok = tmpF >= 0.0f && tmpF < 4294967296.0f;
         ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(B, tmpF), k.rdb, MAGIC), cb);
         ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(R, tmpF), k.rdr, MAGIC), cr);
     } else if (MK == MK_YDZDX) {
         Y = min(__float2uint_rz(G), k.maxCV);
-        ok = G >= 0.0f;
+        ok = G >= 0.0f && G < 4294967296.0f;
         const double hg = __dmul_rn((double)G, -0.5);
         ok &= trunc_from_magic(__dadd_rz(__dadd_rn(hg, __dmul_rn((double)B, 0.5)), MAGIC), cb);
         ok &= trunc_from_magic(__dadd_rz(__dadd_rn(hg, __dmul_rn((double)R, 0.5)), MAGIC), cr);
     } else {   // MK_Y100
         Y = min(__float2uint_rz(G), k.maxCV);
-        ok = G >= 0.0f;
+        ok = G >= 0.0f && G < 4294967296.0f;
         ok &= trunc_from_magic(__dadd_rz((double)__fadd_rn(__fmul_rn(k.P, G), __fmul_rn(k.Q, B)), MAGIC), cb);
         ok &= trunc_from_magic(__dadd_rz((double)__fadd_rn(__fmul_rn(k.RR, R), __fmul_rn(k.S, G)), MAGIC), cr);
     }

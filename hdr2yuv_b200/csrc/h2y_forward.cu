@@ -49,6 +49,10 @@ struct FwdArgs {
     const FrameK *framek;
     const float *luts;       // [nframes*3][65536]
     unsigned long long *fallback_count;   // pixels that took the exact fallback (diagnostic)
+    // behind a plan-reuse pass (h2y_internal.h): only frames with flag[frame] != 0 are left; in mode 1 this kernel
+    // converts all of them, in mode 2 those the rows kernels declined
+    const SpecCtl *ctl;
+    const int *flag;
 };
 
 // ---- 8-pixel loads -------------------------------------------------------------------------------
@@ -171,12 +175,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_fused(const FwdArgs a)
     int cur_slot = -1;
     unsigned cur_lo = 0, cur_hi = 0;
     unsigned fallbacks = 0;
+    if (a.ctl && a.ctl->nflag == 0) return;                     // the plan-reuse pass left nothing to do
 
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
         const int strip = item % a.nstrips;
         const int seg = (item / a.nstrips) % a.nsegs;
         const int frame = item / (a.nstrips * a.nsegs);
-        if (a.skip_clean && (a.framek[frame].clean || (a.skip_clean > 1 && a.framek[frame].clean3))) continue;   // uniform per CTA
+        if (a.flag && !a.flag[frame]) continue;                 // converted and confirmed by the plan-reuse pass
+        if (a.skip_clean && (!a.ctl || a.ctl->mode == 2) &&
+            (a.framek[frame].clean || (a.skip_clean > 1 && a.framek[frame].clean3))) continue;   // uniform per CTA
         const uint8_t *fsrc = a.src + (size_t)frame * a.src_stride;
         uint16_t *fY = reinterpret_cast<uint16_t *>(a.dst + (size_t)frame * a.dst_stride);
         uint16_t *fCb = fY + (size_t)w * h;
@@ -410,20 +417,8 @@ template <int MK, int CM>
 static h2y_status launch_one(h2y_ctx_impl *c, const FwdArgs &a, int grid, size_t smem, cudaStream_t st)
 {
     H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_fused<MK, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#ifndef H2Y_NO_SWEEP_OVERLAP
-    if (a.skip_clean) {
-        // The sweep behind the fast kernels converts only the frames they left (disjoint output, inputs older than
-        // both): it need not wait for the fast kernel to drain (programmatic stream serialization, as between the
-        // rows-kernel instantiations in h2y_forward2.cu).
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        H2Y_CUDA(c, cudaLaunchKernelEx(&cfg, k_forward_fused<MK, CM>, a));
-    } else
-#endif
+    // The sweep behind the fast kernels converts only the frames they left (disjoint output, inputs older than both):
+    // the caller hands it an auxiliary stream forked at the same point as the fast kernels (h2y_api.cu) and joins later.
     k_forward_fused<MK, CM><<<grid, THREADS, smem, st>>>(a);
     c->launches++;
     H2Y_CUDA(c, cudaGetLastError());
@@ -443,17 +438,20 @@ static h2y_status launch_mk(h2y_ctx_impl *c, const FwdArgs &a, int cm, int grid,
 
 h2y_status launch_forward_fused(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, const void *d_src,
                                 size_t src_stride, void *d_dst, size_t dst_stride, int nframes,
-                                const FrameK *d_framek, const float *d_luts, cudaStream_t st, int skip_clean)
+                                const FrameK *d_framek, const float *d_luts, cudaStream_t st, int skip_clean,
+                                const SpecLaunch *sl, cudaStream_t sweep_stream)
 {
     FwdArgs a;
+    if (sweep_stream) st = sweep_stream;
+    a.ctl = sl ? sl->ctl : nullptr;
+    a.flag = sl ? sl->flag : nullptr;
     a.skip_clean = skip_clean;
     a.src = (const uint8_t *)d_src; a.src_stride = src_stride;
     a.dst = (uint8_t *)d_dst; a.dst_stride = dst_stride;
     a.w = p.src.width; a.h = p.src.height; a.nframes = nframes;
     a.layout = p.src.layout;
     a.use_lut = k.convert_transfer;
-    const char *ex = getenv("H2Y_EXACT_MATH");
-    a.exact_math = ex && ex[0] == '1';
+    a.exact_math = c->sw.exact_math;
     a.k = k; a.framek = d_framek; a.luts = d_luts;
     a.fallback_count = nullptr;
 

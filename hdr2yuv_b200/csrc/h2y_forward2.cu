@@ -41,9 +41,6 @@
 #define H2Y_PAIRS_PER_BRANCH_THREE 1
 #endif
 // Pixel pairs per guard-band branch (1, 2 or 4): 2 measured fastest (profiles/r01/variants.md).
-#ifndef H2Y_ROWS_PDL
-#define H2Y_ROWS_PDL 1
-#endif
 #ifndef H2Y_PAIRS_PER_BRANCH_THREE_NC
 #define H2Y_PAIRS_PER_BRANCH_THREE_NC 1
 #endif
@@ -653,15 +650,32 @@ struct Fwd3Args {
     int split_by_lut2;       // two instantiations share the frames: TWO takes those with lut2_ok, the other the rest
     int split_three_nc;      // likewise for three-table frames: TWO (clamp-free) takes those three_nc_frame() accepts
     long total_rows;         // nframes * h
+    // plan reuse (h2y_internal.h, SpecSeed / SpecCtl).  SPEC instantiations: every frame is converted with the one
+    // predicted FrameK at b.framek[0] while the warp gathers the frame's extrema into `slots`; `bail[frame]` is raised
+    // when a code falls outside the predicted LUT window (before it is used as an index).  Classic instantiations
+    // launched behind a SPEC pass convert only frames with flag[frame] != 0, and only when ctl->mode == 2.
+    const SpecCtl *ctl;
+    const int *flag;
+    int *bail;
+    unsigned *slots;
 };
 
 constexpr int THREADS3 = 512, WARPS3 = THREADS3 / 32;     // 16 warps (12 x 168 registers measured 6 % slower: latency hiding wins)
 
 // THREE: the instantiation for frames whose channels need a table each (FrameK::clean3); with TWO as well: the
 // clamp-free chroma path on those three tables (frames that three_nc_frame() accepts)
-template <int MK, int NCH, int CFG, bool TWO, bool THREE>
+// packed 16-bit min / max (ptxas fuses two of them into one VIMNMX3.U16x2)
+__device__ __forceinline__ unsigned vmin2(unsigned a, unsigned b) { unsigned r; asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ unsigned vmax2(unsigned a, unsigned b) { unsigned r; asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+
+// order-preserving key of a finite non-negative half code, as k_stats_vec / k_plan use it (h2y_stats.cu: fkey)
+__device__ __forceinline__ unsigned half_code_key(unsigned code) { return __float_as_uint(half_bits_to_float(code)) | 0x80000000u; }
+
+template <int MK, int NCH, int CFG, bool TWO, bool THREE, bool SPEC = false>
 __device__ __forceinline__ void rows_body(const Fwd3Args &A)
 {
+    if (SPEC) { if (A.ctl->skip) return; }                       // no usable seed: the classic kernels convert everything
+    else if (A.ctl && A.ctl->mode != 2) return;                  // behind a SPEC pass: the rows kernels serve mode 2 only
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *lut_s = reinterpret_cast<float *>(smem_raw);
     // shared-window address of the LUT, held in an ordinary register (the asm hides that it is uniform: as a uniform
@@ -703,7 +717,8 @@ __device__ __forceinline__ void rows_body(const Fwd3Args &A)
                         pk(11.0f / 512.0f, 11.0f / 512.0f), pk(5.0f / 512.0f, 5.0f / 512.0f)};
 
     for (int frame = f_first; frame <= f_last; frame++) {
-        const FrameK &fk = a.framek[frame];
+        const FrameK &fk = a.framek[SPEC ? 0 : frame];
+        if (!SPEC && A.flag && !A.flag[frame]) continue; // converted and confirmed by the SPEC pass
         if (THREE ? !fk.clean3 : !fk.clean) continue;    // uniform per CTA: another launch converts this frame
         if (!THREE && A.split_by_lut2 && TWO != two_lut_frame<CFG>(a, fk)) continue;   // the other instantiation converts this frame
         if (THREE && A.split_three_nc && TWO != three_nc_frame<CFG>(a, fk)) continue;
@@ -773,6 +788,11 @@ __device__ __forceinline__ void rows_body(const Fwd3Args &A)
             for (int i = 0; i < 6; i++)
 #pragma unroll
                 for (int c = 0; c < 4; c++) acc[i][c] = 0ull;
+            // SPEC: running extrema of the raw codes per word kind, (R,G) (B,R) (G,B) for RGB rows, (R,G) (B,A) for RGBA
+            unsigned smn0 = 0xFFFFFFFFu, smn1 = 0xFFFFFFFFu, smn2 = 0xFFFFFFFFu, smx0 = 0u, smx1 = 0u, smx2 = 0u;
+            // no code may index past the LUT copy in shared memory; codes inside it but outside the predicted window read
+            // stale entries, which the verify step catches through the gathered extrema (the frame is converted again)
+            constexpr unsigned SPEC_CAP2 = ((TWO ? LUT2_CODES : (unsigned)LUT_MAX_CODES) - 1u) * 0x10001u;
 
             const int rfirst = ys - 6, rlast = ye + 4;                          // rows feeding outputs ys/2 .. ye/2-1 (both even)
             // running pointers: source row (clamped = edge replicate), Y row, chroma output row
@@ -876,8 +896,9 @@ __device__ __forceinline__ void rows_body(const Fwd3Args &A)
             // loading the next row only after the pixel stage exposes the load latency: profiles/r01/variants.md)
             RawPx<NCH> raw;
             load_px8<NCH>(raw, sp, 0, 0, 0);
+            int r = rfirst;
 #pragma unroll 1
-            for (int r = rfirst; r <= rlast; r++) {
+            for (; r <= rlast; r++) {
                 unsigned g[8], b[8], rr[8];
 #ifdef H2Y_LOAD_BEFORE_SPLIT
                 RawPx<NCH> cur = raw;
@@ -885,6 +906,26 @@ __device__ __forceinline__ void rows_body(const Fwd3Args &A)
                 if (r < rlast) load_px8<NCH>(raw, sp, 0, 0, 0);                 // prefetch the next row
                 row_split(cur, g, b, rr);
 #else
+                if (SPEC) {
+                    // this row's codes join the running extrema (halo rows and halo lanes count twice: harmless), and no
+                    // code above the predicted window may reach the gathers: the whole frame is handed back instead
+                    if (NCH == 3) {
+                        smn0 = vmin2(vmin2(smn0, raw.v[0].x), vmin2(raw.v[0].w, vmin2(raw.v[1].z, raw.v[2].y)));
+                        smn1 = vmin2(vmin2(smn1, raw.v[0].y), vmin2(raw.v[1].x, vmin2(raw.v[1].w, raw.v[2].z)));
+                        smn2 = vmin2(vmin2(smn2, raw.v[0].z), vmin2(raw.v[1].y, vmin2(raw.v[2].x, raw.v[2].w)));
+                        smx0 = vmax2(vmax2(smx0, raw.v[0].x), vmax2(raw.v[0].w, vmax2(raw.v[1].z, raw.v[2].y)));
+                        smx1 = vmax2(vmax2(smx1, raw.v[0].y), vmax2(raw.v[1].x, vmax2(raw.v[1].w, raw.v[2].z)));
+                        smx2 = vmax2(vmax2(smx2, raw.v[0].z), vmax2(raw.v[1].y, vmax2(raw.v[2].x, raw.v[2].w)));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            smn0 = vmin2(smn0, vmin2(raw.v[i].x, raw.v[i].z)); smx0 = vmax2(smx0, vmax2(raw.v[i].x, raw.v[i].z));
+                            smn1 = vmin2(smn1, vmin2(raw.v[i].y, raw.v[i].w)); smx1 = vmax2(smx1, vmax2(raw.v[i].y, raw.v[i].w));
+                        }
+                    }
+                    const unsigned top = NCH == 3 ? vmax2(vmax2(smx0, smx1), smx2) : vmax2(smx0, smx1 & 0xffffu);   // alpha is not a colour sample
+                    if (__any_sync(0xffffffffu, vmax2(top, SPEC_CAP2) != SPEC_CAP2)) break;
+                }
                 // the codes leave the sample registers first, then the next row is loaded into the same registers: no copy
                 row_split(raw, g, b, rr);
                 next_src(r);
@@ -903,41 +944,60 @@ __device__ __forceinline__ void rows_body(const Fwd3Args &A)
                 yp += w;
                 if ((r & 1) == 0) row_even(o, r); else row_odd(o);
             }
+            if (SPEC) {
+                if (r <= rlast) { if (lane == 0) A.bail[frame] = 1; continue; }     // left the row loop early
+                // the run's extrema join the frame's statistics slots in the layout k_plan reads (h2y_stats.cu)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    smn0 = vmin2(smn0, __shfl_xor_sync(0xffffffffu, smn0, o)); smx0 = vmax2(smx0, __shfl_xor_sync(0xffffffffu, smx0, o));
+                    smn1 = vmin2(smn1, __shfl_xor_sync(0xffffffffu, smn1, o)); smx1 = vmax2(smx1, __shfl_xor_sync(0xffffffffu, smx1, o));
+                    if (NCH == 3) {
+                        smn2 = vmin2(smn2, __shfl_xor_sync(0xffffffffu, smn2, o)); smx2 = vmax2(smx2, __shfl_xor_sync(0xffffffffu, smx2, o));
+                    }
+                }
+                if (lane == 0) {
+                    unsigned cmin[3], cmax[3];                              // G, B, R
+                    if (NCH == 3) {
+                        cmin[0] = min(smn0 >> 16, smn2 & 0xffffu); cmax[0] = max(smx0 >> 16, smx2 & 0xffffu);
+                        cmin[1] = min(smn1 & 0xffffu, smn2 >> 16); cmax[1] = max(smx1 & 0xffffu, smx2 >> 16);
+                        cmin[2] = min(smn0 & 0xffffu, smn1 >> 16); cmax[2] = max(smx0 & 0xffffu, smx1 >> 16);
+                    } else {
+                        cmin[0] = smn0 >> 16; cmax[0] = smx0 >> 16;
+                        cmin[1] = smn1 & 0xffffu; cmax[1] = smx1 & 0xffffu;
+                        cmin[2] = smn0 & 0xffffu; cmax[2] = smx0 & 0xffffu;
+                    }
+                    unsigned *sl = A.slots + (size_t)frame * 12;
+#pragma unroll
+                    for (int ch3 = 0; ch3 < 3; ch3++) {
+                        atomicMin(sl + 2 * ch3, half_code_key(cmin[ch3]));
+                        atomicMax(sl + 2 * ch3 + 1, half_code_key(cmax[ch3]));
+                    }
+                    atomicMin(sl + 6, min(cmin[0], min(cmin[1], cmin[2])));
+                    atomicMax(sl + 7, max(cmax[0], max(cmax[1], cmax[2])));
+                }
+            }
         }
     }
 }
 
-template <int MK, int NCH, int CFG = 0, bool TWO = false, bool THREE = false>
+template <int MK, int NCH, int CFG = 0, bool TWO = false, bool THREE = false, bool SPEC = false>
 __global__ void __launch_bounds__(THREADS3, 1) k_forward_exr420_rows(const Fwd3Args A)
 {
-#if H2Y_ROWS_PDL
-    // The instantiations of one call convert disjoint frames and read only what the statistics pass wrote, so the next
-    // one may move onto SMs as this one's CTAs leave them (programmatic dependent launch; measured 14 us per call).
-    // No griddepcontrol.wait anywhere: nothing here consumes a predecessor's output, and the next ordinary operation in
-    // the stream (the general-kernel sweep, a copy, an event) is ordered behind ALL of these launches, not only the last
-    // one -- tests/test_forward_gpu.py::test_stream_order_behind_the_overlapped_rows_launches checks exactly that.  (A
-    // wait at the end of every instantiation, to make completion transitive by hand, cost 0.2 ms per call.)
-    asm volatile("griddepcontrol.launch_dependents;");
-#endif
-    rows_body<MK, NCH, CFG, TWO, THREE>(A);
+    rows_body<MK, NCH, CFG, TWO, THREE, SPEC>(A);
 }
 
-// launch an instantiation that may overlap the tail of the previous one (see above)
+// The instantiations of one call convert disjoint frames and read only what the prologue wrote, so they need not wait
+// for one another: the first runs on the caller's stream, the others on the context's auxiliary streams, forked behind
+// an event recorded after the prologue and joined by events before anything else is queued (aux_fork / aux_stream /
+// aux_join, h2y_api.cu).  Each moves onto the SMs as its predecessor's CTAs leave them.  (Round 1 overlapped them with
+// programmatic stream serialization and no griddepcontrol.wait; the stream ordering that relied on is not documented.)
 template <class K>
-static cudaError_t launch_rows_overlapped(K kernel, int grid, size_t smem, cudaStream_t st, const Fwd3Args &A)
+static cudaError_t launch_rows_on(K kernel, int grid, size_t smem, cudaStream_t st, const Fwd3Args &A)
 {
-#if H2Y_ROWS_PDL
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS3); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, A);
-#else
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     kernel<<<grid, THREADS3, smem, st>>>(A);
-    return cudaSuccess;
-#endif
+    return cudaGetLastError();
 }
 
 // =================================================================================================
@@ -1176,8 +1236,7 @@ h2y_status launch_forward_u16_420(h2y_ctx_impl *c, const h2y_forward_params &p, 
         A3.sub = WARPS3 / A3.wps;
         A3.total_rows = (long)nframes * a.h;
         const long rows_per_worker = A3.total_rows / ((long)c->sm_count * A3.sub);
-        const char *force = getenv("H2Y_FORWARD_KERNEL");             // "ring" / "rows": tests and experiments
-        const bool want_rows = force ? force[1] == 'o' : rows_per_worker >= 128;
+        const bool want_rows = c->sw.fwd_kernel ? c->sw.fwd_kernel == 2 : rows_per_worker >= 128;    // forced by tests and experiments
         if (want_rows && A3.total_rows >= 2) {
             int g3 = c->sm_count;
             while (g3 > 1 && A3.total_rows / ((long)g3 * A3.sub) < 16) g3 >>= 1;   // forced on a tiny batch
@@ -1234,11 +1293,40 @@ static h2y_status launch_v2(h2y_ctx_impl *c, const Fwd2Args &a, int grid, size_t
     return H2Y_OK;
 }
 
-h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, int tmp_bit_depth,
-                                 const void *d_src, size_t src_stride, void *d_dst, size_t dst_stride, int nframes,
-                                 const FrameK *d_framek, const float *d_luts, cudaStream_t st, int *took_three_table_frames)
+// Geometry of a rows-kernel launch and whether the batch is large enough for it
+static bool rows_plan(const h2y_ctx_impl *c, const Fwd2Args &a, int nframes, Fwd3Args *A3, int *g3)
 {
-    Fwd2Args a;
+    memset(A3, 0, sizeof(*A3));
+    A3->b = a;
+    // warps per row worker: the largest count that divides both the strips and the CTA's warps
+    A3->wps = 1;
+    for (int d = 1; d <= WARPS3; d++) if (WARPS3 % d == 0 && a.nstrips % d == 0) A3->wps = d;
+    A3->sub = WARPS3 / A3->wps;
+    A3->total_rows = (long)nframes * a.h;
+    const long rows_per_worker = A3->total_rows / ((long)c->sm_count * A3->sub);
+    const bool want_rows = c->sw.fwd_kernel ? c->sw.fwd_kernel == 2 : rows_per_worker >= 128;
+    if (!want_rows || A3->total_rows < 2) return false;
+    *g3 = c->sm_count;
+    while (*g3 > 1 && A3->total_rows / ((long)*g3 * A3->sub) < 16) *g3 >>= 1;       // forced on a tiny batch
+    return true;
+}
+
+// the headline configurations get their constants as immediates (KC<10>, KC<12>)
+static bool exr_cfgd(const h2y_ctx_impl *c, const PixK &k, const Fwd2Args &a, int tmp_bit_depth)
+{
+    const int sc = 1 << (tmp_bit_depth - 8);
+    return k.mat_kind == MK_YCBCR && k.wr == 0.2627 && k.wg == 0.6780 && k.wb == 0.0593 && k.db == 1.8814 && k.dr == 1.4746 &&
+           (tmp_bit_depth == 10 || tmp_bit_depth == 12) && k.scale_mode == SC_VIDEO && k.down_shift == 0 &&
+           a.k.mulY == (float)(235 * sc) && a.k.mulC == (float)(240 * sc) && a.k.addY == (float)(16 * sc) &&
+           a.k.addC == (float)(16 * sc) && (int)k.loY == 16 * sc && (int)k.hiY == 235 * sc && (int)k.loC == 16 * sc &&
+           (int)k.hiC == 240 * sc && (int)k.maxCV == (1 << tmp_bit_depth) - 1 && c->sw.guard_log2 < 0 && !c->sw.no_specialised;
+}
+
+static void exr_args(const h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, int tmp_bit_depth, const void *d_src,
+                     size_t src_stride, void *d_dst, size_t dst_stride, int nframes, const FrameK *d_framek,
+                     const float *d_luts, Fwd2Args *pa)
+{
+    Fwd2Args &a = *pa;
     a.src = (const uint8_t *)d_src; a.src_stride = src_stride;
     a.dst = (uint8_t *)d_dst; a.dst_stride = dst_stride;
     a.w = p.src.width; a.h = p.src.height; a.nframes = nframes;
@@ -1246,9 +1334,9 @@ h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, c
     if (k.scale_mode == SC_FULL) { a.k.mulC = k.mulY; a.k.addY = 0.0f; a.k.addC = 0.0f; }   // x*maxCV (+0 is exact)
     a.framek = d_framek; a.luts = d_luts;
     a.fallback_count = nullptr;
-    // the fp32 evaluation is within G/2 of the reference at this depth: G = 2^(depth-21)
+    // the fp32 evaluation is within 7.2/8 G of the reference at this depth: G = 2^(depth-22)
     a.guard = 1.0f / (float)(1 << (H2Y_GUARD_SHIFT - tmp_bit_depth));
-    if (const char *e = getenv("H2Y_EXPERIMENT_GUARD_LOG2")) a.guard = exp2f(-(float)atoi(e));   // timing experiments only: breaks parity
+    if (c->sw.guard_log2 >= 0) a.guard = exp2f(-(float)c->sw.guard_log2);   // timing experiments only: breaks parity
     a.wr = (float)k.wr; a.wg = (float)k.wg; a.wb = (float)k.wb;
     a.rdb = k.mat_kind == MK_YCBCR ? (float)k.rdb : 0.5f;
     a.rdr = k.mat_kind == MK_YCBCR ? (float)k.rdr : 0.5f;
@@ -1270,76 +1358,86 @@ h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, c
     a.seg_rows = seg_rows;
     a.nsegs = (a.h + seg_rows - 1) / seg_rows;
     a.nitems = nframes * a.nsegs * a.nstrips;
+}
+
+// Can this call take the single-pass route (SPEC instantiations exist for the compiled-in configurations only)?
+bool forward_exr420_spec_supported(const h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, int tmp_bit_depth, int nframes)
+{
+    if (!forward_exr420_supported(p, k, tmp_bit_depth)) return false;
+    Fwd2Args a;
+    exr_args(c, p, k, tmp_bit_depth, nullptr, 0, nullptr, 0, nframes, nullptr, nullptr, &a);
+    Fwd3Args A3;
+    int g3;
+    return exr_cfgd(c, k, a, tmp_bit_depth) && rows_plan(c, a, nframes, &A3, &g3);
+}
+
+template <int NC, int DD>
+static h2y_status launch_cfgd(h2y_ctx_impl *c, Fwd3Args &A3, int g3, cudaStream_t st, bool spec)
+{
+    const size_t smem2 = (size_t)2 * LUT2_CODES * sizeof(float), smem3 = (size_t)LUT_MAX_CODES * sizeof(float),
+                 smemT = (size_t)LUT3_FLOATS * sizeof(float);
+    A3.split_by_lut2 = 1;
+    A3.split_three_nc = 1;
+    h2y_status s = aux_fork(c, st);
+    if (s != H2Y_OK) return s;
+    if (spec) {
+        // single pass: the frames are converted with the predicted plan; two-copy or single-copy LUT by the seed's window
+        H2Y_CUDA(c, launch_rows_on(k_forward_exr420_rows<MK_YCBCR, NC, DD, true, false, true>, g3, smem2, st, A3));
+        H2Y_CUDA(c, launch_rows_on(k_forward_exr420_rows<MK_YCBCR, NC, DD, false, false, true>, g3, smem3, aux_stream(c, 0), A3));
+        c->launches += 2;
+        return H2Y_OK;
+    }
+    // frames whose code range allows two pre-scaled LUT copies, then the rest; three-table frames, with and without
+    // matrix_convert's chroma clamp
+    H2Y_CUDA(c, launch_rows_on(k_forward_exr420_rows<MK_YCBCR, NC, DD, true>, g3, smem2, st, A3));
+    H2Y_CUDA(c, launch_rows_on(k_forward_exr420_rows<MK_YCBCR, NC, DD, false>, g3, smem3, aux_stream(c, 0), A3));
+    H2Y_CUDA(c, launch_rows_on(k_forward_exr420_rows<MK_YCBCR, NC, DD, false, true>, g3, smemT, aux_stream(c, 1), A3));
+    H2Y_CUDA(c, launch_rows_on(k_forward_exr420_rows<MK_YCBCR, NC, DD, true, true>, g3, smemT, aux_stream(c, 2), A3));
+    c->launches += 4;
+    return H2Y_OK;
+}
+
+template <int MKV, int NC>
+static h2y_status launch_generic_rows(h2y_ctx_impl *c, Fwd3Args &A3, int g3, cudaStream_t st)
+{
+    const size_t smem3 = (size_t)LUT_MAX_CODES * sizeof(float), smemT = (size_t)LUT3_FLOATS * sizeof(float);
+    h2y_status s = aux_fork(c, st);
+    if (s != H2Y_OK) return s;
+    H2Y_CUDA(c, launch_rows_on(k_forward_exr420_rows<MKV, NC>, g3, smem3, st, A3));
+    H2Y_CUDA(c, launch_rows_on(k_forward_exr420_rows<MKV, NC, 0, false, true>, g3, smemT, aux_stream(c, 0), A3));
+    c->launches += 2;
+    return H2Y_OK;
+}
+
+// The caller joins the auxiliary streams (aux_join) after it has queued the general-kernel sweep.
+h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, int tmp_bit_depth,
+                                 const void *d_src, size_t src_stride, void *d_dst, size_t dst_stride, int nframes,
+                                 const FrameK *d_framek, const float *d_luts, cudaStream_t st, int *took_three_table_frames,
+                                 const SpecLaunch *sl)
+{
+    Fwd2Args a;
+    exr_args(c, p, k, tmp_bit_depth, d_src, src_stride, d_dst, dst_stride, nframes, d_framek, d_luts, &a);
     const int nch = layout_channels(p.src.layout);
     // large batches: the warp-autonomous kernel (rows split evenly over all warps of the GPU)
-    {
-        Fwd3Args A3;
-        A3.b = a;
-        // warps per row worker: the largest count that divides both the strips and the CTA's warps
-        A3.wps = 1;
-        for (int d = 1; d <= WARPS3; d++) if (WARPS3 % d == 0 && a.nstrips % d == 0) A3.wps = d;
-        A3.sub = WARPS3 / A3.wps;
-        A3.total_rows = (long)nframes * a.h;
-        A3.split_by_lut2 = 0;
-        A3.split_three_nc = 0;
-        const long rows_per_worker = A3.total_rows / ((long)grid_max * A3.sub);
-        const char *force = getenv("H2Y_FORWARD_KERNEL");             // "ring" / "rows": tests and experiments
-        const bool want_rows = force ? force[0] == 'r' && force[1] == 'o' : rows_per_worker >= 128;
-        if (want_rows && A3.total_rows >= 2) {
-            const size_t smem3 = (size_t)LUT_MAX_CODES * sizeof(float);
-            int g3 = grid_max;
-            while (g3 > 1 && A3.total_rows / ((long)g3 * A3.sub) < 16) g3 >>= 1;   // forced on a tiny batch
-            // frames that need a table per channel (FrameK::clean3) get a third launch of the same kernel
-            const size_t smemT = (size_t)LUT3_FLOATS * sizeof(float);
-            if (took_three_table_frames) *took_three_table_frames = 1;
-#define L3(MKV, NC)                                                                                                        \
-    do {                                                                                                                   \
-        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MKV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
-        k_forward_exr420_rows<MKV, NC><<<g3, THREADS3, smem3, st>>>(A3);                                                  \
-        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MKV, NC, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT)); \
-        k_forward_exr420_rows<MKV, NC, 0, false, true><<<g3, THREADS3, smemT, st>>>(A3);                                  \
-        c->launches++;                                                                                                     \
-    } while (0)
-            // the headline configurations get their constants as immediates (KC<10>, KC<12>)
-            const int sc = 1 << (tmp_bit_depth - 8);
-            const bool cfgd = k.mat_kind == MK_YCBCR && k.wr == 0.2627 && k.wg == 0.6780 && k.wb == 0.0593 && k.db == 1.8814 &&
-                              k.dr == 1.4746 && (tmp_bit_depth == 10 || tmp_bit_depth == 12) && k.scale_mode == SC_VIDEO &&
-                              k.down_shift == 0 && a.k.mulY == (float)(235 * sc) && a.k.mulC == (float)(240 * sc) &&
-                              a.k.addY == (float)(16 * sc) && a.k.addC == (float)(16 * sc) && (int)k.loY == 16 * sc &&
-                              (int)k.hiY == 235 * sc && (int)k.loC == 16 * sc && (int)k.hiC == 240 * sc &&
-                              (int)k.maxCV == (1 << tmp_bit_depth) - 1 && !getenv("H2Y_EXPERIMENT_GUARD_LOG2") &&
-                              !getenv("H2Y_NO_SPECIALISED");
-            if (cfgd) {
-#define L3C(NC, DD)                                                                                                        \
-    do {                                                                                                                   \
-        /* frames whose code range allows two pre-scaled LUT copies, then the rest */                                      \
-        const size_t smem2 = (size_t)2 * LUT2_CODES * sizeof(float);                                                       \
-        A3.split_by_lut2 = 1;                                                                                              \
-        A3.split_three_nc = 1;                                                                                             \
-        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
-        k_forward_exr420_rows<MK_YCBCR, NC, DD, true><<<g3, THREADS3, smem2, st>>>(A3);                                   \
-        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
-        H2Y_CUDA(c, launch_rows_overlapped(k_forward_exr420_rows<MK_YCBCR, NC, DD, false>, g3, smem3, st, A3));            \
-        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT)); \
-        H2Y_CUDA(c, launch_rows_overlapped(k_forward_exr420_rows<MK_YCBCR, NC, DD, false, true>, g3, smemT, st, A3));      \
-        /* three-table frames that provably stay inside matrix_convert's chroma clamp */                                   \
-        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_exr420_rows<MK_YCBCR, NC, DD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT)); \
-        H2Y_CUDA(c, launch_rows_overlapped(k_forward_exr420_rows<MK_YCBCR, NC, DD, true, true>, g3, smemT, st, A3));       \
-        c->launches += 3;                                                                                                  \
-    } while (0)
-                if (tmp_bit_depth == 10) { if (nch == 3) L3C(3, 10); else L3C(4, 10); }
-                else { if (nch == 3) L3C(3, 12); else L3C(4, 12); }
-#undef L3C
-            } else if (k.mat_kind == MK_YCBCR) { if (nch == 3) L3(MK_YCBCR, 3); else L3(MK_YCBCR, 4); }
-            else { if (nch == 3) L3(MK_YDZDX, 3); else L3(MK_YDZDX, 4); }
-#undef L3
-            c->launches++;
-            H2Y_CUDA(c, cudaGetLastError());
-            return H2Y_OK;
+    Fwd3Args A3;
+    int g3 = 0;
+    if (rows_plan(c, a, nframes, &A3, &g3)) {
+        if (sl) { A3.ctl = sl->ctl; A3.flag = sl->flag; A3.bail = sl->bail; A3.slots = sl->slots; }
+        // frames that need a table per channel (FrameK::clean3) are served by further instantiations of the same kernel
+        if (took_three_table_frames) *took_three_table_frames = 1;
+        const bool spec = sl && sl->spec;
+        if (exr_cfgd(c, k, a, tmp_bit_depth)) {
+            if (tmp_bit_depth == 10) return nch == 3 ? launch_cfgd<3, 10>(c, A3, g3, st, spec) : launch_cfgd<4, 10>(c, A3, g3, st, spec);
+            return nch == 3 ? launch_cfgd<3, 12>(c, A3, g3, st, spec) : launch_cfgd<4, 12>(c, A3, g3, st, spec);
         }
+        if (spec) return H2Y_ERR_UNSUPPORTED;                     // forward_exr420_spec_supported() said otherwise
+        if (k.mat_kind == MK_YCBCR) return nch == 3 ? launch_generic_rows<MK_YCBCR, 3>(c, A3, g3, st) : launch_generic_rows<MK_YCBCR, 4>(c, A3, g3, st);
+        return nch == 3 ? launch_generic_rows<MK_YDZDX, 3>(c, A3, g3, st) : launch_generic_rows<MK_YDZDX, 4>(c, A3, g3, st);
     }
+    if (sl && sl->spec) return H2Y_ERR_UNSUPPORTED;
+    if (sl) return H2Y_OK;        // behind a SPEC pass the general kernel converts whatever is flagged (small batches cannot get here)
     const size_t smem = (size_t)RING_ROWS * RING_PITCH * sizeof(float) + (size_t)LUT_MAX_CODES * sizeof(float);
-    const int grid = a.nitems < grid_max ? a.nitems : grid_max;
+    const int grid = a.nitems < c->sm_count ? a.nitems : c->sm_count;
     if (k.mat_kind == MK_YCBCR)
         return nch == 3 ? launch_v2<MK_YCBCR, 3>(c, a, grid, smem, st) : launch_v2<MK_YCBCR, 4>(c, a, grid, smem, st);
     return nch == 3 ? launch_v2<MK_YDZDX, 3>(c, a, grid, smem, st) : launch_v2<MK_YDZDX, 4>(c, a, grid, smem, st);

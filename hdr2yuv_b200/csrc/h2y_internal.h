@@ -28,7 +28,44 @@ struct FrameK {
     int clean3;
     unsigned ch_lo[3], ch_hi[3];
     int zero_entry[3];          // table entry ch_lo[c] holds the value of code 0 (see k_plan)
+    // 1: the single-pass (plan-reuse) kernel converted this frame with the previous plan and the statistics it gathered
+    // on the way confirmed that plan; every later kernel of the call leaves the frame alone (h2y_forward2.cu, "SPEC")
+    int spec_done;
 };
+
+// ---- single-pass forward with plan reuse ("K1s") ---------------------------------------------------
+// The reference needs a frame's extrema before its first pixel (common.cpp:66-168 -> convert.cpp:936-940), which costs
+// a second read of the input.  Frames of a sequence usually share their (int) floor / ceiling, so the rows kernel can
+// convert with the PREVIOUS plan while it gathers this frame's extrema from the samples it loads anyway; a verify step
+// then compares plans and only the frames that differ are converted again the classic way.
+struct SpecSeed {               // device-resident, one per context: the plan predicted for the next call's frames
+    int valid;
+    int est_floor, est_ceiling; // shared by G, B, R
+    unsigned code_lo, code_hi;  // every half code whose value truncates into [floor, ceiling]: the LUT window
+    int lut2_ok;
+};
+struct SpecCtl {                // device-resident, one per call
+    int skip;                   // no usable seed: the speculative kernels return at once, every frame is flagged
+    int nflag;                  // frames the classic kernels still have to convert
+    int mode;                   // 0 nothing to do, 1 the general kernel converts the flagged frames, 2 the rows kernels do
+    int nframes;
+    int seq;                    // call counter (the host reads a copy of this struct, late, as feedback for its policy)
+    int uniform;                // frames of this call whose final plan equals the last frame's (classic calls)
+    int pad[2];
+};
+
+// test / experiment switches: read from the environment once, at h2y_ctx_create, and changed per context through
+// h2y_ctx_set_option (the product path never calls getenv afterwards)
+struct Switches {
+    int force_staged, force_v1, no_specialised, exact_math;
+    int fwd_kernel;             // 0 automatic, 1 "ring", 2 "rows"
+    int inv_kernel;             // 0 automatic, 1 "tile", 2 "rows"
+    int stats_gx;               // 0 automatic
+    int guard_log2;             // < 0: the derived guard band; otherwise 2^-n (timing experiments, breaks parity)
+    int spec;                   // plan reuse: -1 automatic (host policy), 0 never, 1 whenever a seed exists
+};
+void switches_from_env(Switches *s);
+int switches_set(Switches *s, const char *name, const char *value);
 constexpr unsigned LUT3_FLOATS = 58000;  // three tables together: 232 000 B
 constexpr unsigned LUT2_CODES = 29000;   // 2 x 29000 floats = 232 000 B of the 232 448 B a CTA may use (half code 0x7148 ~ 10 800)
 
@@ -38,8 +75,8 @@ struct h2y_ctx_impl {
     int last_cuda_error;
     unsigned long long launches;
     // scratch, grown on demand
-    void *scratch[8];
-    size_t scratch_bytes[8];
+    void *scratch[9];
+    size_t scratch_bytes[9];
     // host pipeline
     cudaStream_t s_h2d, s_compute, s_d2h;
     int pipeline_ready;
@@ -49,11 +86,42 @@ struct h2y_ctx_impl {
     // profiling hooks
     int profile_on, profile_count;      // bracketed calls since h2y_profile_enable (ring of PROFILE_RING)
     cudaEvent_t ev[16][3];
+    Switches sw;
+    // instantiations of one call that convert disjoint frames run on forked streams joined by events
+    cudaStream_t s_aux[4];
+    cudaEvent_t ev_fork, ev_join[4];
+    int aux_ready, aux_forked, aux_used;
+    // one stream in flight per context: a call on another stream first waits for the previous call's work
+    cudaEvent_t ev_busy;
+    int busy_valid;
+    cudaStream_t busy_stream;
+    // plan reuse (SpecSeed / SpecCtl above)
+    void *spec_dev;                     // SpecSeed + SpecCtl + seed LUT (65536 floats) + one predicted FrameK
+    SpecCtl *spec_fb;                   // pinned: copy of the last SpecCtl, read late by the host policy
+    int spec_seen_seq, spec_hint;       // policy state: feedback already acted upon; 1 = try plan reuse in the next call
+    int spec_seq;                       // calls issued
+    unsigned long long spec_key;        // parameters the seed belongs to (0: none yet)
+    int last_is_float;
+    int last_spec;                      // the last group of the last h2y_forward call took the single-pass route
+    int last_groups;                    // 256-frame groups of the last h2y_forward call (h2y_forward_last_stats)
+};
+// fork / join of the context's auxiliary streams around kernels that convert disjoint frames (h2y_api.cu)
+h2y_status aux_fork(h2y_ctx_impl *c, cudaStream_t st);     // record the fork point on st (idempotent until aux_join)
+cudaStream_t aux_stream(h2y_ctx_impl *c, int i);            // auxiliary stream i, made to wait for the fork point
+h2y_status aux_join(h2y_ctx_impl *c, cudaStream_t st);     // st waits for every auxiliary stream used since aux_fork
+
+// what a launch behind (or as) a plan-reuse pass needs to know
+struct SpecLaunch {
+    const SpecCtl *ctl;
+    const int *flag;            // per frame: 1 = still to be converted by the classic kernels
+    int *bail;                  // per frame: raised by the SPEC kernel when a code left the predicted LUT window
+    unsigned *slots;            // statistics slots the SPEC kernel fills
+    int spec;                   // 1: launch the SPEC instantiations; 0: classic instantiations restricted to `flag`
 };
 
 constexpr int PROFILE_RING = 16;
 enum ScratchSlot { SCR_STATS = 0, SCR_FRAMEK = 1, SCR_LUT = 2, SCR_TMP444 = 3, SCR_UNPACK = 4, SCR_OUT = 5,
-                   SCR_RING_IN = 6, SCR_RING_OUT = 7 };
+                   SCR_RING_IN = 6, SCR_RING_OUT = 7, SCR_SPEC = 8, SCR_COUNT = 9 };
 
 h2y_status scratch_reserve(h2y_ctx_impl *c, int slot, size_t bytes, void **out);
 h2y_status cuda_fail(h2y_ctx_impl *c, cudaError_t e);
@@ -78,6 +146,15 @@ inline int layout_channels(int l) { return (l == H2Y_LAYOUT_RGBA16 || l == H2Y_L
 h2y_status launch_stats_and_luts(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, const void *d_src,
                                  size_t src_stride, int nframes, FrameK **d_framek, float **d_luts,
                                  cudaStream_t st);
+// plan reuse: device state of the context, the passes around the SPEC kernel, and the seed update after any call
+struct SpecDev { SpecSeed *seed; SpecCtl *ctl; FrameK *pred; float *seed_lut; };
+h2y_status spec_dev(h2y_ctx_impl *c, SpecDev *out);
+h2y_status launch_spec_prepare(h2y_ctx_impl *c, int nframes, int seq, FrameK **d_framek, unsigned **d_slots, int **d_bail,
+                               int **d_flag, cudaStream_t st);
+h2y_status launch_spec_verify_and_redo_prologue(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, const void *d_src,
+                                                size_t src_stride, int nframes, float **d_luts, cudaStream_t st);
+h2y_status launch_seed_update(h2y_ctx_impl *c, const FrameK *d_framek, const float *d_luts, int nframes, int seq,
+                              int after_spec, int force, cudaStream_t st);
 h2y_status launch_stats_planar(h2y_ctx_impl *c, const h2y_pic_desc &pic, const void *const d_planes[3],
                                FrameK **d_framek, cudaStream_t st);
 
@@ -111,12 +188,15 @@ bool forward_u16_420_supported(const h2y_forward_params &p, const PixK &k);
 h2y_status launch_forward_u16_420(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, const void *d_src,
                                   size_t src_stride, void *d_dst, size_t dst_stride, int nframes, cudaStream_t st);
 bool forward_exr420_supported(const h2y_forward_params &p, const PixK &k, int tmp_bit_depth);
+bool forward_exr420_spec_supported(const h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, int tmp_bit_depth, int nframes);
 h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, int tmp_bit_depth,
                                  const void *d_src, size_t src_stride, void *d_dst, size_t dst_stride, int nframes,
-                                 const FrameK *d_framek, const float *d_luts, cudaStream_t st, int *took_three_table_frames = nullptr);
+                                 const FrameK *d_framek, const float *d_luts, cudaStream_t st, int *took_three_table_frames = nullptr,
+                                 const SpecLaunch *sl = nullptr);
 h2y_status launch_forward_fused(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, const void *d_src,
                                 size_t src_stride, void *d_dst, size_t dst_stride, int nframes,
-                                const FrameK *d_framek, const float *d_luts, cudaStream_t st, int skip_clean = 0);
+                                const FrameK *d_framek, const float *d_luts, cudaStream_t st, int skip_clean = 0,
+                                const SpecLaunch *sl = nullptr, cudaStream_t sweep_stream = nullptr);
 
 struct InvK {
     int w, h, bit_depth, matrix, fir, full_range, alpha, ybar;

@@ -564,8 +564,8 @@ h2y_status launch_inverse(h2y_ctx_impl *c, const InvK &k, const void *d_yuv, siz
         A.nwb = -(float)k.wb; A.nwr = -(float)k.wr; A.rwg = (float)(1.0 / k.wg);
         A.guard = 1.0f / (float)(1 << (21 - k.bit_depth));          // same bound as the forward kernel
         const long rows_per_worker = A.total_crows / ((long)c->sm_count * A.sub);
-        const char *force = getenv("H2Y_INVERSE_KERNEL");           // "tile" / "rows": tests and experiments
-        const bool want_rows = !k.ybar && (force ? force[0] == 'r' : rows_per_worker >= 48);     // -X: tile kernel only
+        // forced by tests and experiments (h2y_ctx_set_option); -X: tile kernel only
+        const bool want_rows = !k.ybar && (c->sw.inv_kernel ? c->sw.inv_kernel == 2 : rows_per_worker >= 48);
         if (want_rows) {
             int grid = c->sm_count;
             while (grid > 1 && A.total_crows / ((long)grid * A.sub) < 4) grid >>= 1;
@@ -584,7 +584,7 @@ h2y_status launch_inverse(h2y_ctx_impl *c, const InvK &k, const void *d_yuv, siz
         else LR(M, false, false);                                                                                          \
     } while (0)
             const bool cfg10 = k.matrix == H2Y_INV_2020 && k.bit_depth == 10 && !k.full_range && k.fir && !k.alpha &&
-                               !getenv("H2Y_NO_SPECIALISED");
+                               !c->sw.no_specialised;
             if (cfg10) {
                 H2Y_CUDA(c, cudaFuncSetAttribute(k_inverse_rows<1, true, false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 k_inverse_rows<1, true, false, 10><<<grid, RTHREADS, smem, st>>>(A);

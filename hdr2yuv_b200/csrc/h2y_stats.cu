@@ -9,6 +9,7 @@
 // and the fused forward kernel gathers from it.  Bit-exact by construction up to CUDA-vs-glibc
 // pow() last-ulp differences before the rounding to float.
 #include <cstdlib>
+#include <cstring>
 
 #include "h2y_internal.h"
 
@@ -149,9 +150,10 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
 template <bool HALF, int NCH>
 __global__ void __launch_bounds__(256, 4)
 k_stats_vec(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int clip_on, unsigned lo, unsigned hi,
-            unsigned *slots)
+            unsigned *slots, const int *mask)
 {
     typedef Pk<HALF> P;
+    if (mask && !mask[blockIdx.y]) return;       // behind a plan-reuse pass: only the frames it handed back
     const uint8_t *f = src + (size_t)blockIdx.y * frame_stride;
     unsigned mnv[3], mxv[3];        // per word kind (interleaved) or per plane (planar), two lanes each
     unsigned umn = 0xFFFFFFFFu, umx = 0u;   // half input: extrema of the RAW codes of the colour channels (packed)
@@ -384,12 +386,15 @@ k_stats_u16_planes(const uint16_t *__restrict__ p0, const uint16_t *__restrict__
 }
 
 // Turn extrema into estimated floor / ceiling, offset / range and LUT slots.  One block.
-__global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_float, int bit_depth, int is_half)
+// `mask` (behind a plan-reuse pass): frames with mask[frame] == 0 keep their FrameK and take no part in the slot search.
+__global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_float, int bit_depth, int is_half, const int *mask)
 {
     const int n = nframes * 3;
     for (int p = threadIdx.x; p < n; p += blockDim.x) {
+        if (mask && !mask[p / 3]) continue;
         FrameK &f = fk[p / 3];
         const int c = p % 3;
+        if (c == 0) f.spec_done = 0;
         unsigned kmin = slots[(p / 3) * SLOTS + c * 2], kmax = slots[(p / 3) * SLOTS + c * 2 + 1];
         int fl, ce;
         if (is_float) {
@@ -418,10 +423,12 @@ __global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_fl
     }
     __syncthreads();
     for (int p = threadIdx.x; p < n; p += blockDim.x) {
+        if (mask && !mask[p / 3]) continue;
         FrameK &f = fk[p / 3];
         const int c = p % 3;
         int slot = p;
         for (int q = 0; q < p; q++) {
+            if (mask && !mask[q / 3]) continue;
             const FrameK &g = fk[q / 3];
             if (g.est_floor[q % 3] == f.est_floor[c] && g.est_ceiling[q % 3] == f.est_ceiling[c]) { slot = q; break; }
         }
@@ -429,6 +436,7 @@ __global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_fl
     }
     __syncthreads();
     for (int fi = threadIdx.x; fi < nframes; fi += blockDim.x) {
+        if (mask && !mask[fi]) continue;
         FrameK &f = fk[fi];
         f.same_lut = f.lut_slot[0] == f.lut_slot[1] && f.lut_slot[0] == f.lut_slot[2];
         // "clean": half source whose raw codes are all below +inf's (finite, sign bit clear, so code order is
@@ -458,9 +466,11 @@ __global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_fl
 
 // grid = (256, nframes*3): LUT p is built only by its owner (lut_slot == p).
 __global__ void __launch_bounds__(256)
-k_build_lut(const FrameK *fk, float *luts, int is_half, int tf_lin, int tf_enc, int clip_on, unsigned lo, unsigned hi)
+k_build_lut(const FrameK *fk, float *luts, int is_half, int tf_lin, int tf_enc, int clip_on, unsigned lo, unsigned hi,
+            const int *mask)
 {
     const int p = blockIdx.y;
+    if (mask && !mask[p / 3]) return;
     const FrameK &f = fk[p / 3];
     const int c = p % 3;
     if (f.lut_slot[c] != p) return;
@@ -478,8 +488,11 @@ k_build_lut(const FrameK *fk, float *luts, int is_half, int tf_lin, int tf_enc, 
 
 // ---- launchers ---------------------------------------------------------------------------------
 
-h2y_status launch_stats_and_luts(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, const void *d_src,
-                                 size_t src_stride, int nframes, FrameK **d_framek, float **d_luts, cudaStream_t st)
+// `mask` != nullptr: behind a plan-reuse pass -- the slots of the masked frames were re-initialised by k_spec_verify,
+// the other frames keep what the SPEC kernel and the first k_plan produced
+static h2y_status stats_and_luts(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, const void *d_src,
+                                 size_t src_stride, int nframes, FrameK **d_framek, float **d_luts, cudaStream_t st,
+                                 const int *mask)
 {
     void *slots, *fk, *luts;
     h2y_status s;
@@ -488,7 +501,7 @@ h2y_status launch_stats_and_luts(h2y_ctx_impl *c, const h2y_forward_params &p, c
     if ((s = scratch_reserve(c, SCR_LUT, (size_t)nframes * 3 * 65536 * sizeof(float), &luts)) != H2Y_OK) return s;
     const long npix = (long)p.src.width * p.src.height;
     const int nslots = nframes * SLOTS;
-    k_stats_init<<<(nslots + 255) / 256, 256, 0, st>>>((unsigned *)slots, nslots);
+    if (!mask) k_stats_init<<<(nslots + 255) / 256, 256, 0, st>>>((unsigned *)slots, nslots);
     const int blocks = (int)(((npix + 2047) / 2048) < 4L * c->sm_count ? ((npix + 2047) / 2048) : 4L * c->sm_count);
     dim3 grid(blocks, nframes);
     const bool half = layout_is_half(p.src.layout);
@@ -499,30 +512,219 @@ h2y_status launch_stats_and_luts(h2y_ctx_impl *c, const h2y_forward_params &p, c
     if (vec) {
         // 2 CTAs of 256 threads per SM per frame row keeps ~16 KB in flight per SM
         // grid.x * 256 threads must be a multiple of 3 (see k_stats_vec, 3-channel case)
-        const char *egx = getenv("H2Y_STATS_GX");
-        const int gx = (egx ? atoi(egx) : (nframes >= 8 ? 2 * c->sm_count : 6 * c->sm_count)) / 3 * 3;
+        const int gx = (c->sw.stats_gx ? c->sw.stats_gx : (nframes >= 8 ? 2 * c->sm_count : 6 * c->sm_count)) / 3 * 3;
         dim3 vgrid(gx, nframes);
         if (half) {
-            if (nch == 3) k_stats_vec<true, 3><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, 0, 0, 0, sl);
-            else k_stats_vec<true, 4><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, 0, 0, 0, sl);
+            if (nch == 3) k_stats_vec<true, 3><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, 0, 0, 0, sl, mask);
+            else k_stats_vec<true, 4><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, 0, 0, 0, sl, mask);
         } else {
-            if (nch == 3) k_stats_vec<false, 3><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl);
-            else if (nch == 4) k_stats_vec<false, 4><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl);
-            else k_stats_vec<false, 0><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl);
+            if (nch == 3) k_stats_vec<false, 3><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl, mask);
+            else if (nch == 4) k_stats_vec<false, 4><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl, mask);
+            else k_stats_vec<false, 0><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl, mask);
         }
-    } else if (half)
+    } else if (mask)
+        return H2Y_ERR_UNSUPPORTED;      // the plan-reuse route only exists for vector-aligned frames
+    else if (half)
         k_stats_codes<true><<<grid, 256, 0, st>>>((const uint16_t *)d_src, src_stride / 2, p.src.layout, npix, 0, 0, 0,
                                                   (unsigned *)slots);
     else
         k_stats_codes<false><<<grid, 256, 0, st>>>((const uint16_t *)d_src, src_stride / 2, p.src.layout, npix,
                                                    k.clip_on_load, k.loadLo, k.loadHi, (unsigned *)slots);
-    k_plan<<<1, 256, 0, st>>>((const unsigned *)slots, (FrameK *)fk, nframes, half ? 1 : 0, p.src.bit_depth, half ? 1 : 0);
+    k_plan<<<1, 256, 0, st>>>((const unsigned *)slots, (FrameK *)fk, nframes, half ? 1 : 0, p.src.bit_depth, half ? 1 : 0, mask);
     k_build_lut<<<dim3(256, nframes * 3), 256, 0, st>>>((const FrameK *)fk, (float *)luts, half ? 1 : 0, k.tf_linearise,
-                                                         k.tf_encode, k.clip_on_load, k.loadLo, k.loadHi);
+                                                         k.tf_encode, k.clip_on_load, k.loadLo, k.loadHi, mask);
     c->launches += 4;
     H2Y_CUDA(c, cudaGetLastError());
     *d_framek = (FrameK *)fk;
     *d_luts = (float *)luts;
+    return H2Y_OK;
+}
+
+h2y_status launch_stats_and_luts(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, const void *d_src,
+                                 size_t src_stride, int nframes, FrameK **d_framek, float **d_luts, cudaStream_t st)
+{
+    return stats_and_luts(c, p, k, d_src, src_stride, nframes, d_framek, d_luts, st, nullptr);
+}
+
+// ---- plan reuse: the passes around the SPEC instantiations of the rows kernel (h2y_forward2.cu) -----------------------
+
+// device state of the context: SpecSeed | SpecCtl | predicted FrameK | seed LUT (65536 floats)
+h2y_status spec_dev(h2y_ctx_impl *c, SpecDev *out)
+{
+    const size_t bytes = 1024 + 65536 * sizeof(float);
+    if (!c->spec_dev) {
+        H2Y_CUDA(c, cudaMalloc(&c->spec_dev, bytes));
+        H2Y_CUDA(c, cudaMemset(c->spec_dev, 0, bytes));             // seed.valid = 0
+        H2Y_CUDA(c, cudaHostAlloc((void **)&c->spec_fb, sizeof(SpecCtl), cudaHostAllocDefault));
+        memset(c->spec_fb, 0, sizeof(SpecCtl));
+    }
+    uint8_t *b = (uint8_t *)c->spec_dev;
+    out->seed = (SpecSeed *)b;
+    out->ctl = (SpecCtl *)(b + 128);
+    out->pred = (FrameK *)(b + 256);
+    out->seed_lut = (float *)(b + 1024);
+    static_assert(sizeof(SpecSeed) <= 128 && sizeof(SpecCtl) <= 128 && sizeof(FrameK) <= 768, "layout of the plan-reuse block");
+    return H2Y_OK;
+}
+
+// Everything the SPEC kernel needs before it starts: the predicted FrameK (one for all frames), fresh statistics slots,
+// cleared per-frame flags, the control block.
+__global__ void k_spec_prepare(const SpecSeed *seed, SpecCtl *ctl, FrameK *pred, unsigned *slots, int *bail, int *flag,
+                               int nframes, int seq)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nframes * SLOTS) {
+        const int j = i % SLOTS;
+        slots[i] = j >= 8 ? 0xffffffffu : ((j & 1) ? 0u : 0xffffffffu);
+    }
+    if (i < nframes) { bail[i] = 0; flag[i] = 0; }
+    if (i == 0) {
+        ctl->skip = !seed->valid;
+        ctl->nflag = 0; ctl->mode = 0; ctl->nframes = nframes; ctl->seq = seq; ctl->uniform = 0;
+        FrameK f;
+        memset(&f, 0, sizeof(f));
+        for (int c = 0; c < 3; c++) {
+            f.est_floor[c] = seed->est_floor; f.est_ceiling[c] = seed->est_ceiling;
+            f.offset[c] = (float)seed->est_floor; f.range[c] = (float)(seed->est_ceiling - seed->est_floor);
+            f.lut_slot[c] = 0;                              // the seed LUT
+        }
+        f.same_lut = 1;
+        f.clean = seed->valid;
+        f.code_lo = seed->code_lo; f.code_hi = seed->code_hi;
+        f.lut2_ok = seed->valid && seed->lut2_ok;
+        *pred = f;
+    }
+}
+
+// Compare the plan k_plan derived from the gathered extrema with the predicted one.  A frame passes when the SPEC kernel
+// did not hand it back, it is a clean single-table frame, its (int) floor / ceiling are the predicted ones (so the seed
+// LUT is the function the reference applies, convert.cpp:1017-1019) and its codes lie inside the window the kernel had in
+// shared memory.  Frames that fail get fresh statistics slots: the classic pass recomputes them from the samples.
+__global__ void k_spec_verify(const FrameK *pred, FrameK *fk, const int *bail, int *flag, SpecCtl *ctl, unsigned *slots, int nframes)
+{
+    __shared__ int count;
+    if (threadIdx.x == 0) count = 0;
+    __syncthreads();
+    const FrameK &q = *pred;
+    for (int f = threadIdx.x; f < nframes; f += blockDim.x) {
+        FrameK &a = fk[f];
+        bool ok = !ctl->skip && !bail[f] && a.clean && a.same_lut && a.code_lo >= q.code_lo && a.code_hi <= q.code_hi;
+        for (int c = 0; c < 3; c++) ok = ok && a.est_floor[c] == q.est_floor[c] && a.est_ceiling[c] == q.est_ceiling[c];
+        flag[f] = !ok;
+        a.spec_done = ok;
+        if (!ok) {
+            atomicAdd(&count, 1);
+            for (int j = 0; j < SLOTS; j++) slots[f * SLOTS + j] = j >= 8 ? 0xffffffffu : ((j & 1) ? 0u : 0xffffffffu);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ctl->nflag = count;
+        // a few stragglers are cheapest through the general kernel (it spreads every frame over the whole GPU); a batch
+        // that mostly failed goes back to the rows kernels, whose row ranges cover all frames of the call
+        ctl->mode = count == 0 ? 0 : (count >= 10 && count * 4 >= nframes ? 2 : 1);
+    }
+}
+
+// After any call on the EXR rows route: the last frame's plan becomes the seed for the next call, with the window
+// widened to every half code that truncates into [floor, ceiling] (so that later frames with slightly different extrema
+// but the same (int) pair still pass), and the control block gets the numbers the host's policy reads (late).
+__global__ void k_seed_update(const FrameK *fk, const float *luts, SpecSeed *seed, float *seed_lut, SpecCtl *ctl, int nframes,
+                              int seq, int after_spec, int force)
+{
+    __shared__ int copy, uniform;
+    const FrameK &l = fk[nframes - 1];
+    if (threadIdx.x == 0) {
+        copy = 0; uniform = 0;
+        const bool single = l.clean && l.same_lut && l.est_floor[0] >= 0 && l.est_ceiling[0] > l.est_floor[0];
+        if (after_spec && l.spec_done) {
+            // confirmed against the seed: nothing changes
+        } else if (single) {
+            const unsigned lo = __half_as_ushort(__float2half_ru((float)l.est_floor[0]));
+            const unsigned top = __half_as_ushort(__float2half_ru((float)l.est_ceiling[0] + 1.0f));   // smallest half >= ceiling + 1
+            const unsigned hi = (top > 0x7C00u ? 0x7C00u : top) - 1u;
+            if (hi >= lo && hi < 0x7C00u && l.code_lo >= lo && l.code_hi <= hi) {
+                copy = force || !seed->valid || seed->est_floor != l.est_floor[0] || seed->est_ceiling != l.est_ceiling[0];
+                seed->valid = 1;
+                seed->est_floor = l.est_floor[0]; seed->est_ceiling = l.est_ceiling[0];
+                seed->code_lo = lo; seed->code_hi = hi;
+                seed->lut2_ok = hi < LUT2_CODES;
+            } else seed->valid = 0;
+        } else seed->valid = 0;
+    }
+    __syncthreads();
+    if (copy) {
+        const float *gl = luts + (size_t)l.lut_slot[0] * 65536;
+        for (unsigned c = threadIdx.x; c < 0x7C00u; c += blockDim.x) seed_lut[c] = gl[c];
+    }
+    if (!after_spec) {
+        // classic call: how many frames share the last frame's plan (what a plan-reuse pass would have confirmed)
+        int n = 0;
+        for (int f = threadIdx.x; f < nframes; f += blockDim.x) {
+            const FrameK &a = fk[f];
+            bool same = a.clean && a.same_lut;
+            for (int c = 0; c < 3; c++) same = same && a.est_floor[c] == l.est_floor[0] && a.est_ceiling[c] == l.est_ceiling[0];
+            n += same;
+        }
+        if (n) atomicAdd(&uniform, n);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ctl->skip = 0; ctl->mode = 0; ctl->nframes = nframes; ctl->seq = seq;
+            ctl->uniform = uniform; ctl->nflag = nframes - uniform;
+        }
+    }
+}
+
+h2y_status launch_spec_prepare(h2y_ctx_impl *c, int nframes, int seq, FrameK **d_framek, unsigned **d_slots, int **d_bail,
+                               int **d_flag, cudaStream_t st)
+{
+    SpecDev sd;
+    h2y_status s = spec_dev(c, &sd);
+    if (s != H2Y_OK) return s;
+    void *slots, *fl;
+    if ((s = scratch_reserve(c, SCR_STATS, (size_t)nframes * SLOTS * sizeof(unsigned), &slots)) != H2Y_OK) return s;
+    if ((s = scratch_reserve(c, SCR_SPEC, (size_t)nframes * 2 * sizeof(int), &fl)) != H2Y_OK) return s;
+    *d_slots = (unsigned *)slots;
+    *d_bail = (int *)fl;
+    *d_flag = (int *)fl + nframes;
+    *d_framek = sd.pred;
+    const int n = nframes * SLOTS;
+    k_spec_prepare<<<(n + 255) / 256, 256, 0, st>>>(sd.seed, sd.ctl, sd.pred, *d_slots, *d_bail, *d_flag, nframes, seq);
+    c->launches++;
+    H2Y_CUDA(c, cudaGetLastError());
+    return H2Y_OK;
+}
+
+// behind the SPEC kernel: plan from the gathered extrema, verify, then the classic statistics / plan / LUT pass for the
+// frames that were handed back (each kernel returns at once for the others)
+h2y_status launch_spec_verify_and_redo_prologue(h2y_ctx_impl *c, const h2y_forward_params &p, const PixK &k, const void *d_src,
+                                                size_t src_stride, int nframes, float **d_luts, cudaStream_t st)
+{
+    SpecDev sd;
+    h2y_status s = spec_dev(c, &sd);
+    if (s != H2Y_OK) return s;
+    void *fk;
+    if ((s = scratch_reserve(c, SCR_FRAMEK, (size_t)nframes * sizeof(FrameK), &fk)) != H2Y_OK) return s;
+    unsigned *slots = (unsigned *)c->scratch[SCR_STATS];
+    int *bail = (int *)c->scratch[SCR_SPEC], *flag = bail + nframes;
+    k_plan<<<1, 256, 0, st>>>(slots, (FrameK *)fk, nframes, 1, p.src.bit_depth, 1, nullptr);
+    k_spec_verify<<<1, 256, 0, st>>>(sd.pred, (FrameK *)fk, bail, flag, sd.ctl, slots, nframes);
+    c->launches += 2;
+    H2Y_CUDA(c, cudaGetLastError());
+    FrameK *dfk;
+    return stats_and_luts(c, p, k, d_src, src_stride, nframes, &dfk, d_luts, st, flag);
+}
+
+h2y_status launch_seed_update(h2y_ctx_impl *c, const FrameK *d_framek, const float *d_luts, int nframes, int seq,
+                              int after_spec, int force, cudaStream_t st)
+{
+    SpecDev sd;
+    h2y_status s = spec_dev(c, &sd);
+    if (s != H2Y_OK) return s;
+    k_seed_update<<<1, 256, 0, st>>>(d_framek, d_luts, sd.seed, sd.seed_lut, sd.ctl, nframes, seq, after_spec, force);
+    c->launches++;
+    H2Y_CUDA(c, cudaGetLastError());
+    H2Y_CUDA(c, cudaMemcpyAsync(c->spec_fb, sd.ctl, sizeof(SpecCtl), cudaMemcpyDeviceToHost, st));
     return H2Y_OK;
 }
 
@@ -545,7 +747,7 @@ h2y_status launch_stats_planar(h2y_ctx_impl *c, const h2y_pic_desc &pic, const v
     else
         k_stats_u16_planes<<<blocks, 256, 0, st>>>((const uint16_t *)d_planes[0], (const uint16_t *)d_planes[1],
                                                    (const uint16_t *)d_planes[2], n0, n12, (unsigned *)slots);
-    k_plan<<<1, 256, 0, st>>>((const unsigned *)slots, (FrameK *)fk, 1, isf ? 1 : 0, pic.bit_depth, 0);
+    k_plan<<<1, 256, 0, st>>>((const unsigned *)slots, (FrameK *)fk, 1, isf ? 1 : 0, pic.bit_depth, 0, nullptr);
     c->launches += 3;
     H2Y_CUDA(c, cudaGetLastError());
     *d_framek = (FrameK *)fk;

@@ -9,10 +9,13 @@ below are bookkeeping for timing only.
 
 
 def frame_range(rank, world, nframes):
-    """Contiguous range [lo, hi) of rank `rank`; sizes differ by at most one frame."""
-    base, extra = divmod(nframes, world)
-    lo = rank * base + min(rank, extra)
-    return lo, lo + base + (1 if rank < extra else 0)
+    """Contiguous range [lo, hi) of rank `rank`; sizes differ by at most one frame.  The formula lives in the C-ABI
+    (h2y_frame_range), which the CLI's --devices workers use as well."""
+    import ctypes as C
+    from ._cabi import check, lib
+    lo, hi = C.c_int(0), C.c_int(0)
+    check(lib().h2y_frame_range(int(rank), int(world), int(nframes), C.byref(lo), C.byref(hi)), "h2y_frame_range")
+    return lo.value, hi.value
 
 
 def output_offset(frame, frame_bytes):

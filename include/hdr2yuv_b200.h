@@ -33,7 +33,7 @@ typedef enum h2y_status {
                                  (convert.cpp:886-890), non-U16 pictures to convert (523-528) */
     H2Y_ERR_MATRIX = 2,       /* "Can't determine color difference to use?" (convert.cpp:1195-1198) */
     H2Y_ERR_BIT_DEPTH = 3,    /* dst bit depth > src bit depth in write_yuv (tiff.cpp:396-401) */
-    H2Y_ERR_UNSUPPORTED = 4,  /* option the reference has (Y'u''v'', -X) that this path does not implement */
+    H2Y_ERR_UNSUPPORTED = 4,  /* a combination the reference accepts that this path does not serve */
     H2Y_ERR_ARG = 5,          /* NULL pointer, bad geometry, unknown enum value */
     H2Y_ERR_CUDA = 6,         /* a CUDA runtime call failed; see h2y_last_cuda_error */
     H2Y_ERR_NOMEM = 7
@@ -111,6 +111,21 @@ void *h2y_host_alloc(size_t bytes);                       /* pinned host memory 
 void h2y_host_free(void *p);
 uint64_t h2y_kernel_launches(const h2y_ctx *ctx);         /* kernels this context has launched so far */
 
+/* Threading and streams.  A context owns one set of scratch buffers (statistics, per-frame plans, LUTs, intermediate
+ * planes), so it serves ONE call at a time: use it from one host thread at a time, and one context per thread that
+ * wants to work concurrently.  Calls are asynchronous on the caller's stream; a call that arrives on a different stream
+ * than the previous one first waits, on the device, for that previous call's work (an event), so streams may be mixed
+ * safely but do not overlap within a context.  Growing a scratch buffer synchronises the device.  Every entry point
+ * switches to the context's device and restores the caller's current device before it returns. */
+
+/* Test and experiment switches.  The library reads the environment exactly once, in h2y_ctx_create; afterwards the
+ * switches belong to the context and are changed with this call (tests force each kernel of a route this way).
+ * Names: "H2Y_FORWARD_KERNEL" = "ring" | "rows" | "", "H2Y_INVERSE_KERNEL" = "tile" | "rows" | "", "H2Y_FORCE_STAGED",
+ * "H2Y_FORCE_V1", "H2Y_NO_SPECIALISED", "H2Y_EXACT_MATH" = "1" | "0", "H2Y_STATS_GX" = n, "H2Y_PLAN_REUSE" = "0" never,
+ * "1" whenever a previous plan exists, "" automatic (see h2y_forward).  name == NULL restores the defaults of
+ * h2y_ctx_create.  Unknown names return H2Y_ERR_ARG. */
+h2y_status h2y_ctx_set_option(h2y_ctx *ctx, const char *name, const char *value);
+
 /* Profiling hooks for bench.py: when enabled, h2y_forward / h2y_inverse bracket their kernels with
  * CUDA events on the caller's stream.  h2y_profile_last_ms waits for the bracketed calls made since
  * h2y_profile_enable (the 16 most recent) and returns the AVERAGE duration of their dominant kernel
@@ -126,6 +141,11 @@ h2y_status h2y_set_pic_clip(int bit_depth, int video_full_range_flag, h2y_clip_l
 h2y_status h2y_plane_dims(int width, int height, int chroma_format_idc, int plane_w[3], int plane_h[3]);
 size_t h2y_src_frame_bytes(const h2y_pic_desc *src);      /* bytes of one source frame in its layout */
 size_t h2y_yuv_frame_bytes(int width, int height, int chroma_format_idc); /* one .yuv frame: Y,Cb,Cr u16 */
+/* Frame-range sharding (frames are independent: pic_stats is per frame, common.cpp:66; n_frames is unused,
+ * hdr2yuv.cpp:157-160): worker `rank` of `world` converts frames [*lo, *hi) of `nframes`, contiguous, sizes differing
+ * by at most one.  The one partition formula of the repo: the CLI's --devices threads, bench.py's ranks and
+ * hdr2yuv_b200/sharding.py all call it. */
+h2y_status h2y_frame_range(int rank, int world, int nframes, int *lo, int *hi);
 /* tmp picture bit depth rule of main(), hdr2yuv.cpp:803-808 (destination of a .yuv is U16) */
 int h2y_tmp_bit_depth(const h2y_pic_desc *src, const h2y_pic_desc *dst);
 
@@ -194,7 +214,16 @@ typedef struct h2y_forward_params {
 /* pic_stats -> matrix_convert -> convert -> write_yuv clamp (hdr2yuv.cpp:797-928) for `nframes`
  * independent frames resident in HBM.  Frame i is read at d_src + i*src_stride_bytes in
  * params->src.layout and written at d_dst + i*dst_stride_bytes as one .yuv frame (Y, Cb, Cr
- * planes of u16, h2y_yuv_frame_bytes).  Asynchronous on `stream`. */
+ * planes of u16, h2y_yuv_frame_bytes).  Asynchronous on `stream`.
+ *
+ * Plan reuse (large batches of half-float frames on the compiled-in BT.2020 10/12-bit configurations).  pic_stats
+ * needs a frame's extrema before its first pixel is converted (common.cpp:66-168 -> convert.cpp:936-940), i.e. a
+ * second pass over the input.  Frames of a sequence usually truncate to the same (int) floor / ceiling, so a call may
+ * convert every frame with the plan of the previous call's last frame while gathering the frame's own extrema from the
+ * samples it loads anyway; a verify step on the device then compares plans and the frames that differ are converted
+ * again the classic way inside the same call.  The output is the reference's in every case; only the time differs.  The
+ * library decides per call from the outcome of earlier calls (never waiting for the GPU); "H2Y_PLAN_REUSE" = "0" / "1"
+ * (h2y_ctx_set_option) switches it off / forces it. */
 h2y_status h2y_forward(h2y_ctx *ctx, const h2y_forward_params *params, const void *d_src, size_t src_stride_bytes,
                        void *d_dst, size_t dst_stride_bytes, int nframes, void *stream);
 
@@ -203,9 +232,16 @@ h2y_status h2y_forward(h2y_ctx *ctx, const h2y_forward_params *params, const voi
 h2y_status h2y_forward_host(h2y_ctx *ctx, const h2y_forward_params *params, const void *h_src,
                             size_t src_stride_bytes, void *h_dst, size_t dst_stride_bytes, int nframes);
 
-/* The per-frame statistics the last h2y_forward / h2y_forward_host call derived (frame index in
- * that call).  Synchronises the stream used. Only meaningful when the transfer changed. */
+/* The per-frame statistics the last h2y_forward call derived (frame index in that call).  Synchronises the stream
+ * used.  Only meaningful when the transfer changed.  The plans live in scratch that every 256-frame group of a call
+ * and every chunk of h2y_forward_host's pipeline overwrites: after a call that spanned several groups or chunks this
+ * returns H2Y_ERR_UNSUPPORTED.  i_min / i_max are filled for integer sources only (0 for half / float sources). */
 h2y_status h2y_forward_last_stats(h2y_ctx *ctx, int frame, h2y_pic_stats_t *out);
+
+/* What the last 256-frame group of the last h2y_forward call did about plan reuse: *attempted = 1 when it took the
+ * single-pass route, *nframes = frames in the group, *nredone = frames the verify step handed back to the classic
+ * kernels (0 when every prediction held).  Synchronises the stream used.  Any pointer may be NULL. */
+h2y_status h2y_forward_last_plan_reuse(h2y_ctx *ctx, int *attempted, int *nframes, int *nredone);
 
 /* ---- inverse path: one loop iteration of yuv2tiff's main() (yuv2tiff.cpp:278-552) --------- */
 enum { H2Y_INV_YDzDx = 0, H2Y_INV_709 = 1, H2Y_INV_2020 = 2, H2Y_INV_Y100 = 3, H2Y_INV_Y500 = 4 };

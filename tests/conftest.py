@@ -46,3 +46,12 @@ def ctx(built_lib):
     c = api.Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture
+def opt(ctx):
+    """Set test switches of the shared context (h2y_ctx_set_option); the defaults come back after the test."""
+    def set_option(name, value):
+        ctx.set_option(name, value)
+    yield set_option
+    ctx.set_option(None)

@@ -28,20 +28,16 @@ def test_fused_forward_matches_golden(ctx, golden_forward, name, src, dst):
 
 
 @pytest.mark.parametrize("name,src,dst", cases.FORWARD_CASES[::3], ids=[c[0] for c in cases.FORWARD_CASES[::3]])
-def test_exact_math_and_staged_routes_agree(ctx, golden_forward, name, src, dst):
+def test_exact_math_and_staged_routes_agree(ctx, opt, golden_forward, name, src, dst):
     # the reciprocal fast path, the reference-order FP64 path and the staged kernels give the same codes
     px = golden_forward[name + "/in"]
     fast = G.gpu_forward(ctx, [px], src, dst)[0]
-    os.environ["H2Y_EXACT_MATH"] = "1"
-    try:
-        exact = G.gpu_forward(ctx, [px], src, dst)[0]
-    finally:
-        del os.environ["H2Y_EXACT_MATH"]
-    os.environ["H2Y_FORCE_STAGED"] = "1"
-    try:
-        staged = G.gpu_forward(ctx, [px], src, dst)[0]
-    finally:
-        del os.environ["H2Y_FORCE_STAGED"]
+    opt("H2Y_EXACT_MATH", "1")
+    exact = G.gpu_forward(ctx, [px], src, dst)[0]
+    opt("H2Y_EXACT_MATH", "0")
+    opt("H2Y_FORCE_STAGED", "1")
+    staged = G.gpu_forward(ctx, [px], src, dst)[0]
+    opt("H2Y_FORCE_STAGED", "0")
     assert np.array_equal(fast, exact)
     G.compare_codes(staged, fast, _uses_transfer(src, dst), name + " staged-vs-fused")
 
@@ -203,18 +199,18 @@ def test_error_convention(ctx):
 
 
 # ---- the two EXR-route kernels (h2y_forward2.cu) --------------------------------------------------------
-def _force_kernel(monkeypatch, which):
+def _force_kernel(opt, which):
     if which:
-        monkeypatch.setenv("H2Y_FORWARD_KERNEL", which)
+        opt("H2Y_FORWARD_KERNEL", which)
     else:
-        monkeypatch.delenv("H2Y_FORWARD_KERNEL", raising=False)
+        opt("H2Y_FORWARD_KERNEL", "")
 
 
 @pytest.mark.parametrize("which", ["ring", "rows", None])
 @pytest.mark.parametrize("matrix,depth,full", [(9, 10, 0), (9, 12, 0), (11, 10, 0), (1, 10, 0), (9, 10, 1), (11, 12, 1)])
-def test_exr_kernels_match_oracle(ctx, monkeypatch, which, matrix, depth, full):
+def test_exr_kernels_match_oracle(ctx, opt, which, matrix, depth, full):
     # widths that are and are not multiples of the 240-px strip, several frames per batch, RGB and RGBA
-    _force_kernel(monkeypatch, which)
+    _force_kernel(opt, which)
     for (w, h, ch) in ((240, 66, 3), (488, 130, 4), (1000, 34, 3)):
         dst = dict(bit_depth=depth, full_range=full, transfer=16, primaries=9, matrix=matrix, chroma=1, resampler=1)
         frames = [synth.exr_half_frame(w, h, seed=100 + s, channels=ch) for s in range(3)]
@@ -223,7 +219,7 @@ def test_exr_kernels_match_oracle(ctx, monkeypatch, which, matrix, depth, full):
             G.compare_codes(g, G.oracle_forward(f, _HALF, dst), True, "%s %dx%d m%d b%d" % (which, w, h, matrix, depth))
 
 
-def test_large_4k_batch_takes_rows_kernel_and_matches_oracle(ctx):
+def test_large_4k_batch_takes_rows_kernel_and_matches_oracle(ctx, opt):
     # 10 frames of 3840x2160: the batch size at which h2y_forward picks the warp-autonomous kernel by itself.
     # Every frame is checked through a checksum of the two oracle-verified frames' neighbours: frames repeat
     # with period 2, so frames 0 and 1 (oracle) pin all ten.
@@ -231,6 +227,7 @@ def test_large_4k_batch_takes_rows_kernel_and_matches_oracle(ctx):
     dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
     base = [synth.exr_half_frame_fast(w, h, seed=s, channels=3) for s in (0, 1)]
     frames = [base[i % 2] for i in range(n)]
+    opt("H2Y_PLAN_REUSE", "0")          # the classic two-pass route (tests/test_plan_reuse_gpu.py covers the single pass)
     before = ctx.kernel_launches
     got = G.gpu_forward(ctx, frames, _HALF, dst)
     # init, stats, plan, LUT, rows kernel (two-LUT, single-LUT and the two three-table instantiations), general-kernel sweep
@@ -241,29 +238,29 @@ def test_large_4k_batch_takes_rows_kernel_and_matches_oracle(ctx):
         assert np.array_equal(got[i], got[i % 2]), i
 
 
-def test_rows_kernel_splits_frames_by_lut_fit(ctx, monkeypatch):
+def test_rows_kernel_splits_frames_by_lut_fit(ctx, opt):
     # frames whose largest sample is above ~10 800 (half code >= LUT2_CODES) cannot keep two pre-scaled LUT copies in
     # shared memory: they go to the single-LUT instantiation, the others to the two-LUT one, in the same call
-    monkeypatch.setenv("H2Y_FORWARD_KERNEL", "rows")
+    opt("H2Y_FORWARD_KERNEL", "rows")
     w, h = 480, 128
     dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
     frames = [synth.exr_half_frame(w, h, seed=60 + s, channels=3, hi=hi) for s, hi in enumerate((4000.0, 40000.0, 900.0, 60000.0))]
     got = G.gpu_forward(ctx, frames, _HALF, dst)
     for i, f in enumerate(frames):
         G.compare_codes(got[i], G.oracle_forward(f, _HALF, dst), True, "frame %d" % i)
-    monkeypatch.setenv("H2Y_NO_SPECIALISED", "1")         # and the generic (run-time constants) instantiation agrees
+    opt("H2Y_NO_SPECIALISED", "1")         # and the generic (run-time constants) instantiation agrees
     again = G.gpu_forward(ctx, frames, _HALF, dst)
     for a, b in zip(got, again):
         assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("depth", [10, 12])
-def test_rows_kernel_keeps_the_clamp_when_a_frame_can_reach_it(ctx, monkeypatch, depth):
+def test_rows_kernel_keeps_the_clamp_when_a_frame_can_reach_it(ctx, opt, depth):
     # The two-LUT instantiation drops matrix_convert's chroma clamp only for frames whose LUT extremes prove it cannot
     # bind.  A frame with max in [1, 2) has range (int)max - (int)min = 1, so its normalised samples reach ~1.9 and the
     # PQ values ~1.07: such frames must take the single-LUT instantiation (clamp kept) inside the same call, next to
     # ordinary frames that take the clamp-free one.  Saturated primaries make the clamp actually bind.
-    monkeypatch.setenv("H2Y_FORWARD_KERNEL", "rows")
+    opt("H2Y_FORWARD_KERNEL", "rows")
     w, h = 480, 128
     dst = dict(bit_depth=depth, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
     frames = [synth.exr_half_frame(w, h, seed=80 + s, channels=3, hi=hi) for s, hi in enumerate((1.9, 4000.0, 1.02, 1.5, 3.7))]
@@ -279,10 +276,10 @@ def test_rows_kernel_keeps_the_clamp_when_a_frame_can_reach_it(ctx, monkeypatch,
 
 
 @pytest.mark.parametrize("which", ["ring", "rows"])
-def test_unclean_frames_fall_back_to_the_general_kernel(ctx, monkeypatch, which):
+def test_unclean_frames_fall_back_to_the_general_kernel(ctx, opt, which):
     # negative zero, +inf and a different (floor, ceiling) per frame: frames 1 and 2 are not "clean" and must come
     # out of the v1 kernel, bit-identical to what the oracle gives; frames 0 and 3 stay on the fast kernel
-    _force_kernel(monkeypatch, which)
+    _force_kernel(opt, which)
     w, h = 256, 64
     dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
     frames = [synth.exr_half_frame(w, h, seed=40 + s, channels=3, hi=1000.0 * (s + 1)) for s in range(4)]
@@ -292,15 +289,15 @@ def test_unclean_frames_fall_back_to_the_general_kernel(ctx, monkeypatch, which)
     for i in (0, 1, 3):
         G.compare_codes(got[i], G.oracle_forward(frames[i], _HALF, dst), True, "frame %d" % i)
     # +inf makes the reference's own range (int)inf - floor overflow: only require that the fast kernel declined it
-    monkeypatch.setenv("H2Y_FORCE_V1", "1")
+    opt("H2Y_FORCE_V1", "1")
     ref2 = G.gpu_forward(ctx, [frames[2]], _HALF, dst)[0]
     assert np.array_equal(got[2], ref2)
 
 
 @pytest.mark.parametrize("which", ["ring", "rows"])
-def test_wide_and_short_pictures(ctx, monkeypatch, which):
+def test_wide_and_short_pictures(ctx, opt, which):
     # more strips than warps (8K: 32 strips of 240), two-row pictures, a single 8-pixel column
-    _force_kernel(monkeypatch, which)
+    _force_kernel(opt, which)
     dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
     for (w, h, n) in ((7680, 36, 2), (8, 2, 3), (8, 130, 1), (3848, 2, 2)):
         frames = [synth.exr_half_frame(w, h, seed=200 + s, channels=3) for s in range(n)]
@@ -342,11 +339,11 @@ def test_dpx10_layout_unpacks_on_the_gpu_and_matches_oracle(ctx, big_endian):
 
 @pytest.mark.parametrize("which", ["ring", "rows"])
 @pytest.mark.parametrize("matrix,depth,full,channels", [(9, 10, 0, 3), (11, 10, 0, 3), (9, 12, 0, 4), (9, 16, 0, 3), (11, 12, 1, 4), (9, 10, 1, 3)])
-def test_tiff_420_kernels_match_oracle(ctx, monkeypatch, which, matrix, depth, full, channels):
+def test_tiff_420_kernels_match_oracle(ctx, opt, which, matrix, depth, full, channels):
     # the two kernels behind the integer 4:2:0 FIR route (CTA ring / warp-autonomous with a private row ring), forced in
     # turn; 16-bit tmp depth, reference operation order in both filters -> bit exact.  Widths that are and are not
     # multiples of the 240-pixel strip, several frames so that row ranges cross frame boundaries, RGB and RGBA rows.
-    _force_kernel(monkeypatch, which)
+    _force_kernel(opt, which)
     src = dict(_TIFF, full_range=full)
     for (w, h) in ((240, 66), (488, 130), (1000, 34), (8, 2), (3848, 4)):
         dst = dict(bit_depth=depth, full_range=full, transfer=16, primaries=9, matrix=matrix, chroma=1, resampler=1)
@@ -372,12 +369,12 @@ def test_large_1080p_tiff_batch_takes_rows_kernel_and_matches_oracle(ctx):
 
 
 @pytest.mark.parametrize("depth,matrix", [(10, 9), (12, 9), (10, 11), (10, 1)])
-def test_rows_kernel_three_table_frames(ctx, monkeypatch, depth, matrix):
+def test_rows_kernel_three_table_frames(ctx, opt, depth, matrix):
     # Real footage: the channels' (int)min / (int)max differ, so the reference normalises each channel on its own
     # (common.cpp:135-136, convert.cpp:936-940) and a frame needs three transfer tables.  The rows kernel keeps three
     # range-restricted tables in shared memory when they fit (FrameK::clean3); other frames of the same call still go
     # to the single-table instantiations or, when nothing fits, to the general kernel.
-    monkeypatch.setenv("H2Y_FORWARD_KERNEL", "rows")
+    opt("H2Y_FORWARD_KERNEL", "rows")
     w, h = 480, 130
     dst = dict(bit_depth=depth, full_range=0, transfer=16, primaries=9, matrix=matrix, chroma=1, resampler=1)
     rng = np.random.default_rng(7)
@@ -414,13 +411,13 @@ def test_rows_kernel_three_table_frames(ctx, monkeypatch, depth, matrix):
 
 
 @pytest.mark.gpu
-def test_stream_order_behind_the_overlapped_rows_launches(ctx, monkeypatch):
-    # The rows-kernel instantiations of one call are launched so that each may start while its predecessor drains
-    # (programmatic dependent launch).  Work queued behind h2y_forward on the same stream must still see every frame
+def test_stream_order_behind_the_overlapped_rows_launches(ctx, opt):
+    # The rows-kernel instantiations of one call run on forked streams (each may start while its predecessor drains) and
+    # are joined to the caller's stream by events.  Work queued behind h2y_forward on the same stream must still see every frame
     # converted: a device-to-host copy queued on that stream right after the call, with no device-wide synchronise in
     # between, has to return the same bytes as a synchronised run.  Single-table frames are converted by the FIRST
     # launch (the long one, the later launches find nothing to do), three-table frames by the last ones.
-    monkeypatch.setenv("H2Y_FORWARD_KERNEL", "rows")
+    opt("H2Y_FORWARD_KERNEL", "rows")
     w, h, n = 1920, 1080, 12
     dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
     single = synth.exr_half_frame_fast(w, h, seed=3, channels=3)
@@ -444,11 +441,11 @@ def test_stream_order_behind_the_overlapped_rows_launches(ctx, monkeypatch):
 
 
 @pytest.mark.gpu
-def test_host_pipeline_with_the_rows_kernels(ctx, monkeypatch):
+def test_host_pipeline_with_the_rows_kernels(ctx, opt):
     # h2y_forward_host with the warp-autonomous kernels forced: per chunk the compute stream runs the overlapped rows
     # launches and the general-kernel sweep, records an event, and the copy stream drains the chunk behind that event.
     # Single-table and three-table frames alternate, so both the first and the last launch of a call do real work.
-    monkeypatch.setenv("H2Y_FORWARD_KERNEL", "rows")
+    opt("H2Y_FORWARD_KERNEL", "rows")
     w, h, n = 1920, 1080, 20
     dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
     base = [synth.exr_half_frame_fast(w, h, seed=11, channels=3), synth.exr_half_frame_smooth_fast(w, h, seed=12)]

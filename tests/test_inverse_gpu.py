@@ -29,8 +29,8 @@ def gpu_inverse(ctx, yuvs, w, h, bd, m, fir, fr, al, ybar=0):
 
 @pytest.mark.parametrize("kernel", ["tile", "rows"])
 @pytest.mark.parametrize("case", cases.INVERSE_CASES, ids=lambda c: "b%d_m%d_fir%d_fr%d_a%d" % c)
-def test_inverse_matches_golden(ctx, golden_inverse, case, kernel, monkeypatch):
-    monkeypatch.setenv("H2Y_INVERSE_KERNEL", kernel)          # both kernels behind h2y_inverse
+def test_inverse_matches_golden(ctx, golden_inverse, case, kernel, opt):
+    opt("H2Y_INVERSE_KERNEL", kernel)          # both kernels behind h2y_inverse
     bd, m, fir, fr, al = case
     yuv = cases.widen_yuv(golden_inverse[cases.inverse_input_key(m)], bd)
     rgb, inv = gpu_inverse(ctx, [yuv], cases.IW, cases.IH, bd, m, fir, fr, al)
@@ -42,12 +42,12 @@ def test_inverse_matches_golden(ctx, golden_inverse, case, kernel, monkeypatch):
 
 @pytest.mark.parametrize("kernel", ["tile", "rows"])
 @pytest.mark.parametrize("bd,fir,fr,al", [(12, 1, 0, 0), (10, 0, 0, 1), (14, 1, 1, 0)])
-def test_ybar_mode_matches_oracle(ctx, kernel, bd, fir, fr, al, monkeypatch):
+def test_ybar_mode_matches_oracle(ctx, kernel, bd, fir, fr, al, opt):
     # yuv2tiff -X (yuv2tiff.cpp:365-399): Y'DzDx rebuilt around the 2x2 luma mean.  The oracle's restatement is pinned
     # against the reference binary in test_oracle_cpu.  Random luma next to mid-range chroma produces many negative
     # (invalid) pixels and values above Full-1.5, so every branch of the mode is taken.  A forced "rows" request still
     # runs the tile kernel (the only one with this mode); with a 709 matrix the flag is inert, as in the reference.
-    monkeypatch.setenv("H2Y_INVERSE_KERNEL", kernel)
+    opt("H2Y_INVERSE_KERNEL", kernel)
     w, h = 264, 70
     rng = np.random.default_rng(bd)
     top = (1 << bd) - 1
@@ -75,8 +75,8 @@ def _yuv_for(w, h, seed, bd, matrix_fwd):
 
 @pytest.mark.parametrize("kernel", ["tile", "rows"])
 @pytest.mark.parametrize("w,h", [(8, 2), (128, 16), (136, 34), (1000, 250), (1920, 1080), (3840, 2160)])
-def test_inverse_sizes_vs_oracle(ctx, w, h, kernel, monkeypatch):
-    monkeypatch.setenv("H2Y_INVERSE_KERNEL", kernel)
+def test_inverse_sizes_vs_oracle(ctx, w, h, kernel, opt):
+    opt("H2Y_INVERSE_KERNEL", kernel)
     big = w * h > 1 << 20
     for bd, m, m_fwd in ((10, O.INV_2020, 9), (12, O.INV_YDZDX, 11), (10, O.INV_709, 1), (12, O.INV_Y100, 13)):
         if big and m not in (O.INV_2020, O.INV_YDZDX):
@@ -203,8 +203,8 @@ def test_empty_batches_are_no_ops(ctx):
 
 
 @pytest.mark.parametrize("kernel", ["tile", "rows"])
-def test_inverse_wide_and_short_pictures(ctx, kernel, monkeypatch):
-    monkeypatch.setenv("H2Y_INVERSE_KERNEL", kernel)
+def test_inverse_wide_and_short_pictures(ctx, kernel, opt):
+    opt("H2Y_INVERSE_KERNEL", kernel)
     for (w, h) in ((7680, 36), (8, 2), (8, 130), (3848, 4)):
         yuvs = [_yuv_for(w, h, 300 + s, 10, 9) for s in range(2)]
         rgb, inv = gpu_inverse(ctx, yuvs, w, h, 10, O.INV_2020, 1, 0, 0)
