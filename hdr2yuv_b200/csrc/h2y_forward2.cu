@@ -660,13 +660,33 @@ struct Fwd3Args {
     unsigned *slots;
 };
 
-constexpr int THREADS3 = 512, WARPS3 = THREADS3 / 32;     // 16 warps (12 x 168 registers measured 6 % slower: latency hiding wins)
+constexpr int THREADS3 = 512, WARPS3 = THREADS3 / 32;
+// SPEC instantiations: the warps' code bounds sit behind the LUT copy (24 bytes per warp)
+constexpr unsigned SPEC_BOUNDS_BYTES = 24 * 16;
+template <bool TWO> __device__ __host__ constexpr unsigned spec_bounds_offset() { return (TWO ? 2u * LUT2_CODES : (unsigned)LUT_MAX_CODES) * 4u; }
+     // 16 warps (12 x 168 registers measured 6 % slower: latency hiding wins)
 
 // THREE: the instantiation for frames whose channels need a table each (FrameK::clean3); with TWO as well: the
 // clamp-free chroma path on those three tables (frames that three_nc_frame() accepts)
 // packed 16-bit min / max (ptxas fuses two of them into one VIMNMX3.U16x2)
 __device__ __forceinline__ unsigned vmin2(unsigned a, unsigned b) { unsigned r; asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ unsigned vmax2(unsigned a, unsigned b) { unsigned r; asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+
+// maximum / minimum over the warp of both 16-bit halves (REDUX: the result is warp-uniform)
+__device__ __forceinline__ unsigned warp_max_u16x2(unsigned v)
+{
+    return __reduce_max_sync(0xffffffffu, v & 0xffffu) | (__reduce_max_sync(0xffffffffu, v >> 16) << 16);
+}
+__device__ __forceinline__ unsigned warp_min_u16x2(unsigned v)
+{
+    return __reduce_min_sync(0xffffffffu, v & 0xffffu) | (__reduce_min_sync(0xffffffffu, v >> 16) << 16);
+}
+
+// one {max, min} pair of the warp's code bounds, re-read from shared memory every row (volatile: not kept in registers)
+__device__ __forceinline__ void lds_bounds(unsigned addr, unsigned &mx, unsigned &mn)
+{
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(mx), "=r"(mn) : "r"(addr));
+}
 
 // order-preserving key of a finite non-negative half code, as k_stats_vec / k_plan use it (h2y_stats.cu: fkey)
 __device__ __forceinline__ unsigned half_code_key(unsigned code) { return __float_as_uint(half_bits_to_float(code)) | 0x80000000u; }
@@ -788,8 +808,17 @@ __device__ __forceinline__ void rows_body(const Fwd3Args &A)
             for (int i = 0; i < 6; i++)
 #pragma unroll
                 for (int c = 0; c < 4; c++) acc[i][c] = 0ull;
-            // SPEC: running extrema of the raw codes per word kind, (R,G) (B,R) (G,B) for RGB rows, (R,G) (B,A) for RGBA
-            unsigned smn0 = 0xFFFFFFFFu, smn1 = 0xFFFFFFFFu, smn2 = 0xFFFFFFFFu, smx0 = 0u, smx1 = 0u, smx2 = 0u;
+            // SPEC: extrema of the raw codes seen so far by the WARP, per word kind: (R,G) (B,R) (G,B) for RGB rows, (R,G)
+            // (B,A) for RGBA, as {max, min} pairs in 24 bytes of shared memory behind the LUT (spec_bounds).  A lane-private
+            // running min / max would need six more registers in a loop that has none to spare, and with 232 KB of the SM
+            // carved out as shared memory the spills that follow go to L2 (measured: 1.10 -> 1.69 ms).  The bounds are read
+            // back every row (three broadcast loads) and only written when a row moves them.
+            volatile uint2 *sb = reinterpret_cast<volatile uint2 *>(smem_raw + spec_bounds_offset<TWO>()) + 3 * warp;
+            const unsigned sb_sa = (unsigned)__cvta_generic_to_shared(const_cast<uint2 *>(sb));
+            if (SPEC) {
+                if (lane < 3) { sb[lane].x = 0u; sb[lane].y = 0xFFFFFFFFu; }
+                __syncwarp();
+            }
             // no code may index past the LUT copy in shared memory; codes inside it but outside the predicted window read
             // stale entries, which the verify step catches through the gathered extrema (the frame is converted again)
             constexpr unsigned SPEC_CAP2 = ((TWO ? LUT2_CODES : (unsigned)LUT_MAX_CODES) - 1u) * 0x10001u;
@@ -907,24 +936,44 @@ __device__ __forceinline__ void rows_body(const Fwd3Args &A)
                 row_split(cur, g, b, rr);
 #else
                 if (SPEC) {
-                    // this row's codes join the running extrema (halo rows and halo lanes count twice: harmless), and no
-                    // code above the predicted window may reach the gathers: the whole frame is handed back instead
+                    // A row costs two 3-input min / max per word kind (the warp's bound is one of the inputs) and one
+                    // vote: does any lane hold a code outside the bounds?  Rarely (a running extremum of n rows moves
+                    // O(log n) times); then the bounds are widened by warp reductions.  Halo rows and halo lanes are
+                    // counted twice: harmless.  No code above the predicted window may reach the gathers: the whole frame
+                    // is handed back instead.
+                    unsigned smx0, smn0, smx1, smn1, smx2 = 0u, smn2 = 0xFFFFFFFFu;
+                    lds_bounds(sb_sa, smx0, smn0); lds_bounds(sb_sa + 8, smx1, smn1);
+                    if (NCH == 3) lds_bounds(sb_sa + 16, smx2, smn2);
+                    unsigned rx0, rx1, rx2 = 0u, rn0, rn1, rn2 = 0xFFFFFFFFu;
                     if (NCH == 3) {
-                        smn0 = vmin2(vmin2(smn0, raw.v[0].x), vmin2(raw.v[0].w, vmin2(raw.v[1].z, raw.v[2].y)));
-                        smn1 = vmin2(vmin2(smn1, raw.v[0].y), vmin2(raw.v[1].x, vmin2(raw.v[1].w, raw.v[2].z)));
-                        smn2 = vmin2(vmin2(smn2, raw.v[0].z), vmin2(raw.v[1].y, vmin2(raw.v[2].x, raw.v[2].w)));
-                        smx0 = vmax2(vmax2(smx0, raw.v[0].x), vmax2(raw.v[0].w, vmax2(raw.v[1].z, raw.v[2].y)));
-                        smx1 = vmax2(vmax2(smx1, raw.v[0].y), vmax2(raw.v[1].x, vmax2(raw.v[1].w, raw.v[2].z)));
-                        smx2 = vmax2(vmax2(smx2, raw.v[0].z), vmax2(raw.v[1].y, vmax2(raw.v[2].x, raw.v[2].w)));
+                        rn0 = vmin2(vmin2(smn0, raw.v[0].x), vmin2(raw.v[0].w, vmin2(raw.v[1].z, raw.v[2].y)));
+                        rn1 = vmin2(vmin2(smn1, raw.v[0].y), vmin2(raw.v[1].x, vmin2(raw.v[1].w, raw.v[2].z)));
+                        rn2 = vmin2(vmin2(smn2, raw.v[0].z), vmin2(raw.v[1].y, vmin2(raw.v[2].x, raw.v[2].w)));
+                        rx0 = vmax2(vmax2(smx0, raw.v[0].x), vmax2(raw.v[0].w, vmax2(raw.v[1].z, raw.v[2].y)));
+                        rx1 = vmax2(vmax2(smx1, raw.v[0].y), vmax2(raw.v[1].x, vmax2(raw.v[1].w, raw.v[2].z)));
+                        rx2 = vmax2(vmax2(smx2, raw.v[0].z), vmax2(raw.v[1].y, vmax2(raw.v[2].x, raw.v[2].w)));
                     } else {
+                        rn0 = smn0; rn1 = smn1; rx0 = smx0; rx1 = smx1;
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            smn0 = vmin2(smn0, vmin2(raw.v[i].x, raw.v[i].z)); smx0 = vmax2(smx0, vmax2(raw.v[i].x, raw.v[i].z));
-                            smn1 = vmin2(smn1, vmin2(raw.v[i].y, raw.v[i].w)); smx1 = vmax2(smx1, vmax2(raw.v[i].y, raw.v[i].w));
+                            rn0 = vmin2(rn0, vmin2(raw.v[i].x, raw.v[i].z)); rx0 = vmax2(rx0, vmax2(raw.v[i].x, raw.v[i].z));
+                            rn1 = vmin2(rn1, vmin2(raw.v[i].y, raw.v[i].w)); rx1 = vmax2(rx1, vmax2(raw.v[i].y, raw.v[i].w));
                         }
                     }
-                    const unsigned top = NCH == 3 ? vmax2(vmax2(smx0, smx1), smx2) : vmax2(smx0, smx1 & 0xffffu);   // alpha is not a colour sample
-                    if (__any_sync(0xffffffffu, vmax2(top, SPEC_CAP2) != SPEC_CAP2)) break;
+                    unsigned moved = (rx0 ^ smx0) | (rx1 ^ smx1) | (rn0 ^ smn0) | (rn1 ^ smn1);
+                    if (NCH == 3) moved |= (rx2 ^ smx2) | (rn2 ^ smn2);
+                    if (__any_sync(0xffffffffu, moved != 0u)) {
+                        rx0 = warp_max_u16x2(rx0); rx1 = warp_max_u16x2(rx1); rn0 = warp_min_u16x2(rn0); rn1 = warp_min_u16x2(rn1);
+                        if (NCH == 3) { rx2 = warp_max_u16x2(rx2); rn2 = warp_min_u16x2(rn2); }
+                        __syncwarp();                                           // every lane has read the old bounds
+                        if (lane == 0) {
+                            sb[0].x = rx0; sb[0].y = rn0; sb[1].x = rx1; sb[1].y = rn1;
+                            if (NCH == 3) { sb[2].x = rx2; sb[2].y = rn2; }
+                        }
+                        __syncwarp();
+                        const unsigned top = NCH == 3 ? vmax2(vmax2(rx0, rx1), rx2) : vmax2(rx0, rx1 & 0xffffu);   // alpha is not a colour sample
+                        if (vmax2(top, SPEC_CAP2) != SPEC_CAP2) break;           // warp-uniform
+                    }
                 }
                 // the codes leave the sample registers first, then the next row is loaded into the same registers: no copy
                 row_split(raw, g, b, rr);
@@ -946,16 +995,10 @@ __device__ __forceinline__ void rows_body(const Fwd3Args &A)
             }
             if (SPEC) {
                 if (r <= rlast) { if (lane == 0) A.bail[frame] = 1; continue; }     // left the row loop early
-                // the run's extrema join the frame's statistics slots in the layout k_plan reads (h2y_stats.cu)
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    smn0 = vmin2(smn0, __shfl_xor_sync(0xffffffffu, smn0, o)); smx0 = vmax2(smx0, __shfl_xor_sync(0xffffffffu, smx0, o));
-                    smn1 = vmin2(smn1, __shfl_xor_sync(0xffffffffu, smn1, o)); smx1 = vmax2(smx1, __shfl_xor_sync(0xffffffffu, smx1, o));
-                    if (NCH == 3) {
-                        smn2 = vmin2(smn2, __shfl_xor_sync(0xffffffffu, smn2, o)); smx2 = vmax2(smx2, __shfl_xor_sync(0xffffffffu, smx2, o));
-                    }
-                }
+                // the run's extrema (already reduced over the warp) join the frame's statistics slots in the layout k_plan
+                // reads (h2y_stats.cu)
                 if (lane == 0) {
+                    const unsigned smx0 = sb[0].x, smn0 = sb[0].y, smx1 = sb[1].x, smn1 = sb[1].y, smx2 = sb[2].x, smn2 = sb[2].y;
                     unsigned cmin[3], cmax[3];                              // G, B, R
                     if (NCH == 3) {
                         cmin[0] = min(smn0 >> 16, smn2 & 0xffffu); cmax[0] = max(smx0 >> 16, smx2 & 0xffffu);
@@ -1382,8 +1425,8 @@ static h2y_status launch_cfgd(h2y_ctx_impl *c, Fwd3Args &A3, int g3, cudaStream_
     if (s != H2Y_OK) return s;
     if (spec) {
         // single pass: the frames are converted with the predicted plan; two-copy or single-copy LUT by the seed's window
-        H2Y_CUDA(c, launch_rows_on(k_forward_exr420_rows<MK_YCBCR, NC, DD, true, false, true>, g3, smem2, st, A3));
-        H2Y_CUDA(c, launch_rows_on(k_forward_exr420_rows<MK_YCBCR, NC, DD, false, false, true>, g3, smem3, aux_stream(c, 0), A3));
+        H2Y_CUDA(c, launch_rows_on(k_forward_exr420_rows<MK_YCBCR, NC, DD, true, false, true>, g3, smem2 + SPEC_BOUNDS_BYTES, st, A3));
+        H2Y_CUDA(c, launch_rows_on(k_forward_exr420_rows<MK_YCBCR, NC, DD, false, false, true>, g3, smem3 + SPEC_BOUNDS_BYTES, aux_stream(c, 0), A3));
         c->launches += 2;
         return H2Y_OK;
     }

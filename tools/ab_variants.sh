@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 for v in "$@"; do
-    H2Y_LIB=$PWD/hdr2yuv_b200/_variants/libh2y_$v.so python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
+    H2Y_LIB=$PWD/hdr2yuv_b200/_variants/libh2y_$v.so python bench.py --steps 10 --warmup 3 --no-cpu ${BENCH_ARGS:-} > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
     python - "$v" <<'PY'
 import json, sys
 v = sys.argv[1]
