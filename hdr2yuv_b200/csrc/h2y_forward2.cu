@@ -327,14 +327,24 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, unsigne
     }
 }
 
-// write_yuv on the luma floor bits: >> shift, range clamp, pack (the low 16 bits of the clamped value are the code)
-template <int CFG>
+// packed 16-bit min / max (ptxas fuses two of them into one VIMNMX3.U16x2)
+__device__ __forceinline__ unsigned vmin2(unsigned a, unsigned b) { unsigned r; asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ unsigned vmax2(unsigned a, unsigned b) { unsigned r; asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+
+// write_yuv on the luma floor bits: >> shift, range clamp, pack (the low 16 bits of the clamped value are the code).
+// NOLOW: the caller's frames cannot produce a luma below the range floor, so only the upper clamp is applied.  That is
+// every frame two_lut_frame() / three_nc_frame() accept: their scaled samples are >= minVR = minVRC (LUT values >= 0),
+// the three weights sum to 1 and the rounding constant adds 0.5, so luma >= minVR + 0.5 - (a few fp32 ulps).
+template <int CFG, bool NOLOW = false>
 __device__ __forceinline__ uint4 pack_luma(const Fwd2Args &a, const unsigned ybits[8])
 {
     typedef KC<CFG> C;
     if (CFG) {
         // shift is 0 and Y < 2^16: pack first, then clamp two codes per instruction
         const unsigned lo2 = (unsigned)C::loY(a) * 0x10001u, hi2 = (unsigned)C::hiY(a) * 0x10001u;
+        if (NOLOW)
+            return make_uint4(vmin2(__byte_perm(ybits[0], ybits[1], 0x5410), hi2), vmin2(__byte_perm(ybits[2], ybits[3], 0x5410), hi2),
+                              vmin2(__byte_perm(ybits[4], ybits[5], 0x5410), hi2), vmin2(__byte_perm(ybits[6], ybits[7], 0x5410), hi2));
         return make_uint4(clamp_u16x2(__byte_perm(ybits[0], ybits[1], 0x5410), lo2, hi2), clamp_u16x2(__byte_perm(ybits[2], ybits[3], 0x5410), lo2, hi2),
                           clamp_u16x2(__byte_perm(ybits[4], ybits[5], 0x5410), lo2, hi2), clamp_u16x2(__byte_perm(ybits[6], ybits[7], 0x5410), lo2, hi2));
     }
@@ -668,9 +678,6 @@ template <bool TWO> __device__ __host__ constexpr unsigned spec_bounds_offset() 
 
 // THREE: the instantiation for frames whose channels need a table each (FrameK::clean3); with TWO as well: the
 // clamp-free chroma path on those three tables (frames that three_nc_frame() accepts)
-// packed 16-bit min / max (ptxas fuses two of them into one VIMNMX3.U16x2)
-__device__ __forceinline__ unsigned vmin2(unsigned a, unsigned b) { unsigned r; asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-__device__ __forceinline__ unsigned vmax2(unsigned a, unsigned b) { unsigned r; asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 
 // maximum / minimum over the warp of both 16-bit halves (REDUX: the result is warp-uniform)
 __device__ __forceinline__ unsigned warp_max_u16x2(unsigned v)
@@ -814,7 +821,7 @@ __device__ __forceinline__ void rows_body(const Fwd3Args &A)
             // carved out as shared memory the spills that follow go to L2 (measured: 1.10 -> 1.69 ms).  The bounds are read
             // back every row (three broadcast loads) and only written when a row moves them.
             volatile uint2 *sb = reinterpret_cast<volatile uint2 *>(smem_raw + spec_bounds_offset<TWO>()) + 3 * warp;
-            const unsigned sb_sa = (unsigned)__cvta_generic_to_shared(const_cast<uint2 *>(sb));
+            const unsigned sb_sa = lut_sa + spec_bounds_offset<TWO>() + 24u * (unsigned)warp;
             if (SPEC) {
                 if (lane < 3) { sb[lane].x = 0u; sb[lane].y = 0xFFFFFFFFu; }
                 __syncwarp();
@@ -857,7 +864,7 @@ __device__ __forceinline__ void rows_body(const Fwd3Args &A)
                 u64 ch[8];
                 if (THREE) pixels8<MK, CFG, TWO, true>(a, lut3G, lut3B, lut3R, g, b, rr, yb, ch);
                 else pixels8<MK, CFG, TWO>(a, lut_sa, lut_sa, lut_sa, g, b, rr, yb, ch);
-                const uint4 ypack = pack_luma<CFG>(a, yb);
+                const uint4 ypack = pack_luma<CFG, TWO>(a, yb);
                 if (lane_interior && r >= ys && r < ye) *reinterpret_cast<uint4 *>(yp) = ypack;
                 float l3x = __shfl_up_sync(0xffffffffu, plo(ch[3]), 1), l3y = __shfl_up_sync(0xffffffffu, phi(ch[3]), 1);
                 float l5x = __shfl_up_sync(0xffffffffu, plo(ch[5]), 1), l5y = __shfl_up_sync(0xffffffffu, phi(ch[5]), 1);
