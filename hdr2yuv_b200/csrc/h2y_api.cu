@@ -736,11 +736,11 @@ h2y_status h2y_forward(h2y_ctx *c, const h2y_forward_params *p, const void *d_sr
             if ((s = launch_spec_verify_and_redo_prologue(c, *p, k, src, src_stride, nf, &dl, st)) != H2Y_OK) return s;
             dfk = (FrameK *)c->scratch[SCR_FRAMEK];
             sl.spec = 0;
-            int three = 0;
-            if ((s = launch_forward_exr420(c, *p, k, tmp.bit_depth, src, src_stride, dst, dst_stride, nf, dfk, dl, st, &three, &sl)) != H2Y_OK) return s;
-            if ((s = aux_fork(c, st)) != H2Y_OK) return s;
-            if ((s = launch_forward_fused(c, *p, k, src, src_stride, dst, dst_stride, nf, dfk, dl, st, three ? 2 : 1, &sl, aux_stream(c, 3))) != H2Y_OK) return s;
-            if ((s = aux_join(c, st)) != H2Y_OK) return s;
+            // Frames the verify step handed back (usually none) are converted by the general kernel, which spreads every
+            // frame over the whole GPU.  The rows kernels are not launched again: four more launches and their stream
+            // joins would be paid by every call for the sake of the one call in which a sequence changes its plan (the
+            // host policy stops speculating after that call).
+            if ((s = launch_forward_fused(c, *p, k, src, src_stride, dst, dst_stride, nf, dfk, dl, st, 0, &sl, nullptr)) != H2Y_OK) return s;
             if ((s = launch_seed_update(c, dfk, dl, nf, seq, 1, 0, st)) != H2Y_OK) return s;
             c->last_nframes = nf;
             c->last_stream = st;

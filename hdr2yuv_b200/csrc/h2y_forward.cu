@@ -49,8 +49,7 @@ struct FwdArgs {
     const FrameK *framek;
     const float *luts;       // [nframes*3][65536]
     unsigned long long *fallback_count;   // pixels that took the exact fallback (diagnostic)
-    // behind a plan-reuse pass (h2y_internal.h): only frames with flag[frame] != 0 are left; in mode 1 this kernel
-    // converts all of them, in mode 2 those the rows kernels declined
+    // behind a plan-reuse pass (h2y_internal.h): only frames with flag[frame] != 0 are left, this kernel converts all of them
     const SpecCtl *ctl;
     const int *flag;
 };
@@ -182,7 +181,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_fused(const FwdArgs a)
         const int seg = (item / a.nstrips) % a.nsegs;
         const int frame = item / (a.nstrips * a.nsegs);
         if (a.flag && !a.flag[frame]) continue;                 // converted and confirmed by the plan-reuse pass
-        if (a.skip_clean && (!a.ctl || a.ctl->mode == 2) &&
+        if (a.skip_clean && !a.ctl &&
             (a.framek[frame].clean || (a.skip_clean > 1 && a.framek[frame].clean3))) continue;   // uniform per CTA
         const uint8_t *fsrc = a.src + (size_t)frame * a.src_stride;
         uint16_t *fY = reinterpret_cast<uint16_t *>(a.dst + (size_t)frame * a.dst_stride);

@@ -660,12 +660,11 @@ struct Fwd3Args {
     int split_by_lut2;       // two instantiations share the frames: TWO takes those with lut2_ok, the other the rest
     int split_three_nc;      // likewise for three-table frames: TWO (clamp-free) takes those three_nc_frame() accepts
     long total_rows;         // nframes * h
-    // plan reuse (h2y_internal.h, SpecSeed / SpecCtl).  SPEC instantiations: every frame is converted with the one
+    // plan reuse (h2y_internal.h, SpecSeed / SpecCtl), SPEC instantiations only: every frame is converted with the one
     // predicted FrameK at b.framek[0] while the warp gathers the frame's extrema into `slots`; `bail[frame]` is raised
-    // when a code falls outside the predicted LUT window (before it is used as an index).  Classic instantiations
-    // launched behind a SPEC pass convert only frames with flag[frame] != 0, and only when ctl->mode == 2.
+    // when a code falls outside the predicted LUT window (before it is used as an index).  The frames the verify step
+    // hands back are converted by the general kernel (h2y_forward.cu).
     const SpecCtl *ctl;
-    const int *flag;
     int *bail;
     unsigned *slots;
 };
@@ -701,8 +700,7 @@ __device__ __forceinline__ unsigned half_code_key(unsigned code) { return __floa
 template <int MK, int NCH, int CFG, bool TWO, bool THREE, bool SPEC = false>
 __device__ __forceinline__ void rows_body(const Fwd3Args &A)
 {
-    if (SPEC) { if (A.ctl->skip) return; }                       // no usable seed: the classic kernels convert everything
-    else if (A.ctl && A.ctl->mode != 2) return;                  // behind a SPEC pass: the rows kernels serve mode 2 only
+    if (SPEC) { if (A.ctl->skip) return; }                       // no usable seed: every frame is handed back
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *lut_s = reinterpret_cast<float *>(smem_raw);
     // shared-window address of the LUT, held in an ordinary register (the asm hides that it is uniform: as a uniform
@@ -745,7 +743,6 @@ __device__ __forceinline__ void rows_body(const Fwd3Args &A)
 
     for (int frame = f_first; frame <= f_last; frame++) {
         const FrameK &fk = a.framek[SPEC ? 0 : frame];
-        if (!SPEC && A.flag && !A.flag[frame]) continue; // converted and confirmed by the SPEC pass
         if (THREE ? !fk.clean3 : !fk.clean) continue;    // uniform per CTA: another launch converts this frame
         if (!THREE && A.split_by_lut2 && TWO != two_lut_frame<CFG>(a, fk)) continue;   // the other instantiation converts this frame
         if (THREE && A.split_three_nc && TWO != three_nc_frame<CFG>(a, fk)) continue;
@@ -1472,7 +1469,7 @@ h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, c
     Fwd3Args A3;
     int g3 = 0;
     if (rows_plan(c, a, nframes, &A3, &g3)) {
-        if (sl) { A3.ctl = sl->ctl; A3.flag = sl->flag; A3.bail = sl->bail; A3.slots = sl->slots; }
+        if (sl) { A3.ctl = sl->ctl; A3.bail = sl->bail; A3.slots = sl->slots; }
         // frames that need a table per channel (FrameK::clean3) are served by further instantiations of the same kernel
         if (took_three_table_frames) *took_three_table_frames = 1;
         const bool spec = sl && sl->spec;
@@ -1485,7 +1482,6 @@ h2y_status launch_forward_exr420(h2y_ctx_impl *c, const h2y_forward_params &p, c
         return nch == 3 ? launch_generic_rows<MK_YDZDX, 3>(c, A3, g3, st) : launch_generic_rows<MK_YDZDX, 4>(c, A3, g3, st);
     }
     if (sl && sl->spec) return H2Y_ERR_UNSUPPORTED;
-    if (sl) return H2Y_OK;        // behind a SPEC pass the general kernel converts whatever is flagged (small batches cannot get here)
     const size_t smem = (size_t)RING_ROWS * RING_PITCH * sizeof(float) + (size_t)LUT_MAX_CODES * sizeof(float);
     const int grid = a.nitems < c->sm_count ? a.nitems : c->sm_count;
     if (k.mat_kind == MK_YCBCR)

@@ -47,7 +47,7 @@ struct SpecSeed {               // device-resident, one per context: the plan pr
 struct SpecCtl {                // device-resident, one per call
     int skip;                   // no usable seed: the speculative kernels return at once, every frame is flagged
     int nflag;                  // frames the classic kernels still have to convert
-    int mode;                   // 0 nothing to do, 1 the general kernel converts the flagged frames, 2 the rows kernels do
+    int mode;                   // 0 nothing to do, 1 the general kernel converts the flagged frames
     int nframes;
     int seq;                    // call counter (the host reads a copy of this struct, late, as feedback for its policy)
     int uniform;                // frames of this call whose final plan equals the last frame's (classic calls)
@@ -116,7 +116,7 @@ struct SpecLaunch {
     const int *flag;            // per frame: 1 = still to be converted by the classic kernels
     int *bail;                  // per frame: raised by the SPEC kernel when a code left the predicted LUT window
     unsigned *slots;            // statistics slots the SPEC kernel fills
-    int spec;                   // 1: launch the SPEC instantiations; 0: classic instantiations restricted to `flag`
+    int spec;                   // 1: launch the SPEC instantiations of the rows kernel; 0: the general kernel, restricted to `flag`
 };
 
 constexpr int PROFILE_RING = 16;

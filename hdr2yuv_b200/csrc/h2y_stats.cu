@@ -148,13 +148,11 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
 
 // grid = (blocks, nframes); npix % 8 == 0, frames 16-byte aligned.  NCH = 3 or 4 interleaved, 0 = planar.
 template <bool HALF, int NCH>
-__global__ void __launch_bounds__(256, 4)
-k_stats_vec(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int clip_on, unsigned lo, unsigned hi,
-            unsigned *slots, const int *mask)
+__device__ __forceinline__ void stats_vec_frame(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int clip_on, unsigned lo,
+                                                unsigned hi, unsigned *slots, const int frame)
 {
     typedef Pk<HALF> P;
-    if (mask && !mask[blockIdx.y]) return;       // behind a plan-reuse pass: only the frames it handed back
-    const uint8_t *f = src + (size_t)blockIdx.y * frame_stride;
+    const uint8_t *f = src + (size_t)frame * frame_stride;
     unsigned mnv[3], mxv[3];        // per word kind (interleaved) or per plane (planar), two lanes each
     unsigned umn = 0xFFFFFFFFu, umx = 0u;   // half input: extrema of the RAW codes of the colour channels (packed)
     unsigned nzv[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};     // half input, 3 channels: smallest nonzero code - 1, per word kind
@@ -265,7 +263,7 @@ k_stats_vec(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int
         r[8] = nzv[0]; r[9] = nzv[1]; r[10] = nzv[2];
     }
     __syncthreads();
-    if (threadIdx.x >= 32) return;
+    if (threadIdx.x >= 32) return;              // the masked kernel's frame loop synchronises before `red` is written again
     {
         typedef Pk<false> U;
         const int wsrc = threadIdx.x & 7;
@@ -287,16 +285,16 @@ k_stats_vec(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int
     }
     if (HALF) {
         if (threadIdx.x == 0) {
-            atomicMin(&slots[blockIdx.y * SLOTS + 6], min(umn & 0xffffu, umn >> 16));
-            atomicMax(&slots[blockIdx.y * SLOTS + 7], max(umx & 0xffffu, umx >> 16));
+            atomicMin(&slots[frame * SLOTS + 6], min(umn & 0xffffu, umn >> 16));
+            atomicMax(&slots[frame * SLOTS + 7], max(umx & 0xffffu, umx >> 16));
             if (NCH == 3) {     // the (word kind, half) pairs of G, B, R: as for the extrema below
-                atomicMin(&slots[blockIdx.y * SLOTS + 8], min(nzv[0] >> 16, nzv[2] & 0xffffu));
-                atomicMin(&slots[blockIdx.y * SLOTS + 9], min(nzv[1] & 0xffffu, nzv[2] >> 16));
-                atomicMin(&slots[blockIdx.y * SLOTS + 10], min(nzv[0] & 0xffffu, nzv[1] >> 16));
+                atomicMin(&slots[frame * SLOTS + 8], min(nzv[0] >> 16, nzv[2] & 0xffffu));
+                atomicMin(&slots[frame * SLOTS + 9], min(nzv[1] & 0xffffu, nzv[2] >> 16));
+                atomicMin(&slots[frame * SLOTS + 10], min(nzv[0] & 0xffffu, nzv[1] >> 16));
             }
         }
     } else if (threadIdx.x == 0 && blockIdx.x == 0) {
-        slots[blockIdx.y * SLOTS + 6] = 0u; slots[blockIdx.y * SLOTS + 7] = 0xffffu;     // integer codes: not the v2 route
+        slots[frame * SLOTS + 6] = 0u; slots[frame * SLOTS + 7] = 0xffffu;     // integer codes: not the v2 route
     }
     if (threadIdx.x == 0) {
         // (word kind, half) pairs that hold each of G, B, R (slot order 0/1/2 = G/B/R)
@@ -329,9 +327,33 @@ k_stats_vec(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int
                     a = a < lo ? lo : (a > hi ? hi : a);
                     b = b < lo ? lo : (b > hi ? hi : b);
                 }
-                if (P::key(a, k)) atomicMin(&slots[blockIdx.y * SLOTS + c * 2 + 0], k);
-                if (P::key(b, k)) atomicMax(&slots[blockIdx.y * SLOTS + c * 2 + 1], k);
+                if (P::key(a, k)) atomicMin(&slots[frame * SLOTS + c * 2 + 0], k);
+                if (P::key(b, k)) atomicMax(&slots[frame * SLOTS + c * 2 + 1], k);
             }
+    }
+}
+
+// grid = (blocks, nframes); npix % 8 == 0, frames 16-byte aligned.  NCH = 3 or 4 interleaved, 0 = planar.
+template <bool HALF, int NCH>
+__global__ void __launch_bounds__(256, 4)
+k_stats_vec(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int clip_on, unsigned lo, unsigned hi,
+            unsigned *slots)
+{
+    stats_vec_frame<HALF, NCH>(src, frame_stride, npix, clip_on, lo, hi, slots, blockIdx.y);
+}
+
+// Behind a plan-reuse pass: only the frames it handed back (mask[frame] != 0), usually none.  A lean grid (a few rows of
+// blocks that walk the frames) instead of one row of blocks per frame: the launch costs what an empty kernel costs.
+template <bool HALF, int NCH>
+__global__ void __launch_bounds__(256, 4)
+k_stats_vec_masked(const uint8_t *__restrict__ src, size_t frame_stride, long npix, int clip_on, unsigned lo, unsigned hi,
+                   unsigned *slots, const int *mask, const SpecCtl *ctl, int nframes)
+{
+    if (ctl->nflag == 0) return;
+    for (int frame = blockIdx.y; frame < nframes; frame += gridDim.y) {
+        if (!mask[frame]) continue;             // uniform per block
+        stats_vec_frame<HALF, NCH>(src, frame_stride, npix, clip_on, lo, hi, slots, frame);
+        __syncthreads();
     }
 }
 
@@ -387,7 +409,7 @@ k_stats_u16_planes(const uint16_t *__restrict__ p0, const uint16_t *__restrict__
 
 // Turn extrema into estimated floor / ceiling, offset / range and LUT slots.  One block.
 // `mask` (behind a plan-reuse pass): frames with mask[frame] == 0 keep their FrameK and take no part in the slot search.
-__global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_float, int bit_depth, int is_half, const int *mask)
+__device__ __forceinline__ void plan_frames(const unsigned *slots, FrameK *fk, int nframes, int is_float, int bit_depth, int is_half, const int *mask)
 {
     const int n = nframes * 3;
     for (int p = threadIdx.x; p < n; p += blockDim.x) {
@@ -464,13 +486,22 @@ __global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_fl
     }
 }
 
-// grid = (256, nframes*3): LUT p is built only by its owner (lut_slot == p).
-__global__ void __launch_bounds__(256)
-k_build_lut(const FrameK *fk, float *luts, int is_half, int tf_lin, int tf_enc, int clip_on, unsigned lo, unsigned hi,
-            const int *mask)
+__global__ void k_plan(const unsigned *slots, FrameK *fk, int nframes, int is_float, int bit_depth, int is_half)
 {
-    const int p = blockIdx.y;
-    if (mask && !mask[p / 3]) return;
+    plan_frames(slots, fk, nframes, is_float, bit_depth, is_half, nullptr);
+}
+// behind a plan-reuse pass: the frames it handed back (usually none)
+__global__ void k_plan_masked(const unsigned *slots, FrameK *fk, int nframes, int is_float, int bit_depth, int is_half, const int *mask,
+                              const SpecCtl *ctl)
+{
+    if (ctl->nflag == 0) return;
+    plan_frames(slots, fk, nframes, is_float, bit_depth, is_half, mask);
+}
+
+// LUT p (= frame * 3 + channel) is built only by its owner (lut_slot == p), one 16-bit code per thread
+__device__ __forceinline__ void build_lut(const FrameK *fk, float *luts, int is_half, int tf_lin, int tf_enc, int clip_on, unsigned lo,
+                                          unsigned hi, const int p)
+{
     const FrameK &f = fk[p / 3];
     const int c = p % 3;
     if (f.lut_slot[c] != p) return;
@@ -484,6 +515,22 @@ k_build_lut(const FrameK *fk, float *luts, int is_half, int tf_lin, int tf_enc, 
     }
     x = __fdiv_rn(__fsub_rn(x, f.offset[c]), f.range[c]);        // convert.cpp:1017-1019
     luts[(size_t)p * 65536 + code] = change_transfer(x, tf_lin, tf_enc);
+}
+
+// grid = (256, nframes*3)
+__global__ void __launch_bounds__(256)
+k_build_lut(const FrameK *fk, float *luts, int is_half, int tf_lin, int tf_enc, int clip_on, unsigned lo, unsigned hi)
+{
+    build_lut(fk, luts, is_half, tf_lin, tf_enc, clip_on, lo, hi, blockIdx.y);
+}
+// behind a plan-reuse pass: grid = (256, a few), the blocks walk the LUTs of the frames that were handed back
+__global__ void __launch_bounds__(256)
+k_build_lut_masked(const FrameK *fk, float *luts, int is_half, int tf_lin, int tf_enc, int clip_on, unsigned lo, unsigned hi,
+                   const int *mask, const SpecCtl *ctl, int nframes)
+{
+    if (ctl->nflag == 0) return;
+    for (int p = blockIdx.y; p < nframes * 3; p += gridDim.y)
+        if (mask[p / 3]) build_lut(fk, luts, is_half, tf_lin, tf_enc, clip_on, lo, hi, p);
 }
 
 // ---- launchers ---------------------------------------------------------------------------------
@@ -509,18 +556,29 @@ static h2y_status stats_and_luts(h2y_ctx_impl *c, const h2y_forward_params &p, c
     const bool vec = (npix % 8) == 0 && (((uintptr_t)d_src | src_stride) & 15) == 0;
     const uint8_t *sb = (const uint8_t *)d_src;
     unsigned *sl = (unsigned *)slots;
+    const SpecCtl *ctl = nullptr;
+    if (mask) {
+        SpecDev sd;
+        if ((s = spec_dev(c, &sd)) != H2Y_OK) return s;
+        ctl = sd.ctl;
+    }
     if (vec) {
         // 2 CTAs of 256 threads per SM per frame row keeps ~16 KB in flight per SM
         // grid.x * 256 threads must be a multiple of 3 (see k_stats_vec, 3-channel case)
         const int gx = (c->sw.stats_gx ? c->sw.stats_gx : (nframes >= 8 ? 2 * c->sm_count : 6 * c->sm_count)) / 3 * 3;
         dim3 vgrid(gx, nframes);
-        if (half) {
-            if (nch == 3) k_stats_vec<true, 3><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, 0, 0, 0, sl, mask);
-            else k_stats_vec<true, 4><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, 0, 0, 0, sl, mask);
+        if (mask) {
+            dim3 lean(gx, nframes < 4 ? nframes : 4);
+            if (!half) return H2Y_ERR_UNSUPPORTED;                   // the plan-reuse route is the half-float route
+            if (nch == 3) k_stats_vec_masked<true, 3><<<lean, 256, 0, st>>>(sb, src_stride, npix, 0, 0, 0, sl, mask, ctl, nframes);
+            else k_stats_vec_masked<true, 4><<<lean, 256, 0, st>>>(sb, src_stride, npix, 0, 0, 0, sl, mask, ctl, nframes);
+        } else if (half) {
+            if (nch == 3) k_stats_vec<true, 3><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, 0, 0, 0, sl);
+            else k_stats_vec<true, 4><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, 0, 0, 0, sl);
         } else {
-            if (nch == 3) k_stats_vec<false, 3><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl, mask);
-            else if (nch == 4) k_stats_vec<false, 4><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl, mask);
-            else k_stats_vec<false, 0><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl, mask);
+            if (nch == 3) k_stats_vec<false, 3><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl);
+            else if (nch == 4) k_stats_vec<false, 4><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl);
+            else k_stats_vec<false, 0><<<vgrid, 256, 0, st>>>(sb, src_stride, npix, k.clip_on_load, k.loadLo, k.loadHi, sl);
         }
     } else if (mask)
         return H2Y_ERR_UNSUPPORTED;      // the plan-reuse route only exists for vector-aligned frames
@@ -530,9 +588,15 @@ static h2y_status stats_and_luts(h2y_ctx_impl *c, const h2y_forward_params &p, c
     else
         k_stats_codes<false><<<grid, 256, 0, st>>>((const uint16_t *)d_src, src_stride / 2, p.src.layout, npix,
                                                    k.clip_on_load, k.loadLo, k.loadHi, (unsigned *)slots);
-    k_plan<<<1, 256, 0, st>>>((const unsigned *)slots, (FrameK *)fk, nframes, half ? 1 : 0, p.src.bit_depth, half ? 1 : 0, mask);
-    k_build_lut<<<dim3(256, nframes * 3), 256, 0, st>>>((const FrameK *)fk, (float *)luts, half ? 1 : 0, k.tf_linearise,
-                                                         k.tf_encode, k.clip_on_load, k.loadLo, k.loadHi, mask);
+    if (mask) {
+        k_plan_masked<<<1, 256, 0, st>>>((const unsigned *)slots, (FrameK *)fk, nframes, 1, p.src.bit_depth, 1, mask, ctl);
+        k_build_lut_masked<<<dim3(256, 6), 256, 0, st>>>((const FrameK *)fk, (float *)luts, 1, k.tf_linearise, k.tf_encode,
+                                                          k.clip_on_load, k.loadLo, k.loadHi, mask, ctl, nframes);
+    } else {
+        k_plan<<<1, 256, 0, st>>>((const unsigned *)slots, (FrameK *)fk, nframes, half ? 1 : 0, p.src.bit_depth, half ? 1 : 0);
+        k_build_lut<<<dim3(256, nframes * 3), 256, 0, st>>>((const FrameK *)fk, (float *)luts, half ? 1 : 0, k.tf_linearise,
+                                                             k.tf_encode, k.clip_on_load, k.loadLo, k.loadHi);
+    }
     c->launches += 4;
     H2Y_CUDA(c, cudaGetLastError());
     *d_framek = (FrameK *)fk;
@@ -600,8 +664,12 @@ __global__ void k_spec_prepare(const SpecSeed *seed, SpecCtl *ctl, FrameK *pred,
 // did not hand it back, it is a clean single-table frame, its (int) floor / ceiling are the predicted ones (so the seed
 // LUT is the function the reference applies, convert.cpp:1017-1019) and its codes lie inside the window the kernel had in
 // shared memory.  Frames that fail get fresh statistics slots: the classic pass recomputes them from the samples.
-__global__ void k_spec_verify(const FrameK *pred, FrameK *fk, const int *bail, int *flag, SpecCtl *ctl, unsigned *slots, int nframes)
+__global__ void k_spec_verify(const FrameK *pred, FrameK *fk, const int *bail, int *flag, SpecCtl *ctl, unsigned *slots, int nframes,
+                              int bit_depth)
 {
+    // the plan the reference would derive from the extrema the SPEC kernel gathered (every frame, one block)
+    plan_frames(slots, fk, nframes, 1, bit_depth, 1, nullptr);
+    __syncthreads();
     __shared__ int count;
     if (threadIdx.x == 0) count = 0;
     __syncthreads();
@@ -620,9 +688,8 @@ __global__ void k_spec_verify(const FrameK *pred, FrameK *fk, const int *bail, i
     __syncthreads();
     if (threadIdx.x == 0) {
         ctl->nflag = count;
-        // a few stragglers are cheapest through the general kernel (it spreads every frame over the whole GPU); a batch
-        // that mostly failed goes back to the rows kernels, whose row ranges cover all frames of the call
-        ctl->mode = count == 0 ? 0 : (count >= 10 && count * 4 >= nframes ? 2 : 1);
+        // the general kernel converts what was handed back (it spreads every frame over the whole GPU)
+        ctl->mode = count == 0 ? 0 : 1;
     }
 }
 
@@ -707,9 +774,8 @@ h2y_status launch_spec_verify_and_redo_prologue(h2y_ctx_impl *c, const h2y_forwa
     if ((s = scratch_reserve(c, SCR_FRAMEK, (size_t)nframes * sizeof(FrameK), &fk)) != H2Y_OK) return s;
     unsigned *slots = (unsigned *)c->scratch[SCR_STATS];
     int *bail = (int *)c->scratch[SCR_SPEC], *flag = bail + nframes;
-    k_plan<<<1, 256, 0, st>>>(slots, (FrameK *)fk, nframes, 1, p.src.bit_depth, 1, nullptr);
-    k_spec_verify<<<1, 256, 0, st>>>(sd.pred, (FrameK *)fk, bail, flag, sd.ctl, slots, nframes);
-    c->launches += 2;
+    k_spec_verify<<<1, 256, 0, st>>>(sd.pred, (FrameK *)fk, bail, flag, sd.ctl, slots, nframes, p.src.bit_depth);
+    c->launches += 1;
     H2Y_CUDA(c, cudaGetLastError());
     FrameK *dfk;
     return stats_and_luts(c, p, k, d_src, src_stride, nframes, &dfk, d_luts, st, flag);
@@ -747,7 +813,7 @@ h2y_status launch_stats_planar(h2y_ctx_impl *c, const h2y_pic_desc &pic, const v
     else
         k_stats_u16_planes<<<blocks, 256, 0, st>>>((const uint16_t *)d_planes[0], (const uint16_t *)d_planes[1],
                                                    (const uint16_t *)d_planes[2], n0, n12, (unsigned *)slots);
-    k_plan<<<1, 256, 0, st>>>((const unsigned *)slots, (FrameK *)fk, 1, isf ? 1 : 0, pic.bit_depth, 0, nullptr);
+    k_plan<<<1, 256, 0, st>>>((const unsigned *)slots, (FrameK *)fk, 1, isf ? 1 : 0, pic.bit_depth, 0);
     c->launches += 3;
     H2Y_CUDA(c, cudaGetLastError());
     *d_framek = (FrameK *)fk;

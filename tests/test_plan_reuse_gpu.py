@@ -87,7 +87,7 @@ def test_frames_with_another_plan_are_converted_again(ctx, opt):
 
 
 def test_a_sequence_that_changed_goes_back_to_the_rows_kernels(ctx, opt):
-    # the seed is from other content: every frame fails (mode 2: the classic rows kernels convert the whole call)
+    # the seed is from other content: every frame fails and the general kernel converts the whole call
     opt("H2Y_FORWARD_KERNEL", "rows")
     w, h = 480, 130
     dst = _dst()
