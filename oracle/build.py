@@ -5,6 +5,10 @@
   oracle/_ref/libh2yref.so the reference's own convert.cpp/common.cpp/tiff.cpp compiled UNMODIFIED,
                            read in place from /root/reference (never copied), plus ref_shim.cpp.
   oracle/_ref/yuv2tiff_ref the reference's whole yuv2tiff.cpp program.
+  oracle/_ref/hdr2yuv_ref  the reference's whole hdr2yuv program: its own main() / parse_options() / read_file()
+                           (hdr2yuv.cpp) linked with the same convert/common/tiff objects and ref_io_stubs.cpp
+                           (the EXR / DPX codecs, which need OpenEXR, abort when reached).  The CLI tests
+                           byte-compare hdr2yuv_b200/cli/bin/hdr2yuv with it on .rgb / .yuv / .tiff sources.
 
 The two reference sources that include "/usr/local/include/tiffio.h" by absolute path
 (tiff.cpp:3, yuv2tiff.cpp:5) are streamed through sed into the compiler's stdin so that the
@@ -24,6 +28,7 @@ OUT_REF = os.path.join(HERE, "_ref")
 ORACLE_SO = os.path.join(HERE, "libh2yoracle.so")
 REF_SO = os.path.join(OUT_REF, "libh2yref.so")
 REF_YUV2TIFF = os.path.join(OUT_REF, "yuv2tiff_ref")
+REF_HDR2YUV = os.path.join(OUT_REF, "hdr2yuv_ref")
 
 CFLAGS = ["-O2", "-fPIC", "-ffp-contract=off"]
 LEGACY_INCLUDES = ["-include", "cstring", "-include", "limits", "-include", "cstdlib", "-include", "cstdio",
@@ -68,7 +73,10 @@ def build_ref(force=False):
     if not os.path.isdir(REF):
         return REF_SO if os.path.exists(REF_SO) else None
     shim = os.path.join(HERE, "ref_shim.cpp")
-    if not force and _newer(REF_SO, shim, os.path.join(REF, "convert.cpp")) and os.path.exists(REF_YUV2TIFF):
+    stub_h = os.path.join(HERE, "stub", "tiffio.h")
+    io_stubs = os.path.join(HERE, "ref_io_stubs.cpp")
+    if not force and _newer(REF_SO, shim, stub_h, io_stubs, os.path.join(REF, "convert.cpp")) and os.path.exists(REF_YUV2TIFF) and \
+            os.path.exists(REF_HDR2YUV):
         return REF_SO
     os.makedirs(OUT_REF, exist_ok=True)
     objs = []
@@ -84,6 +92,13 @@ def build_ref(force=False):
     objs.append(shim_obj)
     _run(["g++", "-shared", "-o", REF_SO] + objs + ["-lm"])
     _compile_via_sed("yuv2tiff.cpp", REF_YUV2TIFF, link=True)
+    # the reference's own main(): hdr2yuv.cpp + the three objects above + the codec stubs
+    main_obj = os.path.join(OUT_REF, "hdr2yuv.o")
+    stubs_obj = os.path.join(OUT_REF, "ref_io_stubs.o")
+    _run(["g++"] + CFLAGS + ["-w", "-I" + REF] + LEGACY_INCLUDES + ["-c", os.path.join(REF, "hdr2yuv.cpp"), "-o", main_obj])
+    _run(["g++"] + CFLAGS + ["-w", "-I" + REF] + LEGACY_INCLUDES + ["-c", io_stubs, "-o", stubs_obj])
+    _run(["g++", "-o", REF_HDR2YUV, main_obj, stubs_obj] + [o for o in objs if not o.endswith("ref_shim.o")] + ["-lm"])
+    objs += [main_obj, stubs_obj]
     for o in objs:
         os.remove(o)
     return REF_SO

@@ -151,6 +151,38 @@ def forward(planes, src, dst, backend="port", want_tmp=False, timing=None):
     return (out, tmp, stats) if want_tmp else out
 
 
+def matrix_convert_f32(planes, src, dst, backend="port"):
+    """matrix_convert into an F32 picture (convert.cpp:1222-1304; what an .exr / .dpx destination runs, hdr2yuv.cpp:797-823).
+    planes: (3,H,W) uint16 or float32, G,B,R.  Returns (3,H,W) float32.  The tmp depth is the reference's
+    (hdr2yuv.cpp:805-808): the source depth for an F32 source, the destination depth for an integer source."""
+    planes = np.ascontiguousarray(planes)
+    _, h, w = planes.shape
+    is_f32 = planes.dtype == np.float32
+    out = np.zeros((3, h, w), np.float32)
+    if backend == "ref":
+        cfg = (C.c_int * 15)(w, h, int(is_f32), src["bit_depth"], src["full_range"], src["transfer"], src["primaries"],
+                             src["matrix"], dst["bit_depth"], dst["full_range"], dst["transfer"], dst["primaries"],
+                             dst["matrix"], 3, 0)
+        pl = (C.c_void_p * 3)(*[planes[c].ctypes.data for c in range(3)])
+        rc = ref_lib().ref_matrix_convert_f32out(cfg, pl, _ptr(out))
+        if rc:
+            raise RuntimeError("reference matrix_convert returned %d" % rc)
+        return out
+    lib = port_lib()
+    pic = _Pic(w, h, CHROMA_444, src["transfer"], src["primaries"], src["matrix"], src["bit_depth"], src["full_range"],
+               PIC_F32 if is_f32 else PIC_U16)
+    t = _Pic(w, h, CHROMA_444, dst["transfer"], dst["primaries"], dst["matrix"], src["bit_depth"] if is_f32 else dst["bit_depth"],
+             dst["full_range"], PIC_F32)
+    for c in range(3):
+        (pic.fbuf if is_f32 else pic.buf)[c] = planes[c].ctypes.data
+        t.fbuf[c] = out[c].ctypes.data
+    lib.orc_pic_stats(C.byref(pic), None, None)
+    rc = lib.orc_matrix_convert(C.byref(t), C.byref(pic))
+    if rc:
+        raise RuntimeError("oracle matrix_convert returned %d" % rc)
+    return out
+
+
 def pic_stats(planes, bit_depth, backend="port"):
     planes = np.ascontiguousarray(planes)
     _, h, w = planes.shape

@@ -143,6 +143,36 @@ int ref_forward_frame(const int *cfg, const void *const planes[3], unsigned shor
     return rc;
 }
 
+/* matrix_convert into an F32 picture (convert.cpp:1117-1122, 1222-1304): what hdr2yuv.cpp:797-823 runs for an .exr / .dpx
+ * destination.  cfg as ref_forward_frame (cfg[13], cfg[14] unused); out444: three float planes.  The caller chooses
+ * combinations whose tmp depth is defined (an F32 source with an F32 destination makes set_pic_clip shift by 32). */
+int ref_matrix_convert_f32out(const int *cfg, const void *const planes[3], float *out444)
+{
+    Quiet q;
+    const int w = cfg[0], h = cfg[1];
+    const size_t n = (size_t)w * h;
+    static hdr_t hd;
+    memset(&hd, 0, sizeof(hd));
+    pic_t *in = &hd.in_pic;
+    pic_t tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    const int in_type = cfg[2] ? PIC_TYPE_F32 : PIC_TYPE_U16;
+    init_pic(in, w, h, CHROMA_444, cfg[3], cfg[4], cfg[6], cfg[5], cfg[7], 0, in_type, 0, 0, "in_pic");
+    for (int c = 0; c < 3; c++) {
+        if (cfg[2]) memcpy(in->fbuf[c], planes[c], n * sizeof(float));
+        else memcpy(in->buf[c], planes[c], n * sizeof(unsigned short));
+    }
+    pic_stats(in, &in->stats, 1);
+    const int tmp_depth = in_type == PIC_TYPE_F32 ? in->bit_depth : cfg[8];          /* hdr2yuv.cpp:805-808 */
+    init_pic(&tmp, w, h, CHROMA_444, tmp_depth, cfg[9], cfg[11], cfg[10], cfg[12], 0, PIC_TYPE_F32, 0, 0, "tmp_pic");
+    const int rc = matrix_convert(&tmp, &hd, in);
+    if (rc == 0)
+        for (int c = 0; c < 3; c++) memcpy(out444 + c * n, tmp.fbuf[c], n * sizeof(float));
+    deinit_pic(in);
+    deinit_pic(&tmp);
+    return rc;
+}
+
 void ref_subsample_fir(unsigned short *dst, const unsigned short *src, int w, int h, unsigned long lo, unsigned long hi)
 {
     Quiet q;

@@ -240,3 +240,62 @@ def test_readers_reject_damaged_files(cli, tmp_path):
     (tmp_path / "cut.tiff").write_bytes(bytes(tif.read_bytes()[:200]))
     rc, text = run([cli["h2y_iotool"], "read-tiff", str(tmp_path / "cut.tiff"), str(out)], check=False)
     assert rc == 1, text
+
+
+# ---- the reference's own program (oracle/_ref/hdr2yuv_ref = hdr2yuv.cpp's main() built unmodified) ------------------------
+# The GPU CLI tests hand the oracle the source / destination parameters the test author derived from an argv.  Here that
+# derivation (option inheritance hdr2yuv.cpp:265-318, defaults, .rgb read path, write_yuv append) is checked against the
+# reference program itself, on the CPU: same argv -> the reference's output file must equal the oracle's forward() result.
+REF_BIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "hdr2yuv_ref")
+needs_ref_bin = pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/hdr2yuv_ref not built (no /root/reference here)")
+
+REF_PROGRAM_CASES = {
+    # argv tail (after the file names and geometry) -> (src bits, src dict, dst dict) as the GPU tests would derive them
+    "rgb12_to_420_bt709_box_default": (
+        12, ["--src_transfer_characteristics", "1", "--dst_transfer_characteristics", "1", "--dst_bit_depth", "10",
+             "--dst_chroma_format_idc", "1", "--src_matrix_coeffs", "0", "--dst_matrix_coeffs", "1", "--src_colour_primaries", "1",
+             "--dst_colour_primaries", "1"],
+        dict(bit_depth=12, full_range=0, transfer=1, primaries=1, matrix=0),
+        dict(bit_depth=10, full_range=0, transfer=1, primaries=1, matrix=1, chroma=1, resampler=0)),
+    "rgb16_everything_inherited": (
+        16, ["--src_transfer_characteristics", "16", "--dst_chroma_format_idc", "1", "--src_matrix_coeffs", "0",
+             "--dst_matrix_coeffs", "9", "--src_colour_primaries", "9"],
+        dict(bit_depth=16, full_range=0, transfer=16, primaries=9, matrix=0),
+        dict(bit_depth=16, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=0)),
+    "rgb16_ydzdx_fir_10": (
+        16, ["--src_transfer_characteristics", "16", "--dst_bit_depth", "10", "--dst_chroma_format_idc", "1", "--src_matrix_coeffs", "0",
+             "--dst_matrix_coeffs", "11", "--src_colour_primaries", "10", "--chroma_resampler_type", "1"],
+        dict(bit_depth=16, full_range=0, transfer=16, primaries=10, matrix=0),
+        dict(bit_depth=10, full_range=0, transfer=16, primaries=10, matrix=11, chroma=1, resampler=1)),
+    # (no 4:2:2 case: the reference's convert() has no 4:2:2 branch, its program writes constant chroma planes; this repo
+    # defines 4:2:2 as stage 1 of the reference's two-stage FIR, pinned through ref_subsample_fir's first stage instead)
+    "rgb16_full_range_flags": (
+        16, ["--src_transfer_characteristics", "16", "--dst_bit_depth", "12", "--dst_chroma_format_idc", "3", "--src_matrix_coeffs", "0",
+             "--dst_matrix_coeffs", "9", "--src_colour_primaries", "9", "--src_video_full_range_flag", "1"],
+        dict(bit_depth=16, full_range=1, transfer=16, primaries=9, matrix=0),
+        dict(bit_depth=12, full_range=1, transfer=16, primaries=9, matrix=9, chroma=3, resampler=0)),
+}
+
+
+@needs_ref_bin
+@pytest.mark.parametrize("name", sorted(REF_PROGRAM_CASES))
+def test_reference_program_agrees_with_the_oracle_parameters(tmp_path, name):
+    from oracle import oracle as O
+    bits, tail, src, dst = REF_PROGRAM_CASES[name]
+    w, h = 128, 64
+    px = synth.tiff16_frame(w, h, seed=len(name)) >> (16 - bits)
+    planes_rgb = np.ascontiguousarray(px.transpose(2, 0, 1)).astype(np.uint16)      # .rgb files are planar R, G, B
+    planes_rgb.tofile(tmp_path / "in.rgb")
+    # transfer options first: the reference indexes its transfer table with the argv position (hdr2yuv.cpp:200)
+    argv = [REF_BIN, "--src_filename", "in.rgb", "--dst_filename", "out.yuv"] + tail[:2] + \
+           (tail[2:4] if tail[2] == "--dst_transfer_characteristics" else []) + \
+           ["--src_pic_width", str(w), "--src_pic_height", str(h), "--src_bit_depth", str(bits), "--src_chroma_format_idc", "3"] + \
+           (tail[4:] if tail[2] == "--dst_transfer_characteristics" else tail[2:])
+    rc, text = run(argv, cwd=tmp_path)
+    got = np.fromfile(tmp_path / "out.yuv", np.uint16)
+    planes = np.ascontiguousarray(np.stack([planes_rgb[1], planes_rgb[2], planes_rgb[0]], 0))    # G, B, R
+    want = O.forward(planes, src, dst, backend="port")
+    assert got.size == want.size, (got.size, want.size, text[-800:])
+    assert np.array_equal(got, want), (name, int((got != want).sum()))
+    rc, text = run(argv, cwd=tmp_path)                 # write_yuv appends (tiff.cpp:440)
+    assert np.fromfile(tmp_path / "out.yuv", np.uint16).size == 2 * want.size

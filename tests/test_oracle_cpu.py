@@ -164,3 +164,23 @@ def test_ybar_mode_and_yuvprime2_keyword_vs_reference_binary():
     for res, bd, fr in ((1, 16, 1), (0, 12, 0)):
         dst = dict(bit_depth=bd, full_range=fr, transfer=18, primaries=10, matrix=15, chroma=1, resampler=res)
         assert np.array_equal(O.forward(planes, src, dst, backend="ref"), O.forward(planes, src, dst, backend="port"))
+
+
+@needs_ref
+def test_matrix_convert_float_output_vs_reference():
+    # The F32-output twin of matrix_convert (convert.cpp:1117-1122, 1222-1304): what an .exr / .dpx destination runs on an
+    # integer source (hdr2yuv.cpp:797-823, 935-962).  Restatement == compiled reference, bit for bit, with and without a
+    # transfer change, for every matrix family the branch has.
+    w, h = 96, 40
+    planes = O.load_rgb16(synth.tiff16_frame(w, h, seed=31), 0)
+    for src_tr, dst_tr in ((16, 16), (16, 8), (16, 1), (1, 16)):
+        for m, prim in ((0, 10), (9, 9), (1, 1), (11, 10), (13, 10)):
+            for depth in (16, 32):
+                src = dict(bit_depth=16, full_range=0, transfer=src_tr, primaries=10 if src_tr == 16 else 1, matrix=0)
+                # matrix 0 with other primaries has no branch in the reference ("Can't determine color difference", exit)
+                dst = dict(bit_depth=depth, full_range=0, transfer=dst_tr, primaries=prim if m else src["primaries"], matrix=m)
+                if depth == 32:
+                    continue        # set_pic_clip shifts by bit_depth - 8 = 24 on an unsigned: defined, but Half overflows; not a route
+                a = O.matrix_convert_f32(planes, src, dst, "port")
+                b = O.matrix_convert_f32(planes, src, dst, "ref")
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (src_tr, dst_tr, m, int((a.view(np.uint32) != b.view(np.uint32)).sum()))
