@@ -299,3 +299,24 @@ def test_reference_program_agrees_with_the_oracle_parameters(tmp_path, name):
     assert np.array_equal(got, want), (name, int((got != want).sum()))
     rc, text = run(argv, cwd=tmp_path)                 # write_yuv appends (tiff.cpp:440)
     assert np.fromfile(tmp_path / "out.yuv", np.uint16).size == 2 * want.size
+
+
+@needs_ref_bin
+@pytest.mark.parametrize("declared_bits", [16, 12])
+def test_reference_program_tiff_route_agrees_with_the_oracle(cli, tmp_path, declared_bits):
+    # test.sh:5-16 on the CPU: the reference's own read_tiff (de-interleave, clip on read, header overriding the declared
+    # depth: tiff.cpp:296-304, 322-338) through the oracle's libtiff stand-in, against the restatement's load_rgb16 + forward.
+    # The file comes from this repo's TIFF writer; read_tiff only accepts 1080 or 2160 strips (tiff.cpp:178-180).
+    from oracle import oracle as O
+    w, h = 256, 1080
+    px = synth.tiff16_frame(w, h, seed=21)
+    px.tofile(tmp_path / "t.raw")
+    run([cli["h2y_iotool"], "write-tiff", str(tmp_path / "in.tiff"), str(w), str(h), "3", str(tmp_path / "t.raw")])
+    run([REF_BIN, "--src_filename", "in.tiff", "--dst_filename", "out.yuv", "--src_transfer_characteristics", "16",
+         "--dst_transfer_characteristics", "16", "--src_pic_width", str(w), "--src_pic_height", str(h), "--src_bit_depth", str(declared_bits),
+         "--dst_bit_depth", "10", "--src_chroma_format_idc", "3", "--dst_chroma_format_idc", "1", "--src_matrix_coeffs", "0",
+         "--dst_matrix_coeffs", "9", "--src_colour_primaries", "10", "--dst_colour_primaries", "9", "--chroma_resampler_type", "1"], cwd=tmp_path)
+    got = np.fromfile(tmp_path / "out.yuv", np.uint16)
+    src = dict(bit_depth=16, full_range=0, transfer=16, primaries=10, matrix=0)
+    dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+    assert np.array_equal(got, O.forward(O.load_rgb16(px, 0), src, dst, backend="port"))

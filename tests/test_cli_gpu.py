@@ -148,3 +148,27 @@ def test_dpx_sequence_to_yuv(cli, tmp_path):
         want = O.forward(O.load_dpx10(stored[i], True), src, dst, backend="port")
         d = np.abs(got[i].astype(int) - want.astype(int))
         assert d.max() <= 1 and (d != 0).sum() <= max(2, d.size // 2000), (i, int(d.max()), int((d != 0).sum()), got[i][:8], want[:8])
+
+
+def test_devices_2_shards_the_frame_range(cli, tmp_path):
+    # --devices N: one worker thread per GPU, contiguous frame ranges (sharding.frame_range), every worker writes its frames
+    # at their own offsets of the one .yuv file.  Needs two GPUs (gpurun --gpus 2); the result must equal the one-GPU file.
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    w, h, n = 256, 96, 7
+    for i in range(n):
+        synth.exr_half_frame(w, h, seed=30 + i, channels=3).tofile(tmp_path / "f.raw")
+        run([cli["h2y_iotool"], "write-exr", str(tmp_path / ("shot.%04d.exr" % i)), str(w), str(h), "3", "0", str(tmp_path / "f.raw")])
+    outs = []
+    for devices in (1, 2):
+        out = tmp_path / ("out%d.yuv" % devices)
+        text = run([cli["hdr2yuv"], "--src_filename", str(tmp_path / "shot.0000.exr"), "--dst_filename", str(out), "--src_pic_width", str(w),
+                    "--src_pic_height", str(h), "--src_bit_depth", "16", "--dst_bit_depth", "10", "--src_chroma_format_idc", "3",
+                    "--dst_chroma_format_idc", "1", "--src_matrix_coeffs", "0", "--dst_matrix_coeffs", "9",
+                    "--src_transfer_characteristics", "LINEAR", "--dst_transfer_characteristics", "PQ", "--src_colour_primaries", "1",
+                    "--dst_colour_primaries", "9", "--chroma_resampler_type", "1", "--n_frames", str(n), "--batch_frames", "2",
+                    "--dst_video_full_range_flag", "0", "--devices", str(devices)])
+        outs.append(np.fromfile(out, np.uint16))
+    assert outs[0].size == outs[1].size == n * (w * h * 3 // 2)
+    assert np.array_equal(outs[0], outs[1])

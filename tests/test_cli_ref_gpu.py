@@ -173,8 +173,9 @@ def test_yuv444_to_tiff_matches_reference_program(cli, tmp_path):
 @pytest.mark.parametrize("src_bits", [16, 12])
 def test_tiff_source_matches_reference_program(cli, tmp_path, src_bits):
     # test.sh:5-16: a 16-bit TIFF container declared with --src_bit_depth 12 / 16; read_tiff's clip and its header overrides
-    # (tiff.cpp:296-304, 322-338) are the reference's own here
-    w, h = 256, 96
+    # (tiff.cpp:296-304, 322-338) are the reference's own here.  read_tiff only accepts files of 1080 or 2160 strips
+    # (tiff.cpp:178-180), hence the height.
+    w, h = 256, 1080
     px = synth.tiff16_frame(w, h, seed=21)
     args = ["--src_filename", "in.tiff", "--dst_filename", "out.yuv", "--src_pic_width", str(w), "--src_pic_height", str(h),
             "--src_bit_depth", str(src_bits), "--dst_bit_depth", "10", "--src_chroma_format_idc", "3", "--dst_chroma_format_idc", "1",
