@@ -265,10 +265,17 @@ bool tiff_read(const std::string &path, uint16_t *dst, int crop_w, int crop_h, I
     const size_t row_bytes = (size_t)w * ch * 2;
     std::vector<uint8_t> strip;
     const uint32_t rps = d.rows_per_strip;
+    // every output row must come from a strip that is really there: a short strip table, RowsPerStrip = 0 or byte counts
+    // smaller than the rows they claim would otherwise leave rows of the (uninitialised, pinned) destination as they were
+    if (rps == 0) return fail(err, "TIFF RowsPerStrip is 0");
+    if ((uint64_t)d.offsets.size() * rps < (uint64_t)h) return fail(err, "TIFF strips do not cover the image");
+    if (row_bytes * std::min<uint64_t>(rps, (uint64_t)h) > ((uint64_t)1 << 31)) return fail(err, "TIFF strip too large");
+    int rows_done = 0;
     for (size_t s = 0; s < d.offsets.size(); s++) {
         const int first_row = (int)(s * rps), nrows = std::min<int>((int)rps, h - first_row);
         if (nrows <= 0) break;
         if (first_row + nrows <= y0 || first_row >= y0 + oh) continue;
+        if (s < d.counts.size() && (uint64_t)d.counts[s] < (uint64_t)row_bytes * nrows) return fail(err, "TIFF strip byte count too small");
         strip.resize(row_bytes * nrows);
         if (!r.file.read_at(strip.data(), strip.size(), d.offsets[s])) return fail(err, "short TIFF strip");
         for (int rr = 0; rr < nrows; rr++) {
@@ -278,8 +285,10 @@ bool tiff_read(const std::string &path, uint16_t *dst, int crop_w, int crop_h, I
             uint16_t *o = dst + (size_t)y * ow * ch;
             if (d.big_endian) for (int i = 0; i < ow * ch; i++) o[i] = bswap16(src[i]);
             else memcpy(o, src, (size_t)ow * ch * 2);
+            rows_done++;
         }
     }
+    if (rows_done != oh) return fail(err, "TIFF strips do not cover the image");
     info->width = ow; info->height = oh; info->channels = ch; info->bits = 16; info->is_half = false;
     return true;
 }

@@ -241,6 +241,30 @@ def test_readers_reject_damaged_files(cli, tmp_path):
     rc, text = run([cli["h2y_iotool"], "read-tiff", str(tmp_path / "cut.tiff"), str(out)], check=False)
     assert rc == 1, text
 
+    # a strip table that does not cover the picture, RowsPerStrip = 0, byte counts smaller than the rows they stand for:
+    # no row of the destination may be left as it was (the CLI's destination is uninitialised pinned memory)
+    def tiff_tag_edit(name, tag, count=None, value=None, entry_of_array=None):
+        b = bytearray(tif.read_bytes())
+        for k in range(n):
+            e = ifd + 2 + 12 * k
+            if int.from_bytes(b[e:e + 2], "little") == tag:
+                if count is not None:
+                    b[e + 4:e + 8] = int(count).to_bytes(4, "little")
+                if value is not None:
+                    b[e + 8:e + 12] = int(value).to_bytes(4, "little")
+                if entry_of_array is not None:
+                    arr = int.from_bytes(b[e + 8:e + 12], "little")
+                    b[arr + 4 * entry_of_array[0]:arr + 4 * entry_of_array[0] + 4] = int(entry_of_array[1]).to_bytes(4, "little")
+        p = tmp_path / name
+        p.write_bytes(bytes(b))
+        rc, text = run([cli["h2y_iotool"], "read-tiff", str(p), str(out)], check=False)
+        assert rc == 1, (name, rc, text)
+        return text
+
+    assert "cover" in tiff_tag_edit("short_table.tiff", 273, count=h - 3)
+    assert "RowsPerStrip" in tiff_tag_edit("rps0.tiff", 278, value=0)
+    assert "byte count" in tiff_tag_edit("small_count.tiff", 279, entry_of_array=(5, 10))
+
 
 # ---- the reference's own program (oracle/_ref/hdr2yuv_ref = hdr2yuv.cpp's main() built unmodified) ------------------------
 # The GPU CLI tests hand the oracle the source / destination parameters the test author derived from an argv.  Here that
