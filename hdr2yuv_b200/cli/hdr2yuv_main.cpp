@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -409,6 +410,7 @@ int main(int argc, char *argv[])
     int batch = a.batch_frames > 0 ? a.batch_frames : (int)std::max<size_t>(1, std::min<size_t>(16, (256u << 20) / s.frame_bytes));
     std::vector<int> rc(ndev, 0);
     std::vector<std::thread> workers;
+    const auto t_start = std::chrono::steady_clock::now();
     for (int d = 0; d < ndev; d++) {
         workers.emplace_back([&, d]() {
             int lo = 0, hi = 0;
@@ -417,10 +419,13 @@ int main(int argc, char *argv[])
             h2y_status st = h2y_ctx_create(d, &ctx);
             if (st != H2Y_OK) { printf("ERROR: device %d: %s\n", d, h2y_status_string(st)); rc[d] = 1; return; }
             const int nb = std::min(batch, hi - lo);
-            uint8_t *hin[2], *hout = (uint8_t *)h2y_host_alloc(out_bytes * nb);
-            hin[0] = (uint8_t *)h2y_host_alloc(s.frame_bytes * nb);
-            hin[1] = (uint8_t *)h2y_host_alloc(s.frame_bytes * nb);
-            if (!hin[0] || !hin[1] || !hout) { printf("ERROR: pinned host allocation failed\n"); rc[d] = 1; return; }
+            // three stages overlap: batch k+1 is decoded and batch k-1 is written while batch k is on the GPU
+            uint8_t *hin[2], *hout[2];
+            for (int i = 0; i < 2; i++) {
+                hin[i] = (uint8_t *)h2y_host_alloc(s.frame_bytes * nb);
+                hout[i] = (uint8_t *)h2y_host_alloc(out_bytes * nb);
+            }
+            if (!hin[0] || !hin[1] || !hout[0] || !hout[1]) { printf("ERROR: pinned host allocation failed\n"); rc[d] = 1; return; }
             std::string rerr[2];
             bool rok[2] = {true, true};
             auto load = [&](int slot, int f0, int n) {      // decode with a few threads: file decoding is the host's bottleneck
@@ -434,6 +439,8 @@ int main(int argc, char *argv[])
                 for (int i = 0; i < n; i++) if (!ok[i]) { rok[slot] = false; rerr[slot] = e[i]; }
             };
             int slot = 0;
+            bool wok = true;
+            std::thread writer;
             load(slot, lo, std::min(nb, hi - lo));
             for (int f0 = lo; f0 < hi && rc[d] == 0; f0 += nb) {
                 const int n = std::min(nb, hi - f0);
@@ -441,27 +448,38 @@ int main(int argc, char *argv[])
                 std::thread next;
                 const int nf0 = f0 + nb;
                 if (nf0 < hi) next = std::thread(load, slot ^ 1, nf0, std::min(nb, hi - nf0));     // overlap decode with the GPU
-                st = h2y_forward_host(ctx, &fp, hin[slot], s.frame_bytes, hout, out_bytes, n);
+                st = h2y_forward_host(ctx, &fp, hin[slot], s.frame_bytes, hout[slot], out_bytes, n);
+                if (writer.joinable()) writer.join();                                               // batch k-1 is on disk
                 if (st != H2Y_OK) {
                     printf("%s (h2y_status %d)\n", h2y_status_string(st), (int)st);
                     rc[d] = st == H2Y_ERR_PRECONDITION ? 1 : 2;
-                } else if (!pwrite_all(fd, hout, out_bytes * n, base + (uint64_t)f0 * out_bytes)) {
+                } else if (!wok) {
                     printf("ERROR: write to %s failed\n", a.dst_filename);
                     rc[d] = 1;
-                } else if (a.verbose_level > 0) {
-                    printf("device %d: frames %d..%d converted, %llu kernel launches so far\n", d, f0, f0 + n - 1,
-                           (unsigned long long)h2y_kernel_launches(ctx));
+                } else {
+                    const uint8_t *wsrc = hout[slot];
+                    writer = std::thread([&, wsrc, n, f0]() { wok = pwrite_all(fd, wsrc, out_bytes * n, base + (uint64_t)f0 * out_bytes); });
+                    if (a.verbose_level > 0)
+                        printf("device %d: frames %d..%d converted, %llu kernel launches so far\n", d, f0, f0 + n - 1,
+                               (unsigned long long)h2y_kernel_launches(ctx));
                 }
                 if (next.joinable()) next.join();
                 slot ^= 1;
             }
-            h2y_host_free(hin[0]); h2y_host_free(hin[1]); h2y_host_free(hout);
+            if (writer.joinable()) writer.join();
+            if (!wok && rc[d] == 0) { printf("ERROR: write to %s failed\n", a.dst_filename); rc[d] = 1; }
+            for (int i = 0; i < 2; i++) { h2y_host_free(hin[i]); h2y_host_free(hout[i]); }
             h2y_ctx_destroy(ctx);
         });
     }
     for (auto &t : workers) t.join();
     close(fd);
     for (int d = 0; d < ndev; d++) if (rc[d]) return rc[d];
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     printf("wrote %d frame(s) of %zu bytes to %s\n", nframes, out_bytes, a.dst_filename);
+    // files in, file out, context creation included: the end-to-end figure of this host
+    printf("%d device(s): %.3f s, %.1f frames/s, %.1f Mpixel/s, source %.2f GB/s, destination %.2f GB/s\n", ndev, secs, nframes / secs,
+           (double)nframes * s.width * s.height / secs * 1e-6, (double)nframes * s.frame_bytes / secs * 1e-9,
+           (double)nframes * out_bytes / secs * 1e-9);
     return 0;
 }
