@@ -1,6 +1,9 @@
 // h2y_io.cpp -- see h2y_io.h.  Host-side file decoding only; no pixel arithmetic of the hot path lives here.
 #include "h2y_io.h"
 
+#include <sys/mman.h>
+#include <sys/stat.h>
+
 #include <zlib.h>
 
 #include <algorithm>
@@ -12,13 +15,43 @@ namespace h2yio {
 
 namespace {
 
+// A file opened for reading is mapped: the decoders address it in place (one scanline chunk at a time) instead of
+// paying two system calls and a copy per chunk, which is what bounded the sequence host before (a 4K EXR has 2160 chunks).
 struct File {
     FILE *f = nullptr;
-    explicit File(const std::string &p, const char *mode) { f = fopen(p.c_str(), mode); }
-    ~File() { if (f) fclose(f); }
+    const uint8_t *map = nullptr;
+    size_t map_size = 0;
+    explicit File(const std::string &p, const char *mode)
+    {
+        f = fopen(p.c_str(), mode);
+        if (f && mode[0] == 'r') {
+            struct stat st;
+            if (fstat(fileno(f), &st) == 0 && st.st_size > 0) {
+                void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fileno(f), 0);
+                if (m != MAP_FAILED) { map = (const uint8_t *)m; map_size = (size_t)st.st_size; madvise(m, map_size, MADV_SEQUENTIAL); }
+            }
+        }
+    }
+    ~File()
+    {
+        if (map) munmap(const_cast<uint8_t *>(map), map_size);
+        if (f) fclose(f);
+    }
+    // n bytes at off, in place; nullptr when the range is not inside the file (or the file could not be mapped)
+    const uint8_t *ptr_at(size_t n, uint64_t off) const
+    {
+        if (!map || off > map_size || n > map_size - off) return nullptr;
+        return map + off;
+    }
     bool read_at(void *dst, size_t n, uint64_t off)
     {
-        if (fseeko(f, (off_t)off, SEEK_SET) != 0) return false;
+        if (map) {
+            const uint8_t *p = ptr_at(n, off);
+            if (!p) return false;
+            memcpy(dst, p, n);
+            return true;
+        }
+        if (!f || fseeko(f, (off_t)off, SEEK_SET) != 0) return false;
         return fread(dst, 1, n, f) == n;
     }
 };
@@ -371,6 +404,8 @@ bool exr_read_half(const std::string &path, uint16_t *dst, int out_channels, Ima
     std::vector<uint64_t> table(nblocks);
     if (!f.read_at(table.data(), (size_t)nblocks * 8, h.table_offset)) return fail(err, "short EXR offset table");
     std::vector<uint8_t> packed, raw, lines;
+    const bool bgr_half = out_channels == 3 && h.ch.size() == 3 && h.ch[0].name == "B" && h.ch[1].name == "G" && h.ch[2].name == "R" &&
+                          h.ch[0].type == 1 && h.ch[1].type == 1 && h.ch[2].type == 1;
     for (int b = 0; b < nblocks; b++) {
         int32_t hdr2[2];
         if (!f.read_at(hdr2, 8, table[b])) return fail(err, "bad EXR chunk offset");
@@ -380,14 +415,18 @@ bool exr_read_half(const std::string &path, uint16_t *dst, int out_channels, Ima
         const size_t want = line_bytes * nl;
         // a chunk is stored raw when compression does not make it smaller, so it is never larger than the lines it holds
         if ((size_t)psize > want || (h.compression == 0 && (size_t)psize != want)) return fail(err, "bad EXR chunk size");
-        packed.resize((size_t)psize);
-        if (!f.read_at(packed.data(), packed.size(), table[b] + 8)) return fail(err, "short EXR chunk");
-        const uint8_t *data;
-        if (h.compression == 0 || (size_t)psize == want) data = packed.data();      // stored raw when not smaller
+        const uint8_t *data = f.ptr_at((size_t)psize, table[b] + 8);                // in place when the file is mapped
+        if (!data) {
+            packed.resize((size_t)psize);
+            if (!f.read_at(packed.data(), packed.size(), table[b] + 8)) return fail(err, "short EXR chunk");
+            data = packed.data();
+        }
+        if (h.compression == 0 || (size_t)psize == want) { }                         // stored raw when not smaller
         else {
+            const uint8_t *pk = data;
             raw.resize(want);
             uLongf got = (uLongf)want;
-            if (uncompress(raw.data(), &got, packed.data(), (uLong)psize) != Z_OK || got != want)
+            if (uncompress(raw.data(), &got, pk, (uLong)psize) != Z_OK || got != want)
                 return fail(err, "EXR zlib stream is corrupt");
             exr_unfilter(raw, lines);
             data = lines.data();
@@ -395,6 +434,25 @@ bool exr_read_half(const std::string &path, uint16_t *dst, int out_channels, Ima
         for (int l = 0; l < nl; l++) {
             const uint8_t *p = data + line_bytes * l;
             uint16_t *o = dst + (size_t)(y0 + l) * w * out_channels;
+            if (bgr_half) {
+                // the common file: half B, G, R (alphabetical channel order) -> interleaved r, g, b in one pass
+                const uint16_t *pb = reinterpret_cast<const uint16_t *>(p), *pg = pb + w, *pr = pg + w;
+                int x = 0;
+                if ((reinterpret_cast<uintptr_t>(o) & 7) == 0)
+                    for (; x + 4 <= w; x += 4) {       // four pixels = three 64-bit stores
+                        uint64_t r4, g4, b4;
+                        memcpy(&r4, pr + x, 8); memcpy(&g4, pg + x, 8); memcpy(&b4, pb + x, 8);
+                        const uint64_t r0 = r4 & 0xffff, r1 = (r4 >> 16) & 0xffff, r2 = (r4 >> 32) & 0xffff, r3 = r4 >> 48;
+                        const uint64_t g0 = g4 & 0xffff, g1 = (g4 >> 16) & 0xffff, g2 = (g4 >> 32) & 0xffff, g3 = g4 >> 48;
+                        const uint64_t b0 = b4 & 0xffff, b1 = (b4 >> 16) & 0xffff, b2 = (b4 >> 32) & 0xffff, b3 = b4 >> 48;
+                        uint64_t *o64 = reinterpret_cast<uint64_t *>(o + 3 * x);
+                        o64[0] = r0 | (g0 << 16) | (b0 << 32) | (r1 << 48);
+                        o64[1] = g1 | (b1 << 16) | (r2 << 32) | (g2 << 48);
+                        o64[2] = b2 | (r3 << 16) | (g3 << 32) | (b3 << 48);
+                    }
+                for (; x < w; x++) { o[3 * x] = pr[x]; o[3 * x + 1] = pg[x]; o[3 * x + 2] = pb[x]; }
+                continue;
+            }
             for (size_t c = 0; c < h.ch.size(); c++) {
                 const bool is_half = h.ch[c].type == 1;
                 if (dest[c] >= 0) {

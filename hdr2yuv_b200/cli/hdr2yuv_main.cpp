@@ -407,14 +407,20 @@ int main(int argc, char *argv[])
     const uint64_t base = (uint64_t)lseek(fd, 0, SEEK_END);
 
     const int ndev = std::max(1, std::min(a.devices, nframes));
-    int batch = a.batch_frames > 0 ? a.batch_frames : (int)std::max<size_t>(1, std::min<size_t>(16, (256u << 20) / s.frame_bytes));
+    // frames per h2y_forward_host call = decode threads per device (file decoding is what bounds this host)
+    int batch = a.batch_frames > 0 ? a.batch_frames : (int)std::max<size_t>(1, std::min<size_t>(16, (448u << 20) / s.frame_bytes));
     std::vector<int> rc(ndev, 0);
     std::vector<std::thread> workers;
+    // seconds each device's worker spent decoding (thread body), inside h2y_forward_host, writing (thread body), setting up
+    std::vector<double> t_decode(ndev, 0.0), t_gpu(ndev, 0.0), t_write(ndev, 0.0), t_setup(ndev, 0.0);
+    auto now = []() { return std::chrono::steady_clock::now(); };
+    auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
     const auto t_start = std::chrono::steady_clock::now();
     for (int d = 0; d < ndev; d++) {
         workers.emplace_back([&, d]() {
             int lo = 0, hi = 0;
             h2y_frame_range(d, ndev, nframes, &lo, &hi);
+            const auto t_s = now();
             h2y_ctx *ctx = nullptr;
             h2y_status st = h2y_ctx_create(d, &ctx);
             if (st != H2Y_OK) { printf("ERROR: device %d: %s\n", d, h2y_status_string(st)); rc[d] = 1; return; }
@@ -428,7 +434,9 @@ int main(int argc, char *argv[])
             if (!hin[0] || !hin[1] || !hout[0] || !hout[1]) { printf("ERROR: pinned host allocation failed\n"); rc[d] = 1; return; }
             std::string rerr[2];
             bool rok[2] = {true, true};
+            t_setup[d] = since(t_s);
             auto load = [&](int slot, int f0, int n) {      // decode with a few threads: file decoding is the host's bottleneck
+                const auto t_l = now();
                 rok[slot] = true;
                 std::vector<std::thread> th;
                 std::vector<std::string> e(n);
@@ -437,6 +445,7 @@ int main(int argc, char *argv[])
                     th.emplace_back([&, i]() { ok[i] = read_frame(a, s, f0 + i, hin[slot] + (size_t)i * s.frame_bytes, &e[i]); });
                 for (auto &t : th) t.join();
                 for (int i = 0; i < n; i++) if (!ok[i]) { rok[slot] = false; rerr[slot] = e[i]; }
+                t_decode[d] += since(t_l);
             };
             int slot = 0;
             bool wok = true;
@@ -448,7 +457,9 @@ int main(int argc, char *argv[])
                 std::thread next;
                 const int nf0 = f0 + nb;
                 if (nf0 < hi) next = std::thread(load, slot ^ 1, nf0, std::min(nb, hi - nf0));     // overlap decode with the GPU
+                const auto t_g = now();
                 st = h2y_forward_host(ctx, &fp, hin[slot], s.frame_bytes, hout[slot], out_bytes, n);
+                t_gpu[d] += since(t_g);
                 if (writer.joinable()) writer.join();                                               // batch k-1 is on disk
                 if (st != H2Y_OK) {
                     printf("%s (h2y_status %d)\n", h2y_status_string(st), (int)st);
@@ -458,7 +469,19 @@ int main(int argc, char *argv[])
                     rc[d] = 1;
                 } else {
                     const uint8_t *wsrc = hout[slot];
-                    writer = std::thread([&, wsrc, n, f0]() { wok = pwrite_all(fd, wsrc, out_bytes * n, base + (uint64_t)f0 * out_bytes); });
+                    // one pwrite per frame, side by side: a single writer is bounded by the page cache's per-thread copy rate
+                    writer = std::thread([&, wsrc, n, f0]() {
+                        const auto t_w = now();
+                        std::vector<std::thread> th;
+                        std::vector<char> ok(n, 1);
+                        for (int i = 0; i < n; i++)
+                            th.emplace_back([&, i]() {
+                                ok[i] = pwrite_all(fd, wsrc + (size_t)i * out_bytes, out_bytes, base + (uint64_t)(f0 + i) * out_bytes);
+                            });
+                        for (auto &t : th) t.join();
+                        for (int i = 0; i < n; i++) if (!ok[i]) wok = false;
+                        t_write[d] += since(t_w);
+                    });
                     if (a.verbose_level > 0)
                         printf("device %d: frames %d..%d converted, %llu kernel launches so far\n", d, f0, f0 + n - 1,
                                (unsigned long long)h2y_kernel_launches(ctx));
@@ -481,5 +504,8 @@ int main(int argc, char *argv[])
     printf("%d device(s): %.3f s, %.1f frames/s, %.1f Mpixel/s, source %.2f GB/s, destination %.2f GB/s\n", ndev, secs, nframes / secs,
            (double)nframes * s.width * s.height / secs * 1e-6, (double)nframes * s.frame_bytes / secs * 1e-9,
            (double)nframes * out_bytes / secs * 1e-9);
+    for (int d = 0; d < ndev; d++)
+        printf("device %d: setup %.3f s, decode %.3f s, h2y_forward_host %.3f s, write %.3f s (stages overlap)\n", d, t_setup[d], t_decode[d],
+               t_gpu[d], t_write[d]);
     return 0;
 }
