@@ -528,7 +528,12 @@ def run_gpu(args, wl, name):
                 "h2d_gbs_per_gpu": in_bytes * nf * args.steps / (e2e_ms * 1e-3) / 1e9,
                 "d2h_gbs_per_gpu": out_bytes * nf * args.steps / (e2e_ms * 1e-3) / 1e9,
                 "api": "h2y_forward_host" if wl["kind"] == "forward" else "h2y_inverse_host",
-                "host_output_equals_device_output": host_matches_device, "pcie_copy_ceiling": pcie},
+                "host_output_equals_device_output": host_matches_device, "pcie_copy_ceiling": pcie,
+                # how much of the box's plain-copy ceiling (same ranks, same 2:1 traffic) the API reaches: the end-to-end
+                # curve over N is read against the host side of the box (profiles/r02: 52 / 71 / 71 / 91 GB/s aggregate
+                # H2D at N = 1 / 2 / 4 / 8 whatever the allocation kind, threads or processes, CPU pinning)
+                "frac_of_copy_ceiling": (in_bytes * nf * args.steps / (e2e_ms * 1e-3) / 1e9) / pcie["h2d_gbs_per_gpu"]
+                if pcie and pcie.get("h2d_gbs_per_gpu") else None},
         "gpu_launches": int(launches) * world,
         "clocks": clocks,
     }
