@@ -184,9 +184,11 @@ h2y_status make_pixk(const h2y_pic_desc &in, const h2y_pic_desc &tmp, int out_bi
     else switch (tmp.matrix_coeffs) {
         case H2Y_MATRIX_YDzDx: k->mat_kind = MK_YDZDX; break;
         case H2Y_MATRIX_BT2020nc:
-            k->mat_kind = MK_YCBCR; k->wr = 0.2627; k->wg = 0.6780; k->wb = 0.0593; k->db = 1.8814; k->dr = 1.4746; break;
+            k->mat_kind = MK_YCBCR; k->wr = 0.2627; k->wg = 0.6780; k->wb = 0.0593; k->db = 1.8814; k->dr = 1.4746;
+            k->wri = 2627; k->wgi = 6780; k->wbi = 593; break;
         case H2Y_MATRIX_BT709:
-            k->mat_kind = MK_YCBCR; k->wr = 0.2126; k->wg = 0.7152; k->wb = 0.0722; k->db = 1.8556; k->dr = 1.5748; break;
+            k->mat_kind = MK_YCBCR; k->wr = 0.2126; k->wg = 0.7152; k->wb = 0.0722; k->db = 1.8556; k->dr = 1.5748;
+            k->wri = 2126; k->wgi = 7152; k->wbi = 722; break;
         case H2Y_MATRIX_YDzDx_Y100:
             k->mat_kind = MK_Y100; k->P = -0.5; k->Q = 0.491722; k->RR = 0.5; k->S = -0.49495; break;
         case H2Y_MATRIX_YDzDx_Y500:

@@ -28,6 +28,7 @@ struct PixK {
     // matrix stage
     int mat_kind;
     double wr, wg, wb;   // luma weights (convert.cpp:1177, 1182)
+    int wri, wgi, wbi;   // the same weights as integers / 10000 (both families are four-decimal constants); 0 = not available
     double db, dr;       // chroma divisors 1.8814/1.4746 or 1.8556/1.5748
     double rdb, rdr;     // RN(1/db), RN(1/dr) for the reciprocal fast path
     float P, Q, RR, S;   // Y100/Y500 (convert.cpp:911-925)
@@ -250,7 +251,14 @@ __device__ __forceinline__ bool px_matrix_fast(float G, float B, float R, const 
 __device__ __forceinline__ double u2d(unsigned v) { return __dadd_rn(__hiloint2double(0x43300000, (int)v), -4503599627370496.0); }
 __device__ __forceinline__ float u2f(unsigned v) { return __fadd_rn(__uint_as_float(0x4B000000u | v), -8388608.0f); }   // v < 2^23
 
-template <int MK>
+// FAM: 0 = constants from PixK at run time; 2020 / 709 = the family's constants as immediates (no constant-bank reloads
+// per pixel; the host picks the instantiation whose constants equal PixK's).
+template <int FAM> struct YccFam {
+    static constexpr int WR = FAM == 2020 ? 2627 : 2126, WG = FAM == 2020 ? 6780 : 7152, WB = FAM == 2020 ? 593 : 722;
+    static constexpr double DB = FAM == 2020 ? 1.8814 : 1.8556, DR = FAM == 2020 ? 1.4746 : 1.5748;
+};
+
+template <int MK, int FAM = 0>
 __device__ __forceinline__ bool px_matrix_fast_u16(unsigned g, unsigned b, unsigned r, const PixK &k, unsigned &Y,
                                                    unsigned &Cb, unsigned &Cr)
 {
@@ -258,12 +266,28 @@ __device__ __forceinline__ bool px_matrix_fast_u16(unsigned g, unsigned b, unsig
     bool ok = true;
     int cb, cr;
     if (MK == MK_YCBCR) {
-        const double s = __dadd_rn(__dadd_rn(__dmul_rn(k.wr, u2d(r)), __dmul_rn(k.wg, u2d(g))), __dmul_rn(k.wb, u2d(b)));
-        const float tmpF = __double2float_rn(__dadd_rn(s, 0.5));
+        // tmpF = (float)((wr*R + wg*G) + wb*B + 0.5), the sum in double (convert.cpp:1177).  For integer samples and the
+        // four-decimal weights this is RN_float(N / 10000) with the INTEGER N = wri*R + wgi*G + wbi*B + 5000 < 2^31:
+        // N / 10^4 is at least 1.6e-3 of a float half-ulp away from every float rounding boundary ((2k+1) * 2^(e-24) =
+        // N / (2^4 * 625) has no solution, and |N * 2^(20-e) - 625 (2k+1)| >= 1), i.e. >= 9.5e-11 relative, while both the
+        // reference's three rounded products and two rounded sums and this single rounded product stay within 5e-16.
+        // One integer-to-double conversion and one DMUL replace three conversions, three DMUL and three DADD.
+        float tmpF;
+        if (FAM) {
+            const int n = (int)r * YccFam<FAM>::WR + (int)g * YccFam<FAM>::WG + (int)b * YccFam<FAM>::WB + 5000;
+            tmpF = __double2float_rn(__dmul_rn(u2d((unsigned)n), 1e-4));
+        } else if (k.wri) {
+            const int n = (int)r * k.wri + (int)g * k.wgi + (int)b * k.wbi + 5000;
+            tmpF = __double2float_rn(__dmul_rn(u2d((unsigned)n), 1e-4));
+        } else {
+            const double s = __dadd_rn(__dadd_rn(__dmul_rn(k.wr, u2d(r)), __dmul_rn(k.wg, u2d(g))), __dmul_rn(k.wb, u2d(b)));
+            tmpF = __double2float_rn(__dadd_rn(s, 0.5));
+        }
         // tmpF >= 0.5 here: truncation = floor, taken by a round-toward-zero add of 2^23
         Y = min(__float_as_uint(__fadd_rz(tmpF, 8388608.0f)) & 0x7FFFFFu, k.maxCV);
-        ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(u2f(b), tmpF), k.rdb, MAGICD), cb);
-        ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(u2f(r), tmpF), k.rdr, MAGICD), cr);
+        const double rdb = FAM ? 1.0 / YccFam<FAM>::DB : k.rdb, rdr = FAM ? 1.0 / YccFam<FAM>::DR : k.rdr;
+        ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(u2f(b), tmpF), rdb, MAGICD), cb);
+        ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(u2f(r), tmpF), rdr, MAGICD), cr);
     } else {   // MK_YDZDX on integers: (int)(-G/2.0 + B/2.0 + 0.5) == (B - G + 1) / 2 with C's truncating division
         Y = min(g, k.maxCV);
         const int tb = (int)b - (int)g + 1, tr = (int)r - (int)g + 1;

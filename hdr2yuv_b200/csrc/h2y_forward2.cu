@@ -381,22 +381,32 @@ __device__ __forceinline__ u64 fir_h7_pair(u64 m5, u64 m3, u64 m1, u64 c, u64 p1
 // observable, so this route keeps the general kernel's FP64 colour difference
 // (reciprocal multiply with 14 guard bits, exact division when unsure) and the reference's float operation order
 // in both filters; it shares the ring / register-blocked vertical stage of k_forward_exr420.
-template <int MK>
+template <int MK, int FAM = 0>
 __device__ __forceinline__ void pixels8_u16(const PixK &k, const unsigned g[8], const unsigned b[8], const unsigned r[8],
                                             uint4 &ypack, u64 chroma[8], unsigned &fallbacks)
 {
     unsigned yv[8];
+    // four pixels share one fallback branch (a pixel needs the exact route about once in 4000)
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-        const unsigned gg = g[q], bb = b[q], rr = r[q];         // already clipped on load (packed, in the caller)
-        unsigned Y, Cb, Cr;
-        if (!px_matrix_fast_u16<MK>(gg, bb, rr, k, Y, Cb, Cr)) {
-            px_matrix_exact<MK>((float)gg, (float)bb, (float)rr, k, Y, Cb, Cr);
-            fallbacks++;
+    for (int q0 = 0; q0 < 8; q0 += 4) {
+        unsigned Y[4], Cb[4], Cr[4];
+        bool ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) ok[i] = px_matrix_fast_u16<MK, FAM>(g[q0 + i], b[q0 + i], r[q0 + i], k, Y[i], Cb[i], Cr[i]);   // codes already clipped on load
+        if (!(ok[0] && ok[1] && ok[2] && ok[3])) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (!ok[i]) {
+                    px_matrix_exact<MK>((float)g[q0 + i], (float)b[q0 + i], (float)r[q0 + i], k, Y[i], Cb[i], Cr[i]);
+                    fallbacks++;
+                }
         }
-        yv[q] = Y;
-        // u2f on both planes at once: 2^23 + code as a bit pattern, minus 2^23 (exact)
-        chroma[q] = fadd2(pk(__uint_as_float(0x4B000000u | Cb), __uint_as_float(0x4B000000u | Cr)), pk(-8388608.0f, -8388608.0f));
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            yv[q0 + i] = Y[i];
+            // u2f on both planes at once: 2^23 + code as a bit pattern, minus 2^23 (exact)
+            chroma[q0 + i] = fadd2(pk(__uint_as_float(0x4B000000u | Cb[i]), __uint_as_float(0x4B000000u | Cr[i])), pk(-8388608.0f, -8388608.0f));
+        }
     }
     // write_yuv on luma: >> shift and the range clamp on two packed codes per instruction (Y <= maxCV < 2^16)
     const unsigned keep = (0xffffu >> k.down_shift) * 0x10001u, lo2 = k.loY * 0x10001u, hi2 = k.hiY * 0x10001u;
@@ -415,19 +425,25 @@ __device__ __forceinline__ u64 fir_h7_pair_ref(u64 m5, u64 m3, u64 m1, u64 c, u6
 }
 
 // The same two filters for the warp-autonomous integer kernel: reference operation order on both planes of a {Cb,Cr}
-// pair at once.  Sums and differences are packed (FADD2); every product is a scalar FMUL because ptxas contracts a
-// packed multiply feeding a packed add into one FFMA2 (see h2y_f32x2.cuh), which would drop the product's rounding.
+// pair at once.  The ORDER of the additions is what the reference fixes (every partial sum is rounded); a product may be
+// fused into the addition that consumes it whenever the product itself is exact, because then fma(k, s, t) = RN(t + k*s)
+// is the reference's RN(t + RN(k*s)).  The taps are n/512 and the samples are integers <= 65535 (sums of two <= 131070),
+// so k*s = n*s/512 is exact when n*s < 2^24: true for n = 5, 11, 21, 37, 52, 70 (70 * 131070 = 9.2 M) and for 256 (one
+// sample, a power of two), false for 159 and 228, whose products stay separately rounded multiplications.  (ptxas
+// contracts a packed multiply feeding a packed add into FFMA2 by itself, see h2y_f32x2.cuh, so those two products are
+// scalar FMULs; the 228 product is the first term and feeds an FFMA2 as its addend, which cannot be contracted.)
 // The reference clamps the float to [0, maxCV] and truncates; flooring first (round-down add of 1.5*2^23) and
 // clamping the integers gives the same code for every t, and leaves the bit pattern the callers want.
 __device__ __forceinline__ u64 fmulk2(float kf, u64 v) { return pk(__fmul_rn(kf, plo(v)), __fmul_rn(kf, phi(v))); }
+__device__ __forceinline__ u64 pk1(float v) { return pk(v, v); }
 
 // convert.cpp:305-317; returns the clamped, truncated samples as floats
 __device__ __forceinline__ u64 fir_h7_pair_ord(u64 m5, u64 m3, u64 m1, u64 c, u64 p1, u64 p3, u64 p5, int hi_bits)
 {
-    u64 t = fmulk2(21.0f / 512.0f, fadd2(m5, p5));
-    t = fsub2(t, fmulk2(52.0f / 512.0f, fadd2(m3, p3)));
-    t = fadd2(t, fmulk2(159.0f / 512.0f, fadd2(m1, p1)));
-    t = fadd2(t, fmulk2(256.0f / 512.0f, c));
+    u64 t = fmulk2(21.0f / 512.0f, fadd2(m5, p5));                      // exact
+    t = ffma2(pk1(-52.0f / 512.0f), fadd2(m3, p3), t);                  // RN(t - c52 * s), product exact
+    t = fadd2(t, fmulk2(159.0f / 512.0f, fadd2(m1, p1)));               // product rounded on its own
+    t = ffma2(pk1(256.0f / 512.0f), c, t);                              // product exact
     t = fadd2(t, pk(0.5f, 0.5f));
     const u64 fl = fadd2_rm(t, pk(MAGIC, MAGIC));
     const int a = clamp3(ilo(fl), MAGIC_BITS, hi_bits), b = clamp3(ihi(fl), MAGIC_BITS, hi_bits);
@@ -437,12 +453,12 @@ __device__ __forceinline__ u64 fir_h7_pair_ord(u64 m5, u64 m3, u64 m1, u64 c, u6
 // convert.cpp:365-374, r[0..11] = rows y-5 .. y+6; returns the floor as MAGIC_BITS + n in both halves (not yet clamped)
 __device__ __forceinline__ u64 fir_v12_pair_ord(const u64 r[12])
 {
-    u64 t = fmulk2(228.0f / 512.0f, fadd2(r[5], r[6]));
-    t = fadd2(t, fmulk2(70.0f / 512.0f, fadd2(r[4], r[7])));
-    t = fsub2(t, fmulk2(37.0f / 512.0f, fadd2(r[3], r[8])));
-    t = fsub2(t, fmulk2(21.0f / 512.0f, fadd2(r[2], r[9])));
-    t = fadd2(t, fmulk2(11.0f / 512.0f, fadd2(r[1], r[10])));
-    t = fadd2(t, fmulk2(5.0f / 512.0f, fadd2(r[0], r[11])));
+    u64 t = fmulk2(228.0f / 512.0f, fadd2(r[5], r[6]));                 // rounded on its own (first term)
+    t = ffma2(pk1(70.0f / 512.0f), fadd2(r[4], r[7]), t);               // products exact from here on
+    t = ffma2(pk1(-37.0f / 512.0f), fadd2(r[3], r[8]), t);
+    t = ffma2(pk1(-21.0f / 512.0f), fadd2(r[2], r[9]), t);
+    t = ffma2(pk1(11.0f / 512.0f), fadd2(r[1], r[10]), t);
+    t = ffma2(pk1(5.0f / 512.0f), fadd2(r[0], r[11]), t);
     t = fadd2(t, pk(0.5f, 0.5f));
     return fadd2_rm(t, pk(MAGIC, MAGIC));
 }
@@ -1055,7 +1071,7 @@ static cudaError_t launch_rows_on(K kernel, int grid, size_t smem, cudaStream_t 
 // row it reads the window back and evaluates convert.cpp:365-374 in order.
 constexpr int VSLOTS = 12;
 
-template <int MK, int NCH>
+template <int MK, int NCH, int FAM = 0>
 __global__ void __launch_bounds__(THREADS3, 1) k_forward_u16_420_rows(const Fwd3Args A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1099,27 +1115,27 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_u16_420_rows(const Fwd3
             const int crd = (int)(fCr - fCb);
             int slot = 0;                                            // ring slot of row r; row r - t sits t slots back
 
-            RawPx<NCH> raw, cur;
+            RawPx<NCH> raw;
             load_px8<NCH>(raw, sp, 0, 0, 0);
 #pragma unroll 1
             for (int r = rfirst; r <= rlast; r++) {
-                cur = raw;
-                sp += ((unsigned)r < (unsigned)(h - 1)) ? spitch : 0;               // clamped rows = edge replicate
-                if (r < rlast) load_px8<NCH>(raw, sp, 0, 0, 0);                     // prefetch the next row
                 if (k.clip_on_load) {                                               // read_tiff's clip (tiff.cpp:296-304)
                     const unsigned lo2 = k.loadLo * 0x10001u, hi2 = k.loadHi * 0x10001u;
 #pragma unroll
                     for (int i = 0; i < NCH; i++) {
-                        unsigned *wv = reinterpret_cast<unsigned *>(&cur.v[i]);
+                        unsigned *wv = reinterpret_cast<unsigned *>(&raw.v[i]);
 #pragma unroll
                         for (int j = 0; j < 4; j++) wv[j] = clamp_u16x2(wv[j], lo2, hi2);
                     }
                 }
+                // the codes leave the sample registers first, then the next row is loaded into the same registers: no copy
                 unsigned g[8], b[8], rr[8];
-                split_codes<NCH>(cur, g, b, rr);
+                split_codes<NCH>(raw, g, b, rr);
+                sp += ((unsigned)r < (unsigned)(h - 1)) ? spitch : 0;               // clamped rows = edge replicate
+                if (r < rlast) load_px8<NCH>(raw, sp, 0, 0, 0);                     // prefetch the next row
                 uint4 ypack;
                 u64 ch[8];
-                pixels8_u16<MK>(k, g, b, rr, ypack, ch, fallbacks);
+                pixels8_u16<MK, FAM>(k, g, b, rr, ypack, ch, fallbacks);
                 if (lane_interior && r >= ys && r < ye) *reinterpret_cast<uint4 *>(yp) = ypack;
                 yp += w;
                 float l3x = __shfl_up_sync(0xffffffffu, plo(ch[3]), 1), l3y = __shfl_up_sync(0xffffffffu, phi(ch[3]), 1);
@@ -1289,13 +1305,20 @@ h2y_status launch_forward_u16_420(h2y_ctx_impl *c, const h2y_forward_params &p, 
             while (g3 > 1 && A3.total_rows / ((long)g3 * A3.sub) < 16) g3 >>= 1;   // forced on a tiny batch
             A3.b = a;
             const size_t smem3 = (size_t)WARPS3 * VSLOTS * 64 * sizeof(float4);
-#define LR(MKV, NC)                                                                                                        \
+#define LR(MKV, NC, FAMV)                                                                                                  \
     do {                                                                                                                   \
-        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_u16_420_rows<MKV, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
-        k_forward_u16_420_rows<MKV, NC><<<g3, THREADS3, smem3, st>>>(A3);                                                 \
+        H2Y_CUDA(c, cudaFuncSetAttribute(k_forward_u16_420_rows<MKV, NC, FAMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
+        k_forward_u16_420_rows<MKV, NC, FAMV><<<g3, THREADS3, smem3, st>>>(A3);                                           \
     } while (0)
-            if (k.mat_kind == MK_YCBCR) { if (nch == 3) LR(MK_YCBCR, 3); else LR(MK_YCBCR, 4); }
-            else { if (nch == 3) LR(MK_YDZDX, 3); else LR(MK_YDZDX, 4); }
+            // the two Y'CbCr families get their constants as immediates
+            const int fam = k.mat_kind != MK_YCBCR || c->sw.no_specialised ? 0
+                            : (k.wri == 2627 && k.wgi == 6780 && k.wbi == 593 && k.db == 1.8814 && k.dr == 1.4746 ? 2020
+                               : (k.wri == 2126 && k.wgi == 7152 && k.wbi == 722 && k.db == 1.8556 && k.dr == 1.5748 ? 709 : 0));
+            if (k.mat_kind == MK_YCBCR) {
+                if (fam == 2020) { if (nch == 3) LR(MK_YCBCR, 3, 2020); else LR(MK_YCBCR, 4, 2020); }
+                else if (fam == 709) { if (nch == 3) LR(MK_YCBCR, 3, 709); else LR(MK_YCBCR, 4, 709); }
+                else { if (nch == 3) LR(MK_YCBCR, 3, 0); else LR(MK_YCBCR, 4, 0); }
+            } else { if (nch == 3) LR(MK_YDZDX, 3, 0); else LR(MK_YDZDX, 4, 0); }
 #undef LR
             c->launches++;
             H2Y_CUDA(c, cudaGetLastError());
