@@ -19,6 +19,7 @@ MATRIX_GBR, MATRIX_BT709, MATRIX_BT2020nc, MATRIX_BT2020c = 0, 1, 9, 10
 MATRIX_YDzDx, MATRIX_YDzDx_Y500, MATRIX_YDzDx_Y100, MATRIX_YUVPRIME1, MATRIX_YUVPRIME2 = 11, 12, 13, 14, 15
 LAYOUT_PLANAR_U16, LAYOUT_PLANAR_F32, LAYOUT_RGB16, LAYOUT_RGBA16, LAYOUT_HALF_RGB, LAYOUT_HALF_RGBA = range(6)
 LAYOUT_DPX10_BE, LAYOUT_DPX10_LE = 6, 7
+LAYOUT_DPX16_BE, LAYOUT_DPX16_LE, LAYOUT_DPXF32_BE, LAYOUT_DPXF32_LE = 8, 9, 10, 11
 INV_YDzDx, INV_709, INV_2020, INV_Y100, INV_Y500 = range(5)
 
 
@@ -87,8 +88,11 @@ SYMBOLS = {
                               C.c_int, C.c_void_p]),
     "h2y_forward_host": (C.c_int, [C.c_void_p, C.POINTER(ForwardParams), C.c_void_p, C.c_size_t, C.c_void_p,
                                    C.c_size_t, C.c_int]),
+    "h2y_forward_f32_host": (C.c_int, [C.c_void_p, C.POINTER(ForwardParams), C.c_void_p, C.c_size_t, C.c_void_p,
+                                   C.c_size_t, C.c_int]),
     "h2y_forward_last_stats": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PicStats)]),
     "h2y_forward_last_plan_reuse": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "h2y_pq_codes_to_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "h2y_rgb_frame_bytes": (C.c_size_t, [C.POINTER(InverseParams)]),
     "h2y_inverse": (C.c_int, [C.c_void_p, C.POINTER(InverseParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                               C.c_int, C.c_void_p, C.c_void_p]),

@@ -167,6 +167,12 @@ class Context:
         check(lib().h2y_forward_host(self._h, C.byref(params), _addr(src), ss, _addr(dst), ds, int(nframes)),
               "h2y_forward_host")
 
+    def forward_f32_host(self, params, src, dst, nframes, src_stride=None, dst_stride=None):
+        """F32 destinations (.exr / .dpx outputs): pic_stats -> matrix_convert into float planes G, B, R (h2y_forward_f32_host)."""
+        ss = src_stride or src_frame_bytes(params.src)
+        ds = dst_stride or params.src.width * params.src.height * 12
+        check(lib().h2y_forward_f32_host(self._h, C.byref(params), _addr(src), ss, _addr(dst), ds, int(nframes)), "h2y_forward_f32_host")
+
     def forward_last_plan_reuse(self):
         """(attempted, nframes, nredone) of the last forward call's last group (h2y_forward_last_plan_reuse)."""
         a, n, r = C.c_int(0), C.c_int(0), C.c_int(0)
@@ -177,6 +183,11 @@ class Context:
         out = PicStats()
         check(lib().h2y_forward_last_stats(self._h, frame, C.byref(out)), "h2y_forward_last_stats")
         return out
+
+    def pq_codes_to_linear(self, codes, linear, stream=None):
+        """optional linear-light stage behind the inverse path: PQ10000_f(code / 65535) per u16 sample (h2y_pq_codes_to_linear)."""
+        check(lib().h2y_pq_codes_to_linear(self._h, codes.data_ptr(), int(codes.numel()), linear.data_ptr(), _stream_ptr(stream)),
+              "h2y_pq_codes_to_linear")
 
     def inverse(self, params, yuv, rgb, nframes, invalid=None, yuv_stride=None, rgb_stride=None, stream=None):
         """one yuv2tiff main-loop iteration per frame (yuv2tiff.cpp:278-552), device resident."""

@@ -573,10 +573,11 @@ bool dpx_probe(const std::string &path, ImageInfo *info, std::string *err)
     info->bits = h[803];
     info->channels = 3;
     info->is_half = false;
-    if (info->bits != 10) {
-        char msg[96];
-        snprintf(msg, sizeof(msg), ": dpx packing is %d-bits, only the 10-bit packing is served", info->bits);
-        return fail(err, path + msg);
+    if (info->bits != 10 && info->bits != 16 && info->bits != 32) {     // dpx.cpp:316-341
+        char msg[512];
+        if (info->bits == 12) snprintf(msg, sizeof(msg), " dpx packing of file %s is 12-bit, which is not (yet) supported (although it should be)", path.c_str());
+        else snprintf(msg, sizeof(msg), " dpx packing of file %s is %d-bits, which is not supported", path.c_str(), info->bits);
+        return fail(err, msg);
     }
     if (info->width < 1 || info->height < 1) return fail(err, path + ": bad dpx picture size");
     return true;
@@ -587,8 +588,74 @@ bool dpx_read_words(const std::string &path, uint32_t *dst, ImageInfo *info, std
     if (!dpx_probe(path, info, err)) return false;
     File f(path, "rb");
     if (!f.f) return fail(err, "Cannot open dpx input file " + path);
-    if (!f.read_at(dst, (size_t)info->width * info->height * 4, info->data_offset)) return fail(err, "short read from " + path);
+    const size_t bpp = info->bits == 10 ? 4 : (info->bits == 16 ? 6 : 12);
+    if (!f.read_at(dst, (size_t)info->width * info->height * bpp, info->data_offset)) return fail(err, "short read from " + path);
     return true;
+}
+
+bool dpx_write_float(const std::string &path, const float *g, const float *b, const float *r, int width, int height, std::string *err)
+{
+    File f(path, "wb");
+    if (!f.f) return fail(err, " Cannot open dpx output file " + path);
+    // The header dpx_write_float builds (its INTEL_LE switch is off, so every field is in the machine's order: a
+    // little-endian file whose magic reads "XPDS").  Undefined fields are 0xff, then the defined ones are stored.
+    std::vector<uint8_t> h(2048, 0);
+    static const int undefined[][2] = {{784, 800}, {812, 816}, {852, 892}, {924, 964}, {996, 1036}, {1068, 1108}, {1140, 1180},
+                                       {1212, 1252}, {1284, 1324}, {1408, 1432}, {1620, 1644}, {1712, 1732}, {1920, 1972}, {20, 36}};
+    for (const auto &u : undefined) memset(h.data() + u[0], 0xff, (size_t)(u[1] - u[0]));
+    h[1931] = 0;                                         // byte alignment: defined as 0
+    auto put32 = [&](int off, uint32_t v) { memcpy(h.data() + off, &v, 4); };
+    auto put16 = [&](int off, uint16_t v) { memcpy(h.data() + off, &v, 2); };
+    const uint32_t size = (uint32_t)width * (uint32_t)height * 12u;
+    put32(0, 0x53445058u);                               // magic
+    put32(4, 2048);                                      // image offset
+    memcpy(h.data() + 8, "v2.0", 5);                     // version (sprintf writes the terminator too)
+    put32(16, size + 2048);                              // total file size
+    put32(660, 0xffffffffu);                             // encryption key
+    put16(768, 0); put16(770, 1);                        // orientation, number of elements
+    put32(772, (uint32_t)(int)(short)width); put32(776, (uint32_t)(int)(short)height);
+    put32(780, 1);                                       // data signed
+    h[800] = 50; h[801] = 2; h[802] = 4; h[803] = 32;    // RGB, linear, unspecified colorimetry, 32 bits per element
+    put16(804, 0); put16(806, 0);                        // no packing, no run-length encoding
+    put32(808, 2048); put32(812, 0); put32(816, 0);      // offset to the pixels, no end-of-line / end-of-image padding
+    put32(1424, 0xffffffffu); put32(1428, 0xffffffffu);
+    if (fwrite(h.data(), 1, h.size(), f.f) != h.size()) return fail(err, "write error on " + path);
+    std::vector<float> row((size_t)width * 3);
+    for (int y = 0; y < height; y++) {
+        const size_t o = (size_t)y * width;
+        for (int x = 0; x < width; x++) { row[3 * (size_t)x] = r[o + x]; row[3 * (size_t)x + 1] = g[o + x]; row[3 * (size_t)x + 2] = b[o + x]; }
+        if (fwrite(row.data(), 4, row.size(), f.f) != row.size()) return fail(err, "write error on " + path);
+    }
+    return true;
+}
+
+bool dpx_write_raw(const std::string &path, const void *rgb, int bits, int width, int height, bool big_endian, std::string *err)
+{
+    if (bits != 16 && bits != 32) return fail(err, "dpx_write_raw: bits must be 16 or 32");
+    File f(path, "wb");
+    if (!f.f) return fail(err, "unable to create " + path);
+    std::vector<uint8_t> h(2048, 0);
+    auto put = [&](int off, uint32_t v) {
+        for (int i = 0; i < 4; i++) h[off + i] = (uint8_t)(v >> (big_endian ? 24 - 8 * i : 8 * i));
+    };
+    const size_t bytes = (size_t)width * height * 3 * (bits / 8);
+    memcpy(h.data(), big_endian ? "SDPX" : "XPDS", 4);
+    put(4, 2048);
+    memcpy(h.data() + 8, "V1.0", 4);
+    put(16, 2048 + (uint32_t)bytes);
+    h[770] = big_endian ? 0 : 1; h[771] = big_endian ? 1 : 0;
+    put(772, (uint32_t)width);
+    put(776, (uint32_t)height);
+    h[800] = 50;
+    h[803] = (uint8_t)bits;
+    fwrite(h.data(), 1, h.size(), f.f);
+    const uint8_t *src = static_cast<const uint8_t *>(rgb);
+    const int es = bits / 8;
+    std::vector<uint8_t> out(bytes);
+    for (size_t i = 0; i < bytes / es; i++)              // samples arrive in the machine's (little-endian) order
+        for (int k = 0; k < es; k++) out[i * es + k] = src[i * es + (big_endian ? es - 1 - k : k)];
+    fwrite(out.data(), 1, out.size(), f.f);
+    return ferror(f.f) ? fail(err, "write error on " + path) : true;
 }
 
 bool dpx_write_10bit(const std::string &path, const uint16_t *rgb10, int width, int height, bool big_endian, std::string *err)
@@ -620,6 +687,17 @@ bool dpx_write_10bit(const std::string &path, const uint16_t *rgb10, int width, 
         fwrite(row.data(), 1, row.size(), f.f);
     }
     return ferror(f.f) ? fail(err, "write error on " + path) : true;
+}
+
+bool exr_write_rgba_from_float(const std::string &path, const float *g, const float *b, const float *r, int width, int height,
+                               int compression, std::string *err)
+{
+    std::vector<uint16_t> px((size_t)width * height * 4);
+    for (size_t i = 0; i < (size_t)width * height; i++) {
+        px[4 * i] = float_to_half(r[i]); px[4 * i + 1] = float_to_half(g[i]); px[4 * i + 2] = float_to_half(b[i]);
+        px[4 * i + 3] = 0;                                // write_exr_file leaves alpha at Array2D's zero (exr.cpp:107-124)
+    }
+    return exr_write_half(path, px.data(), width, height, 4, compression, err);
 }
 
 // ---- raw ---------------------------------------------------------------------------------------------

@@ -47,10 +47,20 @@ bool exr_write_half(const std::string &path, const uint16_t *src, int width, int
 
 // --- DPX ------------------------------------------------------------------------------------------------
 // Header fields dpx_read uses: magic (byte order), image offset at byte 4, width / height at 772 / 776, bit size at
-// 803 (dpx.cpp:268-348).  Only the 10-bit packing is served (16-bit and float DPX are refused with a message).
+// 803 (dpx.cpp:268-348).  The three packings dpx_read knows are served: 10-bit packed words (4 bytes per pixel), 16-bit
+// samples (6) and 32-bit floats (12); 12-bit and everything else is refused with dpx_read's message.  info->bits says which.
 bool dpx_probe(const std::string &path, ImageInfo *info, std::string *err);
-// dst: width*height 32-bit words exactly as stored (no byte swap: the layout tells the GPU the order)
+// dst: the pixel payload exactly as stored, width*height*(4|6|12) bytes (no byte swap: the layout tells the GPU the order)
 bool dpx_read_words(const std::string &path, uint32_t *dst, ImageInfo *info, std::string *err);
+// dpx_write_float (dpx.cpp:719-920): a little-endian 32-bit float DPX with that function's 2048-byte header; planes in
+// pic_t.fbuf order G, B, R (planar_float_to_muxed_dpx_buf, common.cpp:32-47, puts R first)
+bool dpx_write_float(const std::string &path, const float *g, const float *b, const float *r, int width, int height, std::string *err);
+// Test helper: 16-bit (bits = 16, u16 samples) or float (bits = 32) DPX with a generic header in either byte order
+bool dpx_write_raw(const std::string &path, const void *rgb, int bits, int width, int height, bool big_endian, std::string *err);
+// float planes G, B, R -> an RGBA half EXR with A = 0, what write_exr_file stores (exr.cpp:99-133; the container is ZIP or
+// uncompressed scanlines here, PIZ there)
+bool exr_write_rgba_from_float(const std::string &path, const float *g, const float *b, const float *r, int width, int height,
+                               int compression, std::string *err);
 // Test helper: a 2048-byte generic header + packed words, like dpx_write_10bit_from_float's (dpx.cpp:554-716).
 bool dpx_write_10bit(const std::string &path, const uint16_t *rgb10, int width, int height, bool big_endian, std::string *err);
 

@@ -73,10 +73,25 @@ int main(int argc, char **argv)
         if (!h2yio::dpx_write_10bit(argv[2], v.data(), w, h, be != 0, &err)) { printf("%s\n", err.c_str()); return 1; }
         return 0;
     }
+    if (argc >= 8 && !strcmp(argv[1], "write-dpx-raw")) {        // write-dpx-raw out.dpx W H BE(0|1) BITS(16|32) rgb.bin (u16 or float R,G,B)
+        const int w = atoi(argv[3]), h = atoi(argv[4]), be = atoi(argv[5]), bits = atoi(argv[6]);
+        std::vector<uint16_t> v;
+        if (!slurp(argv[7], &v, (size_t)w * h * 3 * (bits / 16))) { printf("cannot read %s\n", argv[7]); return 1; }
+        if (!h2yio::dpx_write_raw(argv[2], v.data(), bits, w, h, be != 0, &err)) { printf("%s\n", err.c_str()); return 1; }
+        return 0;
+    }
+    if (argc >= 6 && !strcmp(argv[1], "write-dpx-float")) {      // write-dpx-float out.dpx W H planes.bin (float G, B, R planes)
+        const int w = atoi(argv[3]), h = atoi(argv[4]);
+        std::vector<uint16_t> v;
+        if (!slurp(argv[5], &v, (size_t)w * h * 6)) { printf("cannot read %s\n", argv[5]); return 1; }
+        const float *p = reinterpret_cast<const float *>(v.data());
+        if (!h2yio::dpx_write_float(argv[2], p, p + (size_t)w * h, p + 2 * (size_t)w * h, w, h, &err)) { printf("%s\n", err.c_str()); return 1; }
+        return 0;
+    }
     if (argc >= 4 && !strcmp(argv[1], "read-dpx")) {             // read-dpx in.dpx words.bin: the stored words, as read
         h2yio::ImageInfo info;
         if (!h2yio::dpx_probe(argv[2], &info, &err)) { printf("%s\n", err.c_str()); return 1; }
-        std::vector<uint16_t> v((size_t)info.width * info.height * 2);
+        std::vector<uint16_t> v((size_t)info.width * info.height * (info.bits == 10 ? 2 : (info.bits == 16 ? 3 : 6)));
         if (!h2yio::dpx_read_words(argv[2], reinterpret_cast<uint32_t *>(v.data()), &info, &err)) { printf("%s\n", err.c_str()); return 1; }
         printf("%d %d %d %d\n", info.width, info.height, info.bits, info.big_endian ? 1 : 0);
         return dump(argv[3], v) ? 0 : 1;

@@ -31,8 +31,8 @@ struct TypeInfo { int idx; const char *name; int supported; };
 // served for .yuv sources (matrix_inverse + write_tiff, hdr2yuv.cpp:818-819, 930-933)
 const TypeInfo kInputTypes[] = {{FT_UNDEFINED, "UNDEFINED", 0}, {FT_YUV, "yuv", 1}, {FT_TIFF, "tiff", 1}, {FT_EXR, "exr", 1},
                                 {FT_Y4M, "y4m", 0}, {FT_DPX, "dpx", 1}, {FT_RGB, "rgb", 1}};
-const TypeInfo kOutputTypes[] = {{FT_UNDEFINED, "UNDEFINED", 0}, {FT_YUV, "yuv", 1}, {FT_TIFF, "tiff", 1}, {FT_EXR, "exr", 0},
-                                 {FT_Y4M, "y4m", 0}, {FT_DPX, "dpx", 0}, {FT_RGB, "rgb", 0}};
+const TypeInfo kOutputTypes[] = {{FT_UNDEFINED, "UNDEFINED", 0}, {FT_YUV, "yuv", 1}, {FT_TIFF, "tiff", 1}, {FT_EXR, "exr", 1},
+                                 {FT_Y4M, "y4m", 0}, {FT_DPX, "dpx", 1}, {FT_RGB, "rgb", 1}};      // hdr.h:59-68
 // hdr.h:140-166 (index = transfer_characteristics code)
 const TypeInfo kTransfers[] = {{0, "RESERVED0", 0}, {1, "BT709", 1}, {2, "UNSPECIFIED", 0}, {3, "RESERVED3", 0},
                                {4, "BT470M", 0}, {5, "BT470BG", 0}, {6, "BT601", 1}, {7, "SMPTE240M", 0}, {8, "LINEAR", 1},
@@ -178,7 +178,17 @@ void parse_options(Args *a, int argc, char *argv[])
         printf("WARNING: output file (%s) type extension (%s) idx(%d) is either not recongized or not supported\n", a->dst_filename, ext, a->output_file_type);
         arg_errors++;
     }
-    if (out.bit_depth < 10 || out.bit_depth > 16)
+    if (a->output_file_type == FT_EXR) {                         // hdr2yuv.cpp:412-428
+        if (out.bit_depth != 16 && out.bit_depth != 32) {
+            printf("WARNING: dst bit_depth(%d) must be 16 or 32 bits for float input file type(%s)\n", out.bit_depth, kOutputTypes[a->output_file_type].name);
+            out.bit_depth = out.half_float_flag ? 32 : 16;
+        }
+    } else if (a->output_file_type == FT_DPX) {                  // hdr2yuv.cpp:430-443
+        if (out.bit_depth != 32) {
+            printf("WARNING: dst bit_depth(%d) must be 16 or 32 bits for float input file type(%s)\n", out.bit_depth, kOutputTypes[a->output_file_type].name);
+            out.bit_depth = 32;
+        }
+    } else if (out.bit_depth < 10 || out.bit_depth > 16)
         printf("WARNING: dst bit_depth(%d) outside range [10,16] for integer input file type(%s)\n", out.bit_depth, kOutputTypes[a->output_file_type].name);
 
     printf("src_filename: %s (type: %s) %s\n", a->src_filename, kInputTypes[a->input_file_type].name, kInputTypes[a->input_file_type].supported ? "(SUPPORTED)" : "(NOT SUPPORTED)");
@@ -220,6 +230,14 @@ struct Source {
     int crop_w = 0, crop_h = 0;
 };
 
+// dpx_read's three packings (dpx.cpp:316-341) as source layouts; 16-bit samples read with the half-float flag are halfs
+h2y_layout dpx_layout(const h2yio::ImageInfo &info, int half_flag)
+{
+    if (info.bits == 16) return half_flag ? H2Y_LAYOUT_HALF_RGB : (info.big_endian ? H2Y_LAYOUT_DPX16_BE : H2Y_LAYOUT_DPX16_LE);
+    if (info.bits == 32) return info.big_endian ? H2Y_LAYOUT_DPXF32_BE : H2Y_LAYOUT_DPXF32_LE;
+    return info.big_endian ? H2Y_LAYOUT_DPX10_BE : H2Y_LAYOUT_DPX10_LE;
+}
+
 bool read_frame(const Args &a, const Source &s, int frame, uint8_t *dst, std::string *err)
 {
     uint16_t *d16 = reinterpret_cast<uint16_t *>(dst);
@@ -241,7 +259,9 @@ bool read_frame(const Args &a, const Source &s, int frame, uint8_t *dst, std::st
         const std::string name = h2yio::sequence_name(a.src_filename, a.src_start_frame + frame);
         if (!h2yio::dpx_read_words(name, reinterpret_cast<uint32_t *>(dst), &info, err)) return false;
         if (info.width != s.width || info.height != s.height) { *err = name + ": geometry differs from the first frame"; return false; }
-        if ((info.big_endian ? H2Y_LAYOUT_DPX10_BE : H2Y_LAYOUT_DPX10_LE) != s.layout) { *err = name + ": byte order differs from the first frame"; return false; }
+        if (dpx_layout(info, a.in.half_float_flag) != s.layout) { *err = name + ": packing or byte order differs from the first frame"; return false; }
+        if (s.layout == H2Y_LAYOUT_HALF_RGB && info.big_endian)      // half samples go to the GPU in the machine's order
+            for (size_t i = 0; i < (size_t)s.width * s.height * 3; i++) d16[i] = (uint16_t)((d16[i] >> 8) | (d16[i] << 8));
         return true;
     }
     case FT_RGB:
@@ -306,7 +326,7 @@ int main(int argc, char *argv[])
         if (!h2yio::dpx_probe(first, &info, &err)) { printf(" %s, aborting\n", err.c_str()); return 1; }
         printf(" reading file %s width = %d, height = %d, cineon = 0\n", first.c_str(), info.width, info.height);
         s.width = info.width; s.height = info.height; s.channels = 3;
-        s.layout = info.big_endian ? H2Y_LAYOUT_DPX10_BE : H2Y_LAYOUT_DPX10_LE;
+        s.layout = dpx_layout(info, in.half_float_flag);
         if (in.matrix_coeffs != H2Y_MATRIX_GBR) printf("reading .dpx file (%s):  setting input picture matrix_coef=%d (MATRIX_GBR)", a.src_filename, H2Y_MATRIX_GBR);
         if (in.chroma_format_idc != H2Y_CHROMA_444) printf("reading .dpx file (%s):  setting input picture chroma_format_idc=%d (CHROMA_444)", a.src_filename, H2Y_CHROMA_444);
         if (in.video_full_range_flag != 1) printf("reading .dpx file (%s):  setting input picture video_full_range_flag to 1", a.src_filename);
@@ -373,6 +393,50 @@ int main(int argc, char *argv[])
         return 0;
     }
 
+    if (a.output_file_type == FT_RGB) {          // the reference has no writer for it either (hdr2yuv.cpp:959-960)
+        printf("WARNING: don't know what file type to write to.\n");
+        return 0;
+    }
+    if (a.output_file_type == FT_EXR || a.output_file_type == FT_DPX) {
+        // F32 destinations (hdr2yuv.cpp:826-850, 935-957): an RGB picture, 4:4:4; matrix_convert's F32-output twin is the
+        // whole conversion; the planes go to write_exr_file's RGBA halfs or dpx_write_float's floats
+        if (out.chroma_format_idc != H2Y_CHROMA_444) {
+            printf("WARNING: out is RGB pic: chroma_format_idc(%d) != CHROMA_444 (%d)", out.chroma_format_idc, H2Y_CHROMA_444);
+            out.chroma_format_idc = H2Y_CHROMA_444;
+        }
+        // (the reference also forces out.matrix_coeffs to GBR here, but only after matrix_convert has run with the
+        // user's value, hdr2yuv.cpp:797-823 vs 845-849: the conversion keeps the requested matrix)
+        if (out.matrix_coeffs != H2Y_MATRIX_GBR)
+            printf("WARNING: out is RGB pic: matrix_coeffs(%d) != MATRIX_GBR (%d)", out.matrix_coeffs, H2Y_MATRIX_GBR);
+        fp.dst.chroma_format_idc = H2Y_CHROMA_444;
+        fp.dst.pic_buffer_type = H2Y_PIC_TYPE_F32; fp.dst.layout = H2Y_LAYOUT_PLANAR_F32;
+        h2y_ctx *ctx = nullptr;
+        h2y_status st = h2y_ctx_create(0, &ctx);
+        if (st != H2Y_OK) { printf("ERROR: %s\n", h2y_status_string(st)); return 1; }
+        const size_t npix = (size_t)s.width * s.height, ob = npix * 12;
+        uint8_t *hin = (uint8_t *)h2y_host_alloc(s.frame_bytes);
+        float *hout = (float *)h2y_host_alloc(ob);
+        if (!hin || !hout) { printf("ERROR: pinned host allocation failed\n"); return 1; }
+        for (int i = 0; i < nframes; i++) {
+            if (!read_frame(a, s, i, hin, &err)) { printf("ERROR: %s\n", err.c_str()); return 1; }
+            st = h2y_forward_f32_host(ctx, &fp, hin, s.frame_bytes, hout, ob, 1);
+            if (st == H2Y_ERR_UNSUPPORTED) {
+                printf("ERROR: a float destination needs an integer source here: with a float source the reference sizes its tmp picture at 32 bits "
+                       "and set_pic_clip shifts by 32 (hdr2yuv.cpp:805-808, common.cpp:303-311)\n");
+                return 1;
+            }
+            if (st != H2Y_OK) { printf("%s (h2y_status %d)\n", h2y_status_string(st), (int)st); return st == H2Y_ERR_PRECONDITION ? 1 : 2; }
+            const std::string name = nframes > 1 ? h2yio::sequence_name(a.dst_filename, i) : std::string(a.dst_filename);
+            const bool ok = a.output_file_type == FT_EXR
+                                ? h2yio::exr_write_rgba_from_float(name, hout, hout + npix, hout + 2 * npix, s.width, s.height, 3, &err)
+                                : h2yio::dpx_write_float(name, hout, hout + npix, hout + 2 * npix, s.width, s.height, &err);
+            if (!ok) { printf("%s\n", err.c_str()); return 1; }
+        }
+        h2y_host_free(hin); h2y_host_free(hout);
+        h2y_ctx_destroy(ctx);
+        printf("wrote %d %s frame(s)\n", nframes, a.output_file_type == FT_EXR ? "exr" : "dpx");
+        return 0;
+    }
     if (a.output_file_type == FT_TIFF) {
         // .yuv (4:4:4) -> .tiff: matrix_inverse into a tmp picture of the source depth, write_tiff at the dst depth
         if (s.type != FT_YUV) { printf("ERROR: a .tiff destination needs a .yuv source (matrix_inverse, hdr2yuv.cpp:818-819)\n"); return 1; }

@@ -298,6 +298,7 @@ h2y_status h2y_ctx_destroy(h2y_ctx *c)
     }
     if (c->ev_busy) cudaEventDestroy(c->ev_busy);
     if (c->spec_dev) cudaFree(c->spec_dev);
+    if (c->pq_linear_lut) cudaFree(c->pq_linear_lut);
     if (c->spec_fb) cudaFreeHost(c->spec_fb);
     if (c->pipeline_ready) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_d2h); }
     if (c->h_framek) cudaFreeHost(c->h_framek);
@@ -389,6 +390,8 @@ size_t h2y_src_frame_bytes(const h2y_pic_desc *s)
     case H2Y_LAYOUT_PLANAR_F32: return n * 12;
     case H2Y_LAYOUT_RGBA16: case H2Y_LAYOUT_HALF_RGBA: return n * 8;
     case H2Y_LAYOUT_DPX10_BE: case H2Y_LAYOUT_DPX10_LE: return n * 4;
+    case H2Y_LAYOUT_DPX16_BE: case H2Y_LAYOUT_DPX16_LE: return n * 6;
+    case H2Y_LAYOUT_DPXF32_BE: case H2Y_LAYOUT_DPXF32_LE: return n * 12;
     }
     return 0;
 }
@@ -591,13 +594,24 @@ h2y_status h2y_write_tiff_rows(h2y_ctx *c, const h2y_pic_desc *pic, const void *
                                   (const uint16_t *)d_planes[2], (uint16_t *)d_rgb, sr, (cudaStream_t)stream);
 }
 
+h2y_status h2y_pq_codes_to_linear(h2y_ctx *c, const void *d_codes, size_t n, void *d_linear, void *stream)
+{
+    if (!c || (n && (!d_codes || !d_linear))) return H2Y_ERR_ARG;
+    H2Y_ON_DEVICE(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    h2y_status s = stream_enter(c, st);
+    if (s != H2Y_OK) return s;
+    if ((s = launch_pq_codes_to_linear(c, (const uint16_t *)d_codes, n, (float *)d_linear, st)) != H2Y_OK) return s;
+    return stream_leave(c, st);
+}
+
 // ---- fused forward ------------------------------------------------------------------------------------
 
 static h2y_status forward_validate(const h2y_forward_params *p, h2y_pic_desc *tmp, PixK *k)
 {
     const h2y_pic_desc &s = p->src, &d = p->dst;
     if (s.width < 2 || s.height < 2 || s.width > 16384 || s.height > 16384) return H2Y_ERR_ARG;
-    if (s.layout < H2Y_LAYOUT_PLANAR_U16 || s.layout > H2Y_LAYOUT_DPX10_LE) return H2Y_ERR_ARG;
+    if (s.layout < H2Y_LAYOUT_PLANAR_U16 || s.layout > H2Y_LAYOUT_DPXF32_LE) return H2Y_ERR_ARG;
     if (s.chroma_format_idc != H2Y_CHROMA_444) return H2Y_ERR_PRECONDITION;        // convert.cpp:886-890
     if (d.chroma_format_idc != H2Y_CHROMA_444 && d.chroma_format_idc != H2Y_CHROMA_420 &&
         d.chroma_format_idc != H2Y_CHROMA_422) return H2Y_ERR_ARG;
@@ -1006,6 +1020,74 @@ h2y_status h2y_inverse444_host(h2y_ctx *c, const h2y_pic_desc *in, int out_bit_d
     if (s != H2Y_OK) return s;
     if (h_invalid) H2Y_CUDA(c, cudaMemcpy(h_invalid, d_inv, sizeof(uint32_t) * (size_t)nframes, cudaMemcpyDeviceToHost));
     return H2Y_OK;
+}
+
+// matrix_convert into an F32 picture, one frame (device buffers): unpack -> pic_stats when the transfer changes -> the
+// staged kernel's F32-output twin.  d_out: three float planes G, B, R.
+static h2y_status forward_f32_frame(h2y_ctx *c, const h2y_forward_params *p, const PixK &k, const uint8_t *d_src, float *d_out,
+                                    cudaStream_t st)
+{
+    const int w = p->src.width, h = p->src.height;
+    const size_t n = (size_t)w * h;
+    h2y_status s;
+    void *unp;
+    if ((s = scratch_reserve(c, SCR_UNPACK, n * 3 * 2, &unp)) != H2Y_OK) return s;
+    void *inpl[3];
+    for (int i = 0; i < 3; i++) inpl[i] = (uint8_t *)unp + i * n * 2;
+    if (p->src.layout == H2Y_LAYOUT_PLANAR_U16) {
+        for (int i = 0; i < 3; i++) inpl[i] = (void *)(d_src + i * n * 2);
+    } else if ((s = launch_unpack(c, p->src.layout, w, h, d_src, inpl, k.clip_on_load, k.loadLo, k.loadHi, st)) != H2Y_OK) return s;
+    NormK nk;
+    memset(&nk, 0, sizeof(nk));
+    if (k.convert_transfer) {
+        h2y_pic_desc sp = p->src;
+        sp.pic_buffer_type = H2Y_PIC_TYPE_U16;
+        FrameK *dfk, hf;
+        if ((s = launch_stats_planar(c, sp, inpl, &dfk, st)) != H2Y_OK) return s;
+        H2Y_CUDA(c, cudaMemcpyAsync(&hf, dfk, sizeof(hf), cudaMemcpyDeviceToHost, st));
+        H2Y_CUDA(c, cudaStreamSynchronize(st));
+        for (int i = 0; i < 3; i++) { nk.offset[i] = hf.offset[i]; nk.range[i] = hf.range[i]; }
+    }
+    void *opl[3] = {d_out, d_out + n, d_out + 2 * n};
+    return launch_matrix_convert(c, k, nk, w, h, 0, inpl, 1, opl, st);
+}
+
+h2y_status h2y_forward_f32_host(h2y_ctx *c, const h2y_forward_params *p, const void *h_src, size_t src_stride, void *h_dst,
+                                size_t dst_stride, int nframes)
+{
+    if (!c || !p || !h_src || !h_dst || nframes < 0) return H2Y_ERR_ARG;
+    if (nframes == 0) return H2Y_OK;
+    const h2y_pic_desc &sd = p->src, &dd = p->dst;
+    if (sd.width < 1 || sd.height < 1 || sd.width > 16384 || sd.height > 16384) return H2Y_ERR_ARG;
+    if (sd.chroma_format_idc != H2Y_CHROMA_444 || dd.chroma_format_idc != H2Y_CHROMA_444) return H2Y_ERR_PRECONDITION;   // convert.cpp:886-890
+    if (dd.width != sd.width || dd.height != sd.height) return H2Y_ERR_UNSUPPORTED;
+    if (sd.layout != H2Y_LAYOUT_PLANAR_U16 && sd.layout != H2Y_LAYOUT_RGB16 && sd.layout != H2Y_LAYOUT_RGBA16)
+        return H2Y_ERR_UNSUPPORTED;                        // F32 sources: the tmp depth is 32 and its clip has no defined value
+    if (!depth_ok(sd.bit_depth)) return H2Y_ERR_ARG;
+    const size_t n = (size_t)sd.width * sd.height, inb = h2y_src_frame_bytes(&sd), outb = n * 12;
+    if (src_stride < inb || dst_stride < outb) return H2Y_ERR_ARG;
+    if (dd.bit_depth == 32) {
+        // set_pic_clip on a 32-bit picture (common.cpp:303-311 on x86-64: 1 << 32 == 1, (unsigned short)(1 << 24) == 0):
+        // maxCV and every range limit are 0, so the clamp at convert.cpp:1286-1293 leaves zeros in all three planes
+        for (int f = 0; f < nframes; f++) memset((uint8_t *)h_dst + (size_t)f * dst_stride, 0, outb);
+        return H2Y_OK;
+    }
+    h2y_pic_desc tmp = dd;
+    tmp.chroma_format_idc = H2Y_CHROMA_444;
+    tmp.pic_buffer_type = H2Y_PIC_TYPE_F32;
+    tmp.layout = H2Y_LAYOUT_PLANAR_F32;
+    PixK k;
+    h2y_status s = make_pixk(sd, tmp, tmp.bit_depth, dd.video_full_range_flag, p->clip_on_load, &k);
+    if (s != H2Y_OK) return s;
+    H2Y_ON_DEVICE(c);
+    return run_pipeline(c, (const uint8_t *)h_src, src_stride, inb, (uint8_t *)h_dst, dst_stride, outb, nframes,
+                        [&](uint8_t *di, size_t ip, uint8_t *dob, size_t op, int nf, cudaStream_t st) {
+                            for (int f = 0; f < nf; f++) {
+                                h2y_status r = forward_f32_frame(c, p, k, di + (size_t)f * ip, (float *)(dob + (size_t)f * op), st);
+                                if (r != H2Y_OK) return r;
+                            }
+                            return H2Y_OK;
+                        });
 }
 
 }   // extern "C"

@@ -275,7 +275,7 @@ __device__ __forceinline__ bool px_matrix_fast_u16(unsigned g, unsigned b, unsig
         float tmpF;
         if (FAM) {
             const int n = (int)r * YccFam<FAM>::WR + (int)g * YccFam<FAM>::WG + (int)b * YccFam<FAM>::WB + 5000;
-            tmpF = __double2float_rn(__dmul_rn(u2d((unsigned)n), 1e-4));
+            tmpF = __double2float_rn(__dmul_rn(__int2double_rn(n), 1e-4));
         } else if (k.wri) {
             const int n = (int)r * k.wri + (int)g * k.wgi + (int)b * k.wbi + 5000;
             tmpF = __double2float_rn(__dmul_rn(u2d((unsigned)n), 1e-4));
@@ -286,8 +286,9 @@ __device__ __forceinline__ bool px_matrix_fast_u16(unsigned g, unsigned b, unsig
         // tmpF >= 0.5 here: truncation = floor, taken by a round-toward-zero add of 2^23
         Y = min(__float_as_uint(__fadd_rz(tmpF, 8388608.0f)) & 0x7FFFFFu, k.maxCV);
         const double rdb = FAM ? 1.0 / YccFam<FAM>::DB : k.rdb, rdr = FAM ? 1.0 / YccFam<FAM>::DR : k.rdr;
-        ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(u2f(b), tmpF), rdb, MAGICD), cb);
-        ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(u2f(r), tmpF), rdr, MAGICD), cr);
+        const float bf = FAM ? __uint2float_rn(b) : u2f(b), rf = FAM ? __uint2float_rn(r) : u2f(r);     // exact either way
+        ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(bf, tmpF), rdb, MAGICD), cb);
+        ok &= trunc_from_magic(__fma_rz((double)__fsub_rn(rf, tmpF), rdr, MAGICD), cr);
     } else {   // MK_YDZDX on integers: (int)(-G/2.0 + B/2.0 + 0.5) == (B - G + 1) / 2 with C's truncating division
         Y = min(g, k.maxCV);
         const int tb = (int)b - (int)g + 1, tr = (int)r - (int)g + 1;

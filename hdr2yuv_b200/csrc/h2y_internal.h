@@ -104,6 +104,7 @@ struct h2y_ctx_impl {
     int last_is_float;
     int last_spec;                      // the last group of the last h2y_forward call took the single-pass route
     int last_groups;                    // 256-frame groups of the last h2y_forward call (h2y_forward_last_stats)
+    float *pq_linear_lut;               // PQ10000_f per 16-bit code (h2y_pq_codes_to_linear), built on first use
 };
 // fork / join of the context's auxiliary streams around kernels that convert disjoint frames (h2y_api.cu)
 h2y_status aux_fork(h2y_ctx_impl *c, cudaStream_t st);     // record the fork point on st (idempotent until aux_join)
@@ -139,7 +140,7 @@ void clip_of(int bit_depth, int full_range, h2y_clip_limits *c);
 
 inline bool layout_is_planar(int l) { return l == H2Y_LAYOUT_PLANAR_U16 || l == H2Y_LAYOUT_PLANAR_F32; }
 inline bool layout_is_half(int l) { return l == H2Y_LAYOUT_HALF_RGB || l == H2Y_LAYOUT_HALF_RGBA; }
-inline bool layout_is_dpx(int l) { return l == H2Y_LAYOUT_DPX10_BE || l == H2Y_LAYOUT_DPX10_LE; }
+inline bool layout_is_dpx(int l) { return l >= H2Y_LAYOUT_DPX10_BE && l <= H2Y_LAYOUT_DPXF32_LE; }
 inline int layout_channels(int l) { return (l == H2Y_LAYOUT_RGBA16 || l == H2Y_LAYOUT_HALF_RGBA) ? 4 : 3; }
 
 // ---- launchers (h2y_stats.cu) ----------------------------------------------------------------
@@ -173,6 +174,7 @@ h2y_status launch_yuvprime2_420(h2y_ctx_impl *c, const uint16_t *const d_in[3], 
                                 int w, int h, int resampler, unsigned maxCV, cudaStream_t st);
 h2y_status launch_out_clamp(h2y_ctx_impl *c, uint16_t *d_plane, size_t n, int shift, unsigned lo, unsigned hi,
                             cudaStream_t st);
+h2y_status launch_pq_codes_to_linear(h2y_ctx_impl *c, const uint16_t *d_codes, size_t n, float *d_linear, cudaStream_t st);
 h2y_status launch_upsample(h2y_ctx_impl *c, const uint16_t *d_src, uint16_t *d_dst, uint16_t *d_mid, int w, int h,
                            int fir, unsigned minCV, unsigned maxCV, cudaStream_t st);
 

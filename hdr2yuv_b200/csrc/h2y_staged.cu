@@ -146,10 +146,57 @@ k_unpack_dpx10(long npix, const unsigned *__restrict__ src, int big_endian, floa
     b[i] = __double2float_rn(__ddiv_rn((double)bb, 1023.0));
 }
 
+// 16-bit DPX: interleaved R,G,B u16 in file byte order -> float planes, sample = code / 65535.0 with the double division
+// rounded to float as dpx_read's assignment does (dpx.cpp:478-494)
+__global__ void __launch_bounds__(256)
+k_unpack_dpx16(long npix, const uint16_t *__restrict__ src, int big_endian, float *__restrict__ g, float *__restrict__ b,
+               float *__restrict__ r)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    unsigned v[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        v[c] = src[3 * i + c];
+        if (big_endian) v[c] = ((v[c] & 0xffu) << 8) | (v[c] >> 8);
+    }
+    r[i] = __double2float_rn(__ddiv_rn((double)v[0], 65535.0));
+    g[i] = __double2float_rn(__ddiv_rn((double)v[1], 65535.0));
+    b[i] = __double2float_rn(__ddiv_rn((double)v[2], 65535.0));
+}
+
+// 32-bit float DPX: interleaved R,G,B floats in file byte order, taken as they are (dpx.cpp:412-443)
+__global__ void __launch_bounds__(256)
+k_unpack_dpxf32(long npix, const unsigned *__restrict__ src, int big_endian, float *__restrict__ g, float *__restrict__ b,
+                float *__restrict__ r)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    unsigned v[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        v[c] = __ldg(src + 3 * i + c);
+        if (big_endian) v[c] = __byte_perm(v[c], 0, 0x0123);
+    }
+    r[i] = __uint_as_float(v[0]); g[i] = __uint_as_float(v[1]); b[i] = __uint_as_float(v[2]);
+}
+
 h2y_status launch_unpack(h2y_ctx_impl *c, int layout, int w, int h, const void *d_src, void *const d_planes[3],
                          int clip_on_load, unsigned lo, unsigned hi, cudaStream_t st)
 {
     const long npix = (long)w * h;
+    if (layout == H2Y_LAYOUT_DPX16_BE || layout == H2Y_LAYOUT_DPX16_LE || layout == H2Y_LAYOUT_DPXF32_BE || layout == H2Y_LAYOUT_DPXF32_LE) {
+        const int grid = (int)((npix + 255) / 256);
+        if (layout == H2Y_LAYOUT_DPX16_BE || layout == H2Y_LAYOUT_DPX16_LE)
+            k_unpack_dpx16<<<grid, 256, 0, st>>>(npix, (const uint16_t *)d_src, layout == H2Y_LAYOUT_DPX16_BE, (float *)d_planes[0],
+                                                 (float *)d_planes[1], (float *)d_planes[2]);
+        else
+            k_unpack_dpxf32<<<grid, 256, 0, st>>>(npix, (const unsigned *)d_src, layout == H2Y_LAYOUT_DPXF32_BE, (float *)d_planes[0],
+                                                  (float *)d_planes[1], (float *)d_planes[2]);
+        c->launches++;
+        H2Y_CUDA(c, cudaGetLastError());
+        return H2Y_OK;
+    }
     if (layout_is_dpx(layout)) {
         k_unpack_dpx10<<<(int)((npix + 255) / 256), 256, 0, st>>>(npix, (const unsigned *)d_src, layout == H2Y_LAYOUT_DPX10_BE,
                                                                    (float *)d_planes[0], (float *)d_planes[1], (float *)d_planes[2]);
@@ -312,6 +359,49 @@ h2y_status launch_out_clamp(h2y_ctx_impl *c, uint16_t *d_plane, size_t n, int sh
 {
     if (n == 0) return H2Y_OK;
     k_out_clamp<<<(int)((n + 255) / 256), 256, 0, st>>>(d_plane, n, shift, lo, hi);
+    c->launches++;
+    H2Y_CUDA(c, cudaGetLastError());
+    return H2Y_OK;
+}
+
+// ---- optional linear-light stage behind the inverse path: PQ10000_f per 16-bit code --------------
+__global__ void __launch_bounds__(256) k_build_pq_linear_lut(float *lut)
+{
+    const unsigned code = blockIdx.x * blockDim.x + threadIdx.x;
+    lut[code] = tf_pq_eotf(__fdiv_rn((float)code, 65535.0f));                 // convert.cpp:1017-1019 with floor 0, ceiling 65535
+}
+
+// eight codes per thread: one 16-byte load, two 16-byte stores; the 256 KB table stays in L1 / L2
+__global__ void __launch_bounds__(256) k_pq_codes_to_linear(const uint16_t *__restrict__ codes, size_t n, const float *__restrict__ lut,
+                                                            float *__restrict__ out)
+{
+    const size_t nvec = n / 8;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+        const uint4 c = __ldg(reinterpret_cast<const uint4 *>(codes) + v);
+        const unsigned w[4] = {c.x, c.y, c.z, c.w};
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { f[2 * i] = __ldg(lut + (w[i] & 0xffffu)); f[2 * i + 1] = __ldg(lut + (w[i] >> 16)); }
+        float4 *o = reinterpret_cast<float4 *>(out) + 2 * v;
+        o[0] = make_float4(f[0], f[1], f[2], f[3]);
+        o[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (unsigned)(n - nvec * 8)) out[nvec * 8 + threadIdx.x] = __ldg(lut + codes[nvec * 8 + threadIdx.x]);
+}
+
+h2y_status launch_pq_codes_to_linear(h2y_ctx_impl *c, const uint16_t *d_codes, size_t n, float *d_linear, cudaStream_t st)
+{
+    if (n == 0) return H2Y_OK;
+    if (!c->pq_linear_lut) {
+        H2Y_CUDA(c, cudaMalloc(&c->pq_linear_lut, 65536 * sizeof(float)));
+        k_build_pq_linear_lut<<<256, 256, 0, st>>>(c->pq_linear_lut);
+        c->launches++;
+    }
+    const bool vec = (((uintptr_t)d_codes | (uintptr_t)d_linear) & 15) == 0;
+    if (!vec) return H2Y_ERR_ARG;                                        // both buffers 16-byte aligned
+    const size_t want = (n / 8 + 255) / 256;
+    const int blocks = (int)(want < (size_t)(16 * c->sm_count) ? (want ? want : 1) : (size_t)(16 * c->sm_count));
+    k_pq_codes_to_linear<<<blocks, 256, 0, st>>>(d_codes, n, c->pq_linear_lut, d_linear);
     c->launches++;
     H2Y_CUDA(c, cudaGetLastError());
     return H2Y_OK;

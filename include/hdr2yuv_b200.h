@@ -68,7 +68,15 @@ typedef enum h2y_layout {
     /* one 32-bit word per pixel as a 10-bit DPX file stores it, R[31:22] G[21:12] B[11:2] (dpx.cpp:506-531), in the
      * file's byte order (big-endian "SDPX", little-endian "XPDS").  The picture is F32: sample = code / 1023.0 */
     H2Y_LAYOUT_DPX10_BE = 6,
-    H2Y_LAYOUT_DPX10_LE = 7
+    H2Y_LAYOUT_DPX10_LE = 7,
+    /* 16-bit DPX: interleaved R,G,B u16 in the file's byte order; the picture is F32, sample = code / 65535.0
+     * (dpx.cpp:478-494).  (A 16-bit DPX read with the half-float flag, dpx.cpp:454-477, is H2Y_LAYOUT_HALF_RGB after a
+     * byte swap on the host.) */
+    H2Y_LAYOUT_DPX16_BE = 8,
+    H2Y_LAYOUT_DPX16_LE = 9,
+    /* 32-bit float DPX: interleaved R,G,B IEEE floats in the file's byte order, taken as they are (dpx.cpp:412-443) */
+    H2Y_LAYOUT_DPXF32_BE = 10,
+    H2Y_LAYOUT_DPXF32_LE = 11
 } h2y_layout;
 
 /* The fields of pic_t (hdr.h:359-392) the hot path reads. */
@@ -267,6 +275,26 @@ h2y_status h2y_inverse(h2y_ctx *ctx, const h2y_inverse_params *params, const voi
 h2y_status h2y_inverse_host(h2y_ctx *ctx, const h2y_inverse_params *params, const void *h_yuv,
                             size_t yuv_stride_bytes, void *h_rgb, size_t rgb_stride_bytes, int nframes,
                             uint32_t *h_invalid_pixels);
+
+/* F32 destinations (.exr / .dpx outputs, hdr2yuv.cpp:797-823, 935-962): pic_stats -> matrix_convert into an F32 picture
+ * (convert.cpp:1117-1122, 1222-1304), frame after frame through the pinned H2D / compute / D2H pipeline.  h_dst receives
+ * three float planes G, B, R per frame (pic_t.fbuf order), 12 bytes per pixel.  dst->bit_depth is the tmp picture's depth
+ * for an integer source (hdr2yuv.cpp:805-808): 16 is the one value for which the reference's result is defined (an .exr
+ * destination); 32 (what parse_options forces for a .dpx destination, hdr2yuv.cpp:436-446) makes set_pic_clip shift by
+ * 32 and 24 (common.cpp:303-311), which on x86-64 leaves maxCV = 0 and every clip limit 0, so matrix_convert's clamp
+ * (convert.cpp:1286-1293) writes an all-zero picture: that is reproduced.  F32 sources return H2Y_ERR_UNSUPPORTED (their
+ * tmp depth is the source's 32 with a U16-style clip that has no defined value). */
+h2y_status h2y_forward_f32_host(h2y_ctx *ctx, const h2y_forward_params *params, const void *h_src, size_t src_stride_bytes,
+                                void *h_dst, size_t dst_stride_bytes, int nframes);
+
+/* Optional linear-light stage behind the inverse path (SURVEY.md 8a note N2).  yuv2tiff stops at PQ-coded 16-bit
+ * integers (yuv2tiff.cpp:535-552; the reference leaves linearisation to an external CTL step, README.md:113).  The in-repo
+ * definition of that step is PQ10000_f (convert.cpp:43-51) on the code normalised as convert.cpp:1017-1019 does with
+ * floor 0 and ceiling 65535:  linear = PQ10000_f((float)code / 65535.0f), in units of 10 000 cd/m2.  d_codes: n u16
+ * samples in any layout (e.g. the interleaved RGB rows h2y_inverse wrote); d_linear: n floats in the same order.
+ * The function is tabulated per 16-bit code in FP64 (once per context) and gathered: within 1 float ulp of the double
+ * evaluation, far inside the 1e-5 relative tolerance the path states. */
+h2y_status h2y_pq_codes_to_linear(h2y_ctx *ctx, const void *d_codes, size_t n, void *d_linear, void *stream);
 
 #ifdef __cplusplus
 }

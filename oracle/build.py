@@ -7,7 +7,7 @@
   oracle/_ref/yuv2tiff_ref the reference's whole yuv2tiff.cpp program.
   oracle/_ref/hdr2yuv_ref  the reference's whole hdr2yuv program: its own main() / parse_options() / read_file()
                            (hdr2yuv.cpp) linked with the same convert/common/tiff objects and ref_io_stubs.cpp
-                           (the EXR / DPX codecs, which need OpenEXR, abort when reached).  The CLI tests
+                           and the reference's own dpx.cpp (the EXR codec, which needs OpenEXR, stops when reached).  The CLI tests
                            byte-compare hdr2yuv_b200/cli/bin/hdr2yuv with it on .rgb / .yuv / .tiff sources.
 
 The two reference sources that include "/usr/local/include/tiffio.h" by absolute path
@@ -87,6 +87,10 @@ def build_ref(force=False):
     tiff_obj = os.path.join(OUT_REF, "tiff.o")
     _compile_via_sed("tiff.cpp", tiff_obj)
     objs.append(tiff_obj)
+    # the reference's DPX codec, unmodified; its three OpenEXR includes resolve to oracle/stub (a stand-in for `half`)
+    dpx_obj = os.path.join(OUT_REF, "dpx.o")
+    _run(["g++"] + CFLAGS + ["-w", "-I" + os.path.join(HERE, "stub"), "-I" + REF] + LEGACY_INCLUDES + ["-c", os.path.join(REF, "dpx.cpp"), "-o", dpx_obj])
+    objs.append(dpx_obj)
     shim_obj = os.path.join(OUT_REF, "ref_shim.o")
     _run(["g++"] + CFLAGS + ["-w", "-I" + REF] + LEGACY_INCLUDES + ["-c", shim, "-o", shim_obj])
     objs.append(shim_obj)

@@ -280,6 +280,20 @@ def load_dpx10(words, big_endian):
     return np.stack([(c.astype(np.float64) / 1023.0).astype(np.float32) for c in (gg, bb, rr)], 0)
 
 
+def load_dpx16(samples, big_endian):
+    """16-bit DPX (dpx.cpp:478-494): (H,W,3) stored u16 R,G,B samples in file byte order -> (3,H,W) float32 planes G,B,R with
+    sample = code / 65535.0 (double division rounded to float by the assignment)."""
+    v = np.ascontiguousarray(samples).view(np.dtype(">u2") if big_endian else np.dtype("<u2")).astype(np.float64)
+    f = (v / 65535.0).astype(np.float32)
+    return np.ascontiguousarray(np.stack([f[..., 1], f[..., 2], f[..., 0]], 0))
+
+
+def load_dpxf32(samples, big_endian):
+    """32-bit float DPX (dpx.cpp:412-443): (H,W,3) stored floats R,G,B in file byte order, taken as they are."""
+    f = np.ascontiguousarray(samples).view(np.dtype(">f4") if big_endian else np.dtype("<f4")).astype(np.float32)
+    return np.ascontiguousarray(np.stack([f[..., 1], f[..., 2], f[..., 0]], 0))
+
+
 def yuv2tiff(yuv, w, h, bit_depth=12, matrix=INV_YDZDX, fir=True, full_range=False, alpha=False, backend="port", ybar=False):
     """One 4:2:0 frame (flat u16 Y,Cb,Cr) -> (H,W,3|4) interleaved RGB16.  Returns (rgb, invalid_pixels)."""
     yuv = np.ascontiguousarray(yuv, np.uint16)

@@ -177,12 +177,12 @@ def test_dpx_10bit_reader_and_dump(cli, tmp_path, big_endian):
                    "--src_transfer_characteristics", "8", "--dst_transfer_characteristics", "16", "--dump_input", str(dump)] + size + BASE)
     assert np.array_equal(np.fromfile(dump, np.uint8), raw[2048:]), text
     assert "layout %d" % (6 if big_endian else 7) in text
-    # a 16-bit DPX is refused with a message, like every packing dpx_read does not know
+    # a 12-bit DPX is refused with dpx_read's message, like every packing it does not know (dpx.cpp:333-338)
     bad = raw.copy(); bad[803] = 12
     bad.tofile(tmp_path / "bad.dpx")
     rc, text = run([cli["hdr2yuv"], "--src_filename", str(tmp_path / "bad.dpx"), "--dst_filename", str(tmp_path / "o.yuv"),
                     "--dump_input", str(dump)] + size + BASE, check=False)
-    assert rc != 0 and "12-bits" in text
+    assert rc != 0 and "12-bit" in text
 
 
 def test_readers_reject_damaged_files(cli, tmp_path):
@@ -344,3 +344,67 @@ def test_reference_program_tiff_route_agrees_with_the_oracle(cli, tmp_path, decl
     src = dict(bit_depth=16, full_range=0, transfer=16, primaries=10, matrix=0)
     dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
     assert np.array_equal(got, O.forward(O.load_rgb16(px, 0), src, dst, backend="port"))
+
+
+@needs_ref_bin
+def test_dpx_float_writer_equals_the_reference_programs_file(cli, tmp_path):
+    # An .rgb -> .dpx run of the reference program (its own dpx_write_float, dpx.cpp:719-920) leaves a float DPX whose
+    # picture is all zero: parse_options forces the destination depth to 32 (hdr2yuv.cpp:436-446) and set_pic_clip then
+    # shifts by 32 and 24 (common.cpp:303-311), so every clip limit is 0 on x86-64 and matrix_convert's clamp
+    # (convert.cpp:1286-1293) zeroes the planes.  This host's writer must produce the same bytes from the same planes.
+    w, h = 64, 32
+    px = synth.tiff16_frame(w, h, seed=4)
+    np.ascontiguousarray(px.transpose(2, 0, 1)).tofile(tmp_path / "in.rgb")
+    run([REF_BIN, "--src_filename", "in.rgb", "--dst_filename", "ref.dpx", "--src_transfer_characteristics", "16", "--src_pic_width", str(w),
+         "--src_pic_height", str(h), "--src_bit_depth", "16", "--src_chroma_format_idc", "3", "--src_matrix_coeffs", "0",
+         "--src_colour_primaries", "9"], cwd=tmp_path)
+    ref = (tmp_path / "ref.dpx").read_bytes()
+    assert len(ref) == 2048 + w * h * 12 and not any(ref[2048:])
+    np.zeros((3, h, w), np.float32).tofile(tmp_path / "planes.bin")
+    run([cli["h2y_iotool"], "write-dpx-float", str(tmp_path / "ours.dpx"), str(w), str(h), str(tmp_path / "planes.bin")])
+    assert (tmp_path / "ours.dpx").read_bytes() == ref
+    # and with real content the pixel section is R, G, B interleaved little-endian floats from the G, B, R planes
+    planes = np.random.default_rng(2).random((3, h, w), dtype=np.float32)
+    planes.tofile(tmp_path / "planes.bin")
+    run([cli["h2y_iotool"], "write-dpx-float", str(tmp_path / "ours2.dpx"), str(w), str(h), str(tmp_path / "planes.bin")])
+    b = (tmp_path / "ours2.dpx").read_bytes()
+    assert b[:2048] == ref[:2048]
+    got = np.frombuffer(b[2048:], "<f4").reshape(h, w, 3)
+    assert np.array_equal(got, np.stack([planes[2], planes[0], planes[1]], -1))
+
+
+@needs_ref_bin
+@pytest.mark.parametrize("bits,big_endian", [(16, 0), (16, 1), (32, 0), (32, 1), (10, 1)])
+def test_reference_program_reads_our_dpx_files_like_the_oracle(cli, tmp_path, bits, big_endian):
+    # The reference's own dpx_read (dpx.cpp:208-547, built unmodified with a stand-in for OpenEXR's half) reads the DPX
+    # files this repo's tools write, and its whole program turns them into the .yuv the restatement predicts from the
+    # Python loaders (oracle.load_dpx10 / load_dpx16 / load_dpxf32): pins those loaders, which the GPU layout tests use.
+    from oracle import oracle as O
+    w, h = 64, 32
+    rng = np.random.default_rng(bits + big_endian)
+    if bits == 10:
+        c = rng.integers(0, 1024, (h, w, 3), dtype=np.uint16)
+        c.tofile(tmp_path / "c.raw")
+        run([cli["h2y_iotool"], "write-dpx", str(tmp_path / "in.dpx"), str(w), str(h), str(big_endian), str(tmp_path / "c.raw")])
+        c32 = c.astype(np.uint32)
+        planes = O.load_dpx10(((c32[..., 0] << 22) | (c32[..., 1] << 12) | (c32[..., 2] << 2)).astype(">u4" if big_endian else "<u4"), bool(big_endian))
+    elif bits == 16:
+        c = rng.integers(0, 65536, (h, w, 3), dtype=np.uint16)
+        c.tofile(tmp_path / "c.raw")
+        run([cli["h2y_iotool"], "write-dpx-raw", str(tmp_path / "in.dpx"), str(w), str(h), str(big_endian), "16", str(tmp_path / "c.raw")])
+        planes = O.load_dpx16(c.astype(">u2" if big_endian else "<u2"), bool(big_endian))
+    else:
+        c = np.exp(rng.uniform(np.log(1e-3), np.log(100.0), (h, w, 3))).astype(np.float32)
+        c.tofile(tmp_path / "c.raw")
+        run([cli["h2y_iotool"], "write-dpx-raw", str(tmp_path / "in.dpx"), str(w), str(h), str(big_endian), "32", str(tmp_path / "c.raw")])
+        planes = O.load_dpxf32(c.astype(">f4" if big_endian else "<f4"), bool(big_endian))
+    run([REF_BIN, "--src_filename", "in.dpx", "--dst_filename", "out.yuv", "--src_transfer_characteristics", "8",
+         "--dst_transfer_characteristics", "16", "--src_pic_width", str(w), "--src_pic_height", str(h), "--src_bit_depth", "32",
+         "--dst_bit_depth", "10", "--src_chroma_format_idc", "3", "--dst_chroma_format_idc", "1", "--src_matrix_coeffs", "0",
+         "--dst_matrix_coeffs", "9", "--src_colour_primaries", "1", "--dst_colour_primaries", "9", "--src_video_full_range_flag", "1",
+         "--dst_video_full_range_flag", "0", "--chroma_resampler_type", "1"], cwd=tmp_path)
+    got = np.fromfile(tmp_path / "out.yuv", np.uint16)
+    src = dict(bit_depth=32, full_range=1, transfer=8, primaries=1, matrix=0)
+    dst = dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1)
+    want = O.forward(planes, src, dst, backend="port")
+    assert got.size == want.size and np.array_equal(got, want), (bits, big_endian, int((got != want).sum()))

@@ -172,3 +172,26 @@ def test_devices_2_shards_the_frame_range(cli, tmp_path):
         outs.append(np.fromfile(out, np.uint16))
     assert outs[0].size == outs[1].size == n * (w * h * 3 // 2)
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_rgb_to_exr_float_destination(cli, tmp_path):
+    # An .exr destination (hdr2yuv.cpp:935-957): matrix_convert's F32 twin at tmp depth 16, then write_exr_file's RGBA
+    # halfs with alpha 0 (exr.cpp:99-133).  The reference's writer needs OpenEXR, so the planes are checked against the
+    # reference's own matrix_convert (or its pinned restatement) rounded to half, read back through this repo's reader.
+    w, h = 128, 64
+    px = synth.tiff16_frame(w, h, seed=71)
+    np.ascontiguousarray(px.transpose(2, 0, 1)).tofile(tmp_path / "in.rgb")
+    out = tmp_path / "out.exr"
+    run([cli["hdr2yuv"], "--src_filename", str(tmp_path / "in.rgb"), "--dst_filename", str(out), "--src_transfer_characteristics", "16",
+         "--dst_transfer_characteristics", "16", "--src_pic_width", str(w), "--src_pic_height", str(h), "--src_bit_depth", "16",
+         "--dst_bit_depth", "16", "--src_chroma_format_idc", "3", "--src_matrix_coeffs", "0", "--dst_matrix_coeffs", "9",
+         "--src_colour_primaries", "9", "--dst_colour_primaries", "9"])
+    run([cli["h2y_iotool"], "read-exr", str(out), str(tmp_path / "o.raw"), "4"])
+    got = np.fromfile(tmp_path / "o.raw", np.uint16).reshape(h, w, 4)
+    planes = np.ascontiguousarray(np.stack([px[..., 1], px[..., 2], px[..., 0]], 0))        # .rgb is read unclipped
+    src = dict(bit_depth=16, full_range=0, transfer=16, primaries=9, matrix=0)
+    dst = dict(bit_depth=16, full_range=0, transfer=16, primaries=9, matrix=9)
+    want = O.matrix_convert_f32(planes, src, dst, "ref" if O.ref_available() else "port")   # G, B, R = Y, Cb, Cr planes
+    want_half = np.stack([want[2], want[0], want[1]], -1).astype(np.float16).view(np.uint16)
+    assert np.array_equal(got[..., :3], want_half)
+    assert not got[..., 3].any()

@@ -191,3 +191,47 @@ def test_tiff_source_matches_reference_program(cli, tmp_path, src_bits):
     assert rcr == rcb == 0, (tr[-1500:], tb[-1500:])
     a, b = np.fromfile(dr / "out.yuv", np.uint16), np.fromfile(db / "out.yuv", np.uint16)
     assert a.size == b.size and np.array_equal(a, b), (a.size, b.size)
+
+
+@needs_ref_bin
+def test_dpx_destination_matches_reference_program(cli, tmp_path):
+    # .rgb -> .dpx: the reference's own dpx_write_float (dpx.cpp:719-920) after its own matrix_convert.  parse_options
+    # forces the destination depth to 32 and set_pic_clip's shifts by 32 and 24 leave every limit at 0 (x86-64), so the
+    # picture the reference writes is zero; the two files must be the same bytes, header included.
+    data = rgb_planes(W, H, 13, 16)
+    args = ["--src_filename", "in.rgb", "--dst_filename", "out.dpx", "--src_transfer_characteristics", "16"] + common(W, H, 16) + \
+           ["--src_matrix_coeffs", "0", "--src_colour_primaries", "9"]
+    res = both(cli, tmp_path, args, lambda d: data.tofile(d / "in.rgb"))
+    (dr, rcr, tr), (db, rcb, tb) = res["ref"], res["b200"]
+    assert rcr == rcb == 0, (tr[-800:], tb[-800:])
+    assert (dr / "out.dpx").read_bytes() == (db / "out.dpx").read_bytes()
+
+
+@needs_ref_bin
+@pytest.mark.parametrize("bits,big_endian", [(16, 1), (16, 0), (32, 1), (32, 0)])
+def test_dpx16_and_float_sources_match_reference_program(cli, tmp_path, bits, big_endian):
+    # 16-bit and 32-bit float DPX sources through the reference's own dpx_read, against this host (GPU unpack)
+    rng = np.random.default_rng(40 + bits + big_endian)
+    w, h = 256, 96
+    if bits == 16:
+        c = rng.integers(0, 65536, (h, w, 3), dtype=np.uint16)
+        c[2, 3] = 65535
+        c[4, 5] = 0
+    else:
+        c = np.exp(rng.uniform(np.log(1e-3), np.log(300.0), (h, w, 3))).astype(np.float32)
+    args = ["--src_filename", "in.dpx", "--dst_filename", "out.yuv", "--src_transfer_characteristics", "8", "--dst_transfer_characteristics", "16",
+            "--src_pic_width", str(w), "--src_pic_height", str(h), "--src_bit_depth", "32", "--dst_bit_depth", "10", "--src_chroma_format_idc", "3",
+            "--dst_chroma_format_idc", "1", "--src_matrix_coeffs", "0", "--dst_matrix_coeffs", "9", "--src_colour_primaries", "1",
+            "--dst_colour_primaries", "9", "--src_video_full_range_flag", "1", "--dst_video_full_range_flag", "0", "--chroma_resampler_type", "1"]
+
+    def make(d):
+        c.tofile(d / "c.raw")
+        rc, text = run_any([cli["h2y_iotool"], "write-dpx-raw", str(d / "in.dpx"), str(w), str(h), str(big_endian), str(bits), str(d / "c.raw")], cwd=d)
+        assert rc == 0, text
+    res = both(cli, tmp_path, args, make)
+    (dr, rcr, tr), (db, rcb, tb) = res["ref"], res["b200"]
+    assert rcr == rcb == 0, (tr[-800:], tb[-800:])
+    a, b = np.fromfile(dr / "out.yuv", np.uint16).astype(np.int32), np.fromfile(db / "out.yuv", np.uint16).astype(np.int32)
+    assert a.size == b.size
+    d = np.abs(a - b)                                   # linear -> PQ: CUDA pow vs glibc pow, <= 1 code, counted
+    assert d.max() <= 1 and (d != 0).sum() <= max(2, d.size // 2000), (int(d.max()), int((d != 0).sum()))

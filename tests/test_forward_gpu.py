@@ -337,6 +337,68 @@ def test_dpx10_layout_unpacks_on_the_gpu_and_matches_oracle(ctx, big_endian):
             G.compare_codes(got[i], want, src["transfer"] != dst["transfer"], "dpx frame %d" % i)
 
 
+@pytest.mark.parametrize("bits", [16, 32])
+@pytest.mark.parametrize("big_endian", [True, False])
+def test_dpx16_and_float_layouts_unpack_on_the_gpu_and_match_oracle(ctx, bits, big_endian):
+    # H2Y_LAYOUT_DPX16_* (sample = code / 65535.0, dpx.cpp:478-494) and H2Y_LAYOUT_DPXF32_* (floats as they are,
+    # dpx.cpp:412-443): the file's samples go to the device in the file's byte order.  The Python loaders used as the
+    # oracle here are pinned to the reference's own dpx_read on the CPU (tests/test_cli_cpu.py).
+    w, h = 136, 52
+    rng = np.random.default_rng(bits + int(big_endian))
+    if bits == 16:
+        c = rng.integers(0, 65536, (2, h, w, 3), dtype=np.uint16)
+        c[:, 3, 5] = 65535
+        c[:, 7, 9] = 0
+        stored = c.astype(">u2" if big_endian else "<u2")
+        load, layout, bpp = O.load_dpx16, (cabi.LAYOUT_DPX16_BE if big_endian else cabi.LAYOUT_DPX16_LE), 6
+    else:
+        c = np.exp(rng.uniform(np.log(1e-3), np.log(300.0), (2, h, w, 3))).astype(np.float32)
+        stored = c.astype(">f4" if big_endian else "<f4")
+        load, layout, bpp = O.load_dpxf32, (cabi.LAYOUT_DPXF32_BE if big_endian else cabi.LAYOUT_DPXF32_LE), 12
+    src = dict(kind="dpx", bit_depth=32, full_range=1, transfer=8, primaries=1, matrix=0)
+    for dst in (dict(bit_depth=10, full_range=0, transfer=16, primaries=9, matrix=9, chroma=1, resampler=1),
+                dict(bit_depth=12, full_range=1, transfer=18, primaries=9, matrix=11, chroma=3, resampler=1)):
+        params = api.forward_params(w, h, layout, src, dst, resampler=dst["resampler"])
+        assert api.src_frame_bytes(params.src) == w * h * bpp
+        d_src = G.to_dev(stored.view(np.uint8))
+        nbytes = api.yuv_frame_bytes(w, h, dst["chroma"])
+        d_dst = torch.zeros(nbytes * 2, dtype=torch.uint8, device="cuda")
+        ctx.forward(params, d_src, d_dst, 2)
+        torch.cuda.synchronize()
+        got = d_dst.cpu().numpy().view(np.uint16).reshape(2, -1)
+        for i in range(2):
+            want = O.forward(load(stored[i], big_endian), cases.oracle_src(src), dst, backend="port")
+            G.compare_codes(got[i], want, True, "dpx%d frame %d" % (bits, i))
+
+
+@pytest.mark.parametrize("depth", [16, 32])
+def test_float_destination_host_route(ctx, depth):
+    # h2y_forward_f32_host = what an .exr / .dpx destination runs (hdr2yuv.cpp:797-823): pic_stats -> matrix_convert into
+    # float planes.  Depth 16 (an .exr destination) against the compiled reference's own F32 branch when it is here
+    # (else the restatement, which a CPU test pins to it bit for bit); depth 32 (what a .dpx destination is forced to)
+    # is the all-zero picture the reference's program writes (tests/test_cli_cpu.py checks that against its file).
+    w, h, n = 200, 64, 3
+    frames = [synth.tiff16_frame(w, h, seed=60 + i) for i in range(n)]
+    backend = "ref" if O.ref_available() else "port"
+    for src_tr, dst_tr, m, prim in ((16, 16, 9, 9), (16, 8, 0, 10), (16, 1, 1, 1), (16, 16, 11, 10)):
+        src = dict(kind="tiff16", bit_depth=16, full_range=0, transfer=src_tr, primaries=10, matrix=0)
+        dst = dict(bit_depth=depth, full_range=0, transfer=dst_tr, primaries=prim, matrix=m, chroma=3, resampler=1)
+        params = api.forward_params(w, h, cabi.LAYOUT_RGB16, src, dst, resampler=1, clip_on_load=1)
+        h_in = np.ascontiguousarray(np.stack(frames, 0))
+        h_out = np.full((n, 3, h, w), -1.0, np.float32)
+        ctx.forward_f32_host(params, h_in, h_out, n)
+        for i in range(n):
+            if depth == 32:
+                assert not h_out[i].any()
+                continue
+            want = O.matrix_convert_f32(O.load_rgb16(frames[i], 0), cases.oracle_src(src), dst, backend)
+            if src_tr == dst_tr:
+                assert np.array_equal(h_out[i].view(np.uint32), want.view(np.uint32)), (m, i)
+            else:
+                rel = np.abs(h_out[i].astype(np.float64) - want) / np.maximum(np.abs(want.astype(np.float64)), 1e-6)
+                assert float(rel.max()) <= 1e-5, (m, i, float(rel.max()))      # the path's tolerance for float output
+
+
 @pytest.mark.parametrize("which", ["ring", "rows"])
 @pytest.mark.parametrize("matrix,depth,full,channels", [(9, 10, 0, 3), (11, 10, 0, 3), (9, 12, 0, 4), (9, 16, 0, 3), (11, 12, 1, 4), (9, 10, 1, 3)])
 def test_tiff_420_kernels_match_oracle(ctx, opt, which, matrix, depth, full, channels):

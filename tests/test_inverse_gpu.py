@@ -212,3 +212,27 @@ def test_inverse_wide_and_short_pictures(ctx, kernel, opt):
             want, invalid = O.yuv2tiff(yuvs[i], w, h, 10, O.INV_2020, True, False, False)
             assert np.array_equal(rgb[i], want), (kernel, w, h)
             assert int(inv[i]) == invalid
+
+
+def test_linear_light_stage_behind_the_inverse(ctx, golden_inverse):
+    # SURVEY.md 8a note N2: yuv2tiff stops at PQ-coded 16-bit integers; the optional linear stage is the reference's own
+    # PQ10000_f (convert.cpp:43-51) on code / 65535 (the normalisation of convert.cpp:1017-1019 with floor 0, ceiling 65535).
+    # Tolerance of the path for float output: 1e-5 relative.  Every 16-bit code is checked, then an inverse frame's rows.
+    codes = np.arange(65536, dtype=np.uint16)
+    d_codes = torch.from_numpy(codes.view(np.int16)).cuda()
+    d_lin = torch.zeros(65536, dtype=torch.float32, device="cuda")
+    ctx.pq_codes_to_linear(d_codes, d_lin)
+    torch.cuda.synchronize()
+    got = d_lin.cpu().numpy()
+    # which = 0: PQ10000_f; the compiled reference itself when it is there (one C call for all codes), else the restatement
+    want = O.transfer(0, codes.astype(np.float32) / np.float32(65535.0), "ref" if O.ref_available() else "port")
+    rel = np.abs(got.astype(np.float64) - want.astype(np.float64)) / np.maximum(np.abs(want.astype(np.float64)), 1e-30)
+    assert float(rel.max()) <= 1e-5, float(rel.max())
+    assert got[0] == 0.0 and abs(float(got[65535]) - 1.0) <= 1e-6
+    yuv = cases.widen_yuv(golden_inverse[cases.inverse_input_key(2)], 10)
+    rgb, _ = gpu_inverse(ctx, [yuv], cases.IW, cases.IH, 10, 2, 1, 0, 0)
+    d_rgb = torch.from_numpy(np.ascontiguousarray(rgb[0]).view(np.int16).reshape(-1)).cuda()
+    d_out = torch.zeros(d_rgb.numel(), dtype=torch.float32, device="cuda")
+    ctx.pq_codes_to_linear(d_rgb, d_out)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), got[rgb[0].reshape(-1)])
