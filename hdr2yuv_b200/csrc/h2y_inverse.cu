@@ -248,7 +248,13 @@ struct Inv2Args {
 };
 
 namespace {
-constexpr int RTHREADS = 512, RWARPS = RTHREADS / 32, RSLOTS = 8;
+#ifndef H2Y_INV_THREADS
+#define H2Y_INV_THREADS 512
+#endif
+#ifndef H2Y_INV_MINB
+#define H2Y_INV_MINB 1
+#endif
+constexpr int RTHREADS = H2Y_INV_THREADS, RWARPS = RTHREADS / 32, RSLOTS = 8, RMINB = H2Y_INV_MINB;
 constexpr float TWO23 = 8388608.0f;
 }
 
@@ -268,7 +274,7 @@ template <int CFG> struct IC {
 
 // mode: 0 = every pixel through inv_pixel (Y100 / Y500), 1 = guarded fp32 (709 / 2020), 2 = integer Y'DzDx
 template <int MODE, bool FIR, bool ALPHA, int CFG = 0>
-__global__ void __launch_bounds__(RTHREADS, 1) k_inverse_rows(const Inv2Args A)
+__global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const InvK &k = A.k;
@@ -563,11 +569,11 @@ h2y_status launch_inverse(h2y_ctx_impl *c, const InvK &k, const void *d_yuv, siz
         A.hm = (float)k.Half - 0.5f; A.kb = (float)k.kb; A.kr = (float)k.kr;
         A.nwb = -(float)k.wb; A.nwr = -(float)k.wr; A.rwg = (float)(1.0 / k.wg);
         A.guard = 1.0f / (float)(1 << (21 - k.bit_depth));          // same bound as the forward kernel
-        const long rows_per_worker = A.total_crows / ((long)c->sm_count * A.sub);
+        const long rows_per_worker = A.total_crows / ((long)c->sm_count * RMINB * A.sub);
         // forced by tests and experiments (h2y_ctx_set_option); -X: tile kernel only
         const bool want_rows = !k.ybar && (c->sw.inv_kernel ? c->sw.inv_kernel == 2 : rows_per_worker >= 48);
         if (want_rows) {
-            int grid = c->sm_count;
+            int grid = c->sm_count * RMINB;
             while (grid > 1 && A.total_crows / ((long)grid * A.sub) < 4) grid >>= 1;
             const size_t smem = (size_t)RWARPS * RSLOTS * 64 * sizeof(float4);
             const int mode = (k.matrix == H2Y_INV_2020 || k.matrix == H2Y_INV_709) ? 1 : (k.matrix == H2Y_INV_YDzDx ? 2 : 0);
