@@ -235,6 +235,18 @@ k_inverse_fused(InvK k, const uint16_t *__restrict__ yuv, size_t yuv_stride_elem
 // evaluated in fp32 with a guard band: each truncation is taken at x-G and x+G and the reference-exact
 // inv_pixel() (double arithmetic, true division) runs only for the rare pixel where the two disagree or a
 // component is negative (which also carries the invalidPixels bookkeeping).
+//
+// Guard bands, in units of u = 2^(d-25) (half an fp32 ulp of values in [2^(d-1), 2^d)).  x = the exact real value of a
+// chain, t_ref = the reference's float (double arithmetic rounded once to float: |t_ref - x| <= 1u below 2^d; above
+// Full-1 both sides clamp).  The kernel takes floor(lo) and floor(RN(lo + 2G)) with lo ~ x - G and accepts the pixel
+// when they agree, i.e. when no integer lies in (lo, RN(lo + 2G)], so it needs lo < t_ref <= RN(lo + 2G).
+//  * B', R': lo = fma(C - (Half-0.5), k32, Y - G).  C - (Half-0.5) and Y - G are exact; |k32 - k| <= 2^-24 (k in [1,2))
+//    times 2^(d-1) is 1u, the fma's rounding 1u: |lo - (x - G)| <= 2u.  t_ref > lo needs G > 3u, t_ref <= RN(lo + 2G)
+//    (another 1u of rounding) needs G >= 4u.  G = 6u (6u keeps Y - G exact: 24 bits).
+//  * G': g2 = fma(-wr32, R', fma(-wb32, B', Y)) with integer B', R' (the accepted values): weight images u/8 + u/2, two
+//    roundings 2u: 2.625u; times 1/wg <= 1.475 is 3.87u; the image of 1/wg 2u; the fma's rounding 1u:
+//    |lo - (x - G)| <= 6.87u, so G >= 8.87u.  G = 10u.
+// (One band of 2^(d-21) = 16u for all three chains sent 2.2 times as many pixels to inv_pixel.)
 struct Inv2Args {
     InvK k;
     const uint8_t *yuv;
@@ -244,7 +256,8 @@ struct Inv2Args {
     uint32_t *invalid;
     int nstrips, sub, wps;
     long total_crows;        // nframes * (h / 2)
-    float hm, kb, kr, nwb, nwr, rwg, guard;   // Half-0.5, chroma gains, -wb, -wr, 1/wg as fp32
+    float hm, kb, kr, nwb, nwr, rwg;          // Half-0.5, chroma gains, -wb, -wr, 1/wg as fp32
+    float guard_c, guard_g;                   // guard bands of the B' / R' chains and of the G' chain (see k_inverse_rows)
 };
 
 namespace {
@@ -254,18 +267,51 @@ namespace {
 #ifndef H2Y_INV_MINB
 #define H2Y_INV_MINB 1
 #endif
+#ifndef H2Y_INV_GUARD_C
+#define H2Y_INV_GUARD_C 6.0f         // guard bands in units of u = 2^(d-25); 16 / 16 was the single band of rounds 1-2
+#define H2Y_INV_GUARD_G 10.0f
+#endif
+#ifndef H2Y_INV_LUMA_STAGES
+#define H2Y_INV_LUMA_STAGES 2        // cp.async stages of the luma rows per warp: 2 = one trip ahead, 4 = three
+#endif
 constexpr int RTHREADS = H2Y_INV_THREADS, RWARPS = RTHREADS / 32, RSLOTS = 8, RMINB = H2Y_INV_MINB;
+constexpr int LSTAGES = H2Y_INV_LUMA_STAGES;          // luma trips in flight + 1 (power of two)
 constexpr float TWO23 = 8388608.0f;
+constexpr size_t INV_ROWS_SMEM = 8192 + (size_t)RWARPS * 8192 + (size_t)RWARPS * LSTAGES * 1024;
 }
+
+// shared-memory accesses by 32-bit shared-window address (the ring and the luma stages are private to a lane)
+__device__ __forceinline__ float4 lds128(unsigned a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128u(unsigned a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(unsigned a, float x, float y, float z, float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(a), "f"(x), "f"(y), "f"(z), "f"(w));
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
 
 // Per-launch constants: CFG 0 from the launch arguments, CFG 10 = `B10 2020`, video range (yuv2tiff.cpp:137-147,
 // 178-186, 404-413) with every constant an immediate (no constant-bank reloads in the pixel loop).
 template <int CFG> struct IC {
-    static constexpr float G = 1.0f / 2048.0f;
+    static constexpr float GC = H2Y_INV_GUARD_C / 32768.0f, GG = H2Y_INV_GUARD_G / 32768.0f;     // 6u and 10u, u = 2^(10-25)
 #define ICF(name, rt, ct) __device__ __forceinline__ static float name(const Inv2Args &A) { return CFG ? (ct) : (rt); }
 #define ICU(name, rt, ct) __device__ __forceinline__ static unsigned name(const Inv2Args &A) { return CFG ? (unsigned)(ct) : (unsigned)(rt); }
     ICF(hm, A.hm, 511.5f) ICF(kb, A.kb, (float)1.8814) ICF(kr, A.kr, (float)1.4746)
-    ICF(nwb, A.nwb, -(float)0.0593) ICF(nwr, A.nwr, -(float)0.2627) ICF(rwg, A.rwg, (float)(1.0 / 0.6780)) ICF(guard, A.guard, G)
+    ICF(nwb, A.nwb, -(float)0.0593) ICF(nwr, A.nwr, -(float)0.2627) ICF(rwg, A.rwg, (float)(1.0 / 0.6780)) ICF(guard_c, A.guard_c, GC) ICF(guard_g, A.guard_g, GG)
     ICU(full_range, A.k.full_range, 0) ICU(minVR, A.k.minVR, 64) ICU(maxVR, A.k.maxVR, 940) ICU(minVRC, A.k.minVRC, 64)
     ICU(maxVRC, A.k.maxVRC, 960) ICU(maxCV, A.k.maxCV, 1023) ICU(Full, A.k.Full, 1024) ICU(SR, A.k.SR, 6)
 #undef ICF
@@ -279,7 +325,16 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const InvK &k = A.k;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float4 *ring = reinterpret_cast<float4 *>(smem_raw) + (size_t)warp * RSLOTS * 2 * 32;      // [slot][half][lane]
+    // Shared memory, all of it private to a lane (no barrier anywhere):
+    //  * the chroma ring: per warp 8 slots x {first, second pair of columns} x 32 lanes x float4 = 8 KB, each warp's ring
+    //    aligned to 8 KB so that the slot number is address bits 10-12 and a slot's address is one LOP3 away
+    //    (ring_lane | ((row << 10) & 0x1c00));
+    //  * the luma stages: rows 2c and 2c+1 of the next trips arrive there with cp.async (LDGSTS: no registers, and a
+    //    whole trip or two of distance; as register loads they were ~300 instructions ahead of their use and the warps
+    //    spent 17 % of their time waiting for them, ncu of round 2's kernel).
+    const unsigned smem_sa = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned ring_lane = ((smem_sa + 8191u) & ~8191u) + (unsigned)warp * 8192u + (unsigned)lane * 16u;
+    const unsigned luma_lane = ((smem_sa + 8191u) & ~8191u) + RWARPS * 8192u + (unsigned)warp * (LSTAGES * 1024u) + (unsigned)lane * 16u;
     const int w = k.w, h = k.h, wh = w >> 1, hh = h >> 1;
     constexpr int nch = ALPHA ? 4 : 3;
     typedef IC<CFG> C;
@@ -289,7 +344,7 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
     const long K = (long)gridDim.x * A.sub, kid = (long)blockIdx.x * A.sub + wk;
     const long g0 = (kid * A.total_crows) / K, g1 = ((kid + 1) * A.total_crows) / K;
     if (g1 <= g0) return;
-    const float G = C::guard(A);
+    const float guardC = C::guard_c(A), guardG = C::guard_g(A);
     int invalid_frame = -1;
     unsigned invalid = 0;
 
@@ -297,7 +352,8 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
         const long fbase = (long)frame * hh;
         const int cs = (int)(max(g0, fbase) - fbase), ce = (int)(min(g1, fbase + hh) - fbase);
         const uint16_t *fy = reinterpret_cast<const uint16_t *>(A.yuv + (size_t)frame * A.yuv_stride);
-        const uint16_t *fcb = fy + (size_t)w * h, *fcr = fcb + (size_t)wh * hh;
+        const uint16_t *fcb = fy + (size_t)w * h;
+        const ptrdiff_t crd = (ptrdiff_t)wh * hh;                               // Cr plane behind Cb, in samples
         uint16_t *frgb = reinterpret_cast<uint16_t *>(A.rgb + (size_t)frame * A.rgb_stride);
         if (A.invalid && invalid_frame != frame) {
             if (invalid && invalid_frame >= 0) atomicAdd(&A.invalid[invalid_frame], invalid);
@@ -309,13 +365,13 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
             const bool lane_interior = lane >= 1 && lane < 31 && xl < min(x0 + 240, w);
             const int cl = (lane_in_pic ? xl : (xl < 0 ? 0 : w - 8)) >> 1;       // first of this lane's 4 chroma columns
 
-            // chroma row r (picture row, already clamped) -> two float4 {cb0,cr0,cb1,cr1},{cb2,cr2,cb3,cr3}
-            auto fetch = [&](int r, uint2 &vb, uint2 &vr) {
-                vb = __ldg(reinterpret_cast<const uint2 *>(fcb + (size_t)r * wh + cl));
-                vr = __ldg(reinterpret_cast<const uint2 *>(fcr + (size_t)r * wh + cl));
-            };
-            auto stash = [&](int r, uint2 vb, uint2 vr) {
-                unsigned wb[2] = {vb.x, vb.y}, wr[2] = {vr.x, vr.y};
+            // Columns clamp to [0, w/2-1] (yuv2tiff.cpp:655-683): the halo lane left of the picture holds column 0 four
+            // times, the lanes right of it the last column, so the neighbours' shuffles deliver the replicated samples.
+            const unsigned sel0 = xl < 0 ? 0x1010u : (xl >= w ? 0x7676u : 0x3210u), sel1 = xl < 0 ? 0x1010u : (xl >= w ? 0x7676u : 0x7654u);
+            // chroma row -> two float4 {cb0,cr0,cb1,cr1},{cb2,cr2,cb3,cr3} in ring slot (slot10 >> 10) & 7
+            auto stash = [&](unsigned slot10, uint2 vb, uint2 vr) {
+                unsigned wb[2] = {__byte_perm(vb.x, vb.y, sel0), __byte_perm(vb.x, vb.y, sel1)};
+                unsigned wr[2] = {__byte_perm(vr.x, vr.y, sel0), __byte_perm(vr.x, vr.y, sel1)};
                 if (!C::full_range(A)) {                                          // read clamp, yuv2tiff.cpp:297-320
                     const unsigned lo2 = C::minVRC(A) * 0x10001u, hi2 = C::maxVRC(A) * 0x10001u;
 #pragma unroll
@@ -331,32 +387,52 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
                     p[2 * i] = fadd2(pk(__uint_as_float(__byte_perm(wb[i], 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(wr[i], 0x4B000000u, 0x7610))), m2);
                     p[2 * i + 1] = fadd2(pk(__uint_as_float(__byte_perm(wb[i], 0x4B000000u, 0x7632)), __uint_as_float(__byte_perm(wr[i], 0x4B000000u, 0x7632))), m2);
                 }
-                float4 *slot = ring + (size_t)(r & (RSLOTS - 1)) * 64 + lane;
-                slot[0] = make_float4(plo(p[0]), phi(p[0]), plo(p[1]), phi(p[1]));
-                slot[32] = make_float4(plo(p[2]), phi(p[2]), plo(p[3]), phi(p[3]));
+                const unsigned sa = ring_lane | (slot10 & 0x1c00u);
+                sts128(sa, plo(p[0]), phi(p[0]), plo(p[1]), phi(p[1]));
+                sts128(sa + 512u, plo(p[2]), phi(p[2]), plo(p[3]), phi(p[3]));
             };
-            // prime the ring with rows clamp(cs-3) .. clamp(cs+3)
-            for (int r = max(cs - 3, 0); r <= min(cs + 3, hh - 1); r++) {
-                uint2 vb, vr;
-                fetch(r, vb, vr);
-                stash(r, vb, vr);
+            // Running pointers.  The ring always holds rows clamp(c-3) .. clamp(c+3) in slots (c-3)&7 .. (c+3)&7: at the
+            // picture's top the first row is stashed for rows -3..-1 as well, at its bottom the last fetched row (hh-1)
+            // is stashed again, so the window read needs no row clamps (yuv2tiff.cpp:617-622 replicates the edge rows).
+            const uint16_t *pcb = fcb + (size_t)min(max(cs - 3, 0), hh - 1) * wh + cl;       // next chroma row to fetch
+            int rnext = cs - 3;                                                              // its (unclamped) row number
+            uint2 nb, nr;
+            auto fetch_next = [&]() {
+                nb = __ldg(reinterpret_cast<const uint2 *>(pcb));
+                nr = __ldg(reinterpret_cast<const uint2 *>(pcb + crd));
+                if (rnext >= 0 && rnext < hh - 1) pcb += wh;
+                rnext++;
+            };
+            for (int r = cs - 3; r <= cs + 3; r++) {
+                fetch_next();
+                stash((unsigned)(r + 8) << 10, nb, nr);
             }
-            uint2 nb = make_uint2(0, 0), nr = make_uint2(0, 0);
-            if (cs + 4 <= hh - 1) fetch(cs + 4, nb, nr);
+            fetch_next();                                                                    // row clamp(cs + 4)
+            const uint16_t *pyl = fy + (size_t)(2 * cs) * w + (cl << 1);                     // luma rows of the next trip to request
+            uint16_t *po = frgb + ((size_t)(2 * cs) * w + xl) * nch;
+            auto luma_request = [&](int cc) {
+                const unsigned sa = luma_lane + (unsigned)(cc & (LSTAGES - 1)) * 1024u;
+                cp_async16(sa, pyl);
+                cp_async16(sa + 512u, pyl + w);
+                pyl += 2 * w;
+            };
+#pragma unroll
+            for (int i = 0; i < LSTAGES - 1; i++) {
+                if (cs + i < ce) luma_request(cs + i);
+                cp_async_commit();
+            }
+            unsigned c10 = (unsigned)(cs + 5) << 10;                                         // slot of row c-3, times 1024
 
-            for (int c = cs; c < ce; c++) {
-                // luma rows 2c, 2c+1 (issued early)
-                uint4 yrow[2];
-                yrow[0] = __ldg(reinterpret_cast<const uint4 *>(fy + (size_t)(2 * c) * w + (cl << 1)));
-                yrow[1] = __ldg(reinterpret_cast<const uint4 *>(fy + (size_t)(2 * c + 1) * w + (cl << 1)));
+            for (int c = cs; c < ce; c++, c10 += 1024u) {
+                if (c + LSTAGES - 1 < ce) luma_request(c + LSTAGES - 1);
+                cp_async_commit();
                 __syncwarp();
                 // ---- vertical 2-phase 6-tap (yuv2tiff.cpp:615-650) on the 7-row window ----
                 u64 win[7][4];
 #pragma unroll
                 for (int t = 0; t < 7; t++) {
-                    const int r = min(max(c - 3 + t, 0), hh - 1);
-                    const float4 *slot = ring + (size_t)(r & (RSLOTS - 1)) * 64 + lane;
-                    const float4 a = slot[0], b = slot[32];
+                    const unsigned sa = ring_lane | ((c10 + 1024u * t) & 0x1c00u);
+                    const float4 a = lds128(sa), b = lds128(sa + 512u);
                     win[t][0] = pk(a.x, a.y); win[t][1] = pk(a.z, a.w); win[t][2] = pk(b.x, b.y); win[t][3] = pk(b.z, b.w);
                 }
                 u64 dv[2][4];          // the reference's dst422 rows 2c and 2c+1, this lane's 4 columns
@@ -382,12 +458,13 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
                     }
                 }
                 // the next row enters the ring while the pixels are finished; then prefetch the one after
-                if (c + 4 <= hh - 1) stash(c + 4, nb, nr);
-                if (c + 5 <= hh - 1 && c + 1 < ce) fetch(c + 5, nb, nr);
+                stash(c10 + 7u * 1024u, nb, nr);                         // row clamp(c + 4)
+                if (c + 1 < ce) fetch_next();                            // row clamp(c + 5)
+                cp_async_wait<LSTAGES - 1>();                            // this trip's luma rows have landed
 
 #pragma unroll 1
                 for (int half = 0; half < 2; half++) {                  // not unrolled: the instruction cache is the limit
-                    // both passes read dv[0] / yrow[0]; the second row moves down at the end of the first pass
+                    // both passes read dv[0]; the second row moves down at the end of the first pass
                     // (12 moves per chroma row instead of 12 selects per luma row, and no run-time array index)
                     u64 d[4];
 #pragma unroll
@@ -402,8 +479,7 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
                         u64 R0 = pk(__shfl_down_sync(0xffffffffu, plo(d[0]), 1), __shfl_down_sync(0xffffffffu, phi(d[0]), 1));
                         u64 R1 = pk(__shfl_down_sync(0xffffffffu, plo(d[1]), 1), __shfl_down_sync(0xffffffffu, phi(d[1]), 1));
                         u64 R2 = pk(__shfl_down_sync(0xffffffffu, plo(d[2]), 1), __shfl_down_sync(0xffffffffu, phi(d[2]), 1));
-                        if (xl == 0) L2 = L3 = d[0];                    // columns clamp to [0, w/2-1]
-                        if (xl + 8 >= w) R0 = R1 = R2 = d[3];
+                        // (the picture's edge columns are replicated by the halo lanes, see sel0 / sel1)
                         const u64 nb8[9] = {L2, L3, d[0], d[1], d[2], d[3], R0, R1, R2};
                         const u64 b21 = pk(21.0f / 256.0f, 21.0f / 256.0f), b52n = pk(-52.0f / 256.0f, -52.0f / 256.0f),
                                   b159 = pk(159.0f / 256.0f, 159.0f / 256.0f), hf = pk(0.5f, 0.5f);
@@ -422,9 +498,10 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
                     }
 #pragma unroll
                     for (int i = 0; i < 4; i++) dv[0][i] = dv[1][i];
-                    const uint4 yr = yrow[0];
-                    yrow[0] = yrow[1];
+                    uint16_t *const orow = po;
+                    po += (size_t)w * nch;
                     if (!lane_interior) continue;
+                    const uint4 yr = lds128u(luma_lane + (unsigned)(c & (LSTAGES - 1)) * 1024u + (unsigned)half * 512u);
                     // ---- eight pixels of luma row 2c + half ----
                     // Phase 1, branch-free: the colour difference inverse as integers Rp/Gp/Bp (before the output clamp
                     // and shift) plus one bit per pixel that needs the reference-exact routine.
@@ -443,23 +520,23 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
                             // One PRMT per pixel builds the float 2^23 + Y from the luma word.
                             const u64 Yf2 = fadd2(pk(__uint_as_float(__byte_perm(yw[q >> 1], 0x4B000000u, 0x7610)),
                                                      __uint_as_float(__byte_perm(yw[q >> 1], 0x4B000000u, 0x7632))), pk(-TWO23, -TWO23));
-                            const u64 Yg2 = fadd2(Yf2, pk(-G, -G));
+                            const u64 Yg2 = fadd2(Yf2, pk(-guardC, -guardC));
                             int B1[2], R1[2], B2[2], R2[2], Bc[2], Rc[2];
 #pragma unroll
                             for (int e = 0; e < 2; e++) {
                                 const float Yg = e ? phi(Yg2) : plo(Yg2);
                                 const u64 tlo = ffma2(fadd2(cpx[q + e], pk(-C::hm(A), -C::hm(A))), pk(C::kb(A), C::kr(A)), pk(Yg, Yg));
                                 unpk(fadd2_rm(tlo, pk(MAGIC, MAGIC)), B1[e], R1[e]);
-                                unpk(fadd2_rm(fadd2(tlo, pk(2.0f * G, 2.0f * G)), pk(MAGIC, MAGIC)), B2[e], R2[e]);
+                                unpk(fadd2_rm(fadd2(tlo, pk(2.0f * guardC, 2.0f * guardC)), pk(MAGIC, MAGIC)), B2[e], R2[e]);
                                 Bc[e] = min(B1[e], hi_bits); Rc[e] = min(R1[e], hi_bits);    // t > Full-1 -> Full-1 (406-412)
                             }
                             const u64 bf = fadd2(pk(__int_as_float(Bc[0]), __int_as_float(Bc[1])), pk(-MAGIC, -MAGIC));
                             const u64 rf = fadd2(pk(__int_as_float(Rc[0]), __int_as_float(Rc[1])), pk(-MAGIC, -MAGIC));
                             const u64 g2 = ffma2(pk(C::nwr(A), C::nwr(A)), rf, ffma2(pk(C::nwb(A), C::nwb(A)), bf, Yf2));
-                            const u64 glo = ffma2(g2, pk(C::rwg(A), C::rwg(A)), pk(0.5f - G, 0.5f - G));
+                            const u64 glo = ffma2(g2, pk(C::rwg(A), C::rwg(A)), pk(0.5f - guardG, 0.5f - guardG));
                             int G1[2], G2[2];
                             unpk(fadd2_rm(glo, pk(MAGIC, MAGIC)), G1[0], G1[1]);
-                            unpk(fadd2_rm(fadd2(glo, pk(2.0f * G, 2.0f * G)), pk(MAGIC, MAGIC)), G2[0], G2[1]);
+                            unpk(fadd2_rm(fadd2(glo, pk(2.0f * guardG, 2.0f * guardG)), pk(MAGIC, MAGIC)), G2[0], G2[1]);
 #pragma unroll
                             for (int e = 0; e < 2; e++) {
                                 // guarded (a floor changed inside the band) or negative (bit 22 of MAGIC_BITS + n clear)
@@ -518,7 +595,7 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
                             if (ALPHA && (i & 1)) ow[i] |= 0xffff0000u;
                         }
                     }
-                    uint4 *o = reinterpret_cast<uint4 *>(frgb + ((size_t)(2 * c + half) * w + xl) * nch);
+                    uint4 *o = reinterpret_cast<uint4 *>(orow);
 #pragma unroll
                     for (int i = 0; i < nch; i++) o[i] = make_uint4(ow[4 * i], ow[4 * i + 1], ow[4 * i + 2], ow[4 * i + 3]);
                 }
@@ -568,14 +645,15 @@ h2y_status launch_inverse(h2y_ctx_impl *c, const InvK &k, const void *d_yuv, siz
         A.total_crows = (long)nframes * (k.h / 2);
         A.hm = (float)k.Half - 0.5f; A.kb = (float)k.kb; A.kr = (float)k.kr;
         A.nwb = -(float)k.wb; A.nwr = -(float)k.wr; A.rwg = (float)(1.0 / k.wg);
-        A.guard = 1.0f / (float)(1 << (21 - k.bit_depth));          // same bound as the forward kernel
+        A.guard_c = H2Y_INV_GUARD_C / (float)(1 << (25 - k.bit_depth));        // 6u and 10u with u = 2^(d-25): bounds in k_inverse_rows
+        A.guard_g = H2Y_INV_GUARD_G / (float)(1 << (25 - k.bit_depth));
         const long rows_per_worker = A.total_crows / ((long)c->sm_count * RMINB * A.sub);
         // forced by tests and experiments (h2y_ctx_set_option); -X: tile kernel only
         const bool want_rows = !k.ybar && (c->sw.inv_kernel ? c->sw.inv_kernel == 2 : rows_per_worker >= 48);
         if (want_rows) {
             int grid = c->sm_count * RMINB;
             while (grid > 1 && A.total_crows / ((long)grid * A.sub) < 4) grid >>= 1;
-            const size_t smem = (size_t)RWARPS * RSLOTS * 64 * sizeof(float4);
+            const size_t smem = INV_ROWS_SMEM;
             const int mode = (k.matrix == H2Y_INV_2020 || k.matrix == H2Y_INV_709) ? 1 : (k.matrix == H2Y_INV_YDzDx ? 2 : 0);
 #define LR(M, F, AL)                                                                                                       \
     do {                                                                                                                   \

@@ -99,6 +99,71 @@ def test_inverse_sizes_vs_oracle(ctx, w, h, kernel, opt):
                 assert int(inv[0]) == winv
 
 
+def _inverse_dev(ctx, d_yuv, n, w, h, bd, m, fir, fr):
+    d_rgb = torch.zeros(n * w * h * 6, dtype=torch.uint8, device="cuda")
+    d_inv = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ctx.inverse(cabi.InverseParams(w, h, bd, m, fir, fr, 0, 0), d_yuv, d_rgb, n, invalid=d_inv)
+    torch.cuda.synchronize()
+    return d_rgb, d_inv
+
+
+@pytest.mark.parametrize("m", [O.INV_2020, O.INV_709])
+@pytest.mark.parametrize("fr", [0, 1])
+def test_rows_kernel_on_every_10bit_triplet(ctx, m, fr, opt):
+    # The rows kernel evaluates the Y'CbCr inverse in fp32 behind guard bands (h2y_inverse.cu); the tile kernel runs the
+    # reference's double arithmetic for every pixel and is pinned to the reference by the tests above.  With the box
+    # upsampler the chroma of a pixel is the stored sample, so a 2048 x 2048 picture whose Cb plane counts columns and
+    # whose Cr plane counts rows holds every (Cb, Cr) pair, and 256 frames with the luma code stepping through
+    # (4 f + position in the 2 x 2 block + a per-block offset) mod 1024 hold every 10-bit (Y', Cb, Cr) triplet once:
+    # 2^30 pixels, compared on the device.
+    w = h = 2048
+    dev = torch.device("cuda")
+    i = torch.arange(1024, device=dev, dtype=torch.int32)
+    cb = i.view(1, 1024).expand(1024, 1024).contiguous().view(-1)
+    cr = i.view(1024, 1).expand(1024, 1024).contiguous().view(-1)
+    x = torch.arange(w, device=dev, dtype=torch.int32).view(1, w)
+    y = torch.arange(h, device=dev, dtype=torch.int32).view(h, 1)
+    base = ((y & 1) * 2 + (x & 1) + 37 * (x >> 1) + 101 * (y >> 1))             # (h, w)
+    batch = 32
+    total_invalid = 0
+    for f0 in range(0, 256, batch):
+        frames = []
+        for f in range(f0, f0 + batch):
+            luma = ((base + 4 * f) & 1023).view(-1)
+            frames.append(torch.cat([luma, cb, cr]).to(torch.int16))
+        d_yuv = torch.stack(frames, 0).view(torch.uint8).view(-1)
+        res = {}
+        for kernel in ("tile", "rows"):
+            opt("H2Y_INVERSE_KERNEL", kernel)
+            res[kernel] = _inverse_dev(ctx, d_yuv, batch, w, h, 10, m, 0, fr)
+        assert torch.equal(res["tile"][0], res["rows"][0]), (m, fr, f0)
+        assert torch.equal(res["tile"][1], res["rows"][1]), (m, fr, f0)
+        total_invalid += int(res["tile"][1].sum().item())
+        del res, d_yuv, frames
+    assert total_invalid > 0                        # the lattice includes the out-of-gamut corners
+
+
+@pytest.mark.parametrize("bd,m", [(10, O.INV_2020), (12, O.INV_2020), (12, O.INV_709), (14, O.INV_2020), (14, O.INV_709)])
+def test_rows_kernel_dense_random_triplets(ctx, bd, m, opt):
+    # The same comparison with the FIR upsampler (for 10-bit BT.2020 video range that is the instantiation with the
+    # constants compiled in) and at the depths where the lattice is too large: 2^27 random pixels per case.
+    w = h = 2048
+    n = 32
+    g = torch.Generator(device="cuda")
+    g.manual_seed(bd * 10 + m)
+    top = 1 << bd
+    d_yuv = torch.randint(0, top, (n, w * h * 3 // 2), device="cuda", generator=g, dtype=torch.int32).to(torch.int16)
+    # half of the frames: smooth chroma, so that the upsampled values stay near the stored ones (in-gamut pixels)
+    d_yuv[n // 2:, w * h:] = (top // 2 + torch.randint(-top // 8, top // 8, (n // 2, w * h // 2), device="cuda", generator=g, dtype=torch.int32)).to(torch.int16)
+    d_yuv = d_yuv.view(torch.uint8).view(-1)
+    res = {}
+    for kernel in ("tile", "rows"):
+        opt("H2Y_INVERSE_KERNEL", kernel)
+        res[kernel] = _inverse_dev(ctx, d_yuv, n, w, h, bd, m, 1, 0)
+    assert torch.equal(res["tile"][0], res["rows"][0])
+    assert torch.equal(res["tile"][1], res["rows"][1])
+
+
 def test_staged_upsample_matches_oracle(ctx):
     rng = np.random.default_rng(4)
     for wh, hh, top in ((64, 24, 1023), (101, 37, 4095), (960, 540, 16383)):
