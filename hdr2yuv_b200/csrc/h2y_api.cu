@@ -44,7 +44,7 @@ int switches_set(Switches *s, const char *name, const char *v)
     else if (!strcmp(name, "H2Y_NO_SPECIALISED")) s->no_specialised = on;
     else if (!strcmp(name, "H2Y_EXACT_MATH")) s->exact_math = v && v[0] == '1';
     else if (!strcmp(name, "H2Y_FORWARD_KERNEL")) s->fwd_kernel = !v || !v[0] ? 0 : (v[0] == 'r' && v[1] == 'o' ? 2 : 1);
-    else if (!strcmp(name, "H2Y_INVERSE_KERNEL")) s->inv_kernel = !v || !v[0] ? 0 : (v[0] == 'r' ? 2 : 1);
+    else if (!strcmp(name, "H2Y_INVERSE_KERNEL")) s->inv_kernel = !v || !v[0] ? 0 : (v[0] == 'r' ? 2 : (v[0] == 'e' ? 3 : 1));
     else if (!strcmp(name, "H2Y_STATS_GX")) s->stats_gx = v ? atoi(v) : 0;
     else if (!strcmp(name, "H2Y_EXPERIMENT_GUARD_LOG2")) s->guard_log2 = v && v[0] ? atoi(v) : -1;
     else if (!strcmp(name, "H2Y_PLAN_REUSE")) s->spec = !v || !v[0] ? -1 : atoi(v);

@@ -59,7 +59,7 @@ struct SpecCtl {                // device-resident, one per call
 struct Switches {
     int force_staged, force_v1, no_specialised, exact_math;
     int fwd_kernel;             // 0 automatic, 1 "ring", 2 "rows"
-    int inv_kernel;             // 0 automatic, 1 "tile", 2 "rows"
+    int inv_kernel;             // 0 automatic, 1 "tile", 2 "rows", 3 "exact" = rows with every pixel through the exact routine
     int stats_gx;               // 0 automatic
     int guard_log2;             // < 0: the derived guard band; otherwise 2^-n (timing experiments, breaks parity)
     int spec;                   // plan reuse: -1 automatic (host policy), 0 never, 1 whenever a seed exists
@@ -202,6 +202,7 @@ h2y_status launch_forward_fused(h2y_ctx_impl *c, const h2y_forward_params &p, co
 
 struct InvK {
     int w, h, bit_depth, matrix, fir, full_range, alpha, ybar;
+    int int10;                  // `B10 2020`: the exact routine has an integer form (inv_pixel_int10)
     int SR;
     unsigned Half, Full, maxCV;
     unsigned minVR, maxVR, minVRC, maxVRC;

@@ -95,6 +95,36 @@ __device__ __forceinline__ int inv_pixel(const InvK &k, int Y, float fcb, float 
     return invalid;
 }
 
+// The same pixel for `B10 2020` in integer arithmetic (InvK::int10; used by the rows kernel for the pixels its fp32
+// guard bands hand back).  With C a chroma code and Y', B', R' integers,
+//     (C - 511.5) * 1.8814 + Y'                        = ((2 C - 1023) * 9407 + 10000 Y') / 10000
+//     (Y' - 0.0593 B' - 0.2627 R') / 0.6780 + 0.5      = (2 (10000 Y' - 593 B' - 2627 R') + 6780) / 13560
+// exactly (and 1.4746 / 2 = 0.7373 for R').  The reference evaluates the left sides in double (a handful of roundings,
+// 1e-12 absolute at these magnitudes), rounds to float (at most 2^-15 = 3.05e-5 below 1024, 6.1e-5 below 2048) and
+// truncates (yuv2tiff.cpp:404-413).  A quotient that is not an integer is at least 1/13560 = 7.4e-5 away from the
+// next integer, further than those roundings can move it, and an integer quotient is rounded back onto itself: the
+// truncated float is the integer quotient rounded toward zero, which is what C's division gives.  Values above
+// Full-1 are set to Full-1 before the truncation there, after it here.  Every 10-bit triplet is compared with
+// inv_pixel() by tests/test_inverse_gpu.py (H2Y_INVERSE_KERNEL=exact sends every pixel here).
+__device__ __forceinline__ int inv_pixel_int10(const InvK &k, int Y, int cb, int cr, unsigned &Ro, unsigned &Go, unsigned &Bo)
+{
+    const int y4 = Y * 10000;
+    int Bp = min(((2 * cb - 1023) * 9407 + y4) / 10000, 1023);
+    int Rp = min(((2 * cr - 1023) * 7373 + y4) / 10000, 1023);
+    int Gp = min((2 * (y4 - 593 * Bp - 2627 * Rp) + 6780) / 13560, 1023);
+    int invalid = 0;
+    if (Gp < 0) { Gp = 0; invalid++; }
+    if (Rp < 0) { Rp = 0; if (Y != 0) invalid++; }
+    if (Bp < 0) { Bp = 0; if (Y != 0) invalid++; }
+    if (!k.full_range) {
+        Rp = iclamp(Rp, (int)k.minVR, (int)k.maxVR);
+        Gp = iclamp(Gp, (int)k.minVR, (int)k.maxVR);
+        Bp = iclamp(Bp, (int)k.minVR, (int)k.maxVR);
+    }
+    Ro = (unsigned)Rp << 6; Go = (unsigned)Gp << 6; Bo = (unsigned)Bp << 6;
+    return invalid;
+}
+
 template <bool FIR, bool ALPHA>
 __global__ void __launch_bounds__(256)
 k_inverse_fused(InvK k, const uint16_t *__restrict__ yuv, size_t yuv_stride_elems, uint16_t *__restrict__ rgb,
@@ -319,7 +349,8 @@ template <int CFG> struct IC {
 };
 
 // mode: 0 = every pixel through inv_pixel (Y100 / Y500), 1 = guarded fp32 (709 / 2020), 2 = integer Y'DzDx
-template <int MODE, bool FIR, bool ALPHA, int CFG = 0>
+// ALLSLOW: every pixel takes the exact routine (tests: H2Y_INVERSE_KERNEL=exact)
+template <int MODE, bool FIR, bool ALPHA, int CFG = 0, bool ALLSLOW = false>
 __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -512,7 +543,7 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
                         for (int i = 0; i < 4; i++) yw[i] = clamp_u16x2(yw[i], lo2, hi2);
                     }
                     int Rv[8], Gv8[8], Bv[8];
-                    unsigned slow_mask = MODE == 0 ? 0xffu : 0u;
+                    unsigned slow_mask = MODE == 0 || ALLSLOW ? 0xffu : 0u;
 #pragma unroll
                     for (int q = 0; q < 8; q += 2) {                     // two pixels at a time: one luma word
                         if (MODE == 1) {
@@ -568,7 +599,11 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
                         for (int q = 0; q < 8; q++)
                             if (slow_mask & (1u << q)) {
                                 unsigned R, Gg, B;
-                                invalid += (unsigned)inv_pixel<MODE == 1 ? H2Y_INV_2020 : (MODE == 2 ? H2Y_INV_YDzDx : -1)>(k, (int)((q & 1) ? yw[q >> 1] >> 16 : yw[q >> 1] & 0xffffu), plo(cpx[q]), phi(cpx[q]), R, Gg, B);
+                                const int Yq = (int)((q & 1) ? yw[q >> 1] >> 16 : yw[q >> 1] & 0xffffu);
+                                if (MODE == 1 && (CFG == 10 || k.int10))
+                                    invalid += (unsigned)inv_pixel_int10(k, Yq, (int)plo(cpx[q]), (int)phi(cpx[q]), R, Gg, B);
+                                else
+                                    invalid += (unsigned)inv_pixel<MODE == 1 ? H2Y_INV_2020 : (MODE == 2 ? H2Y_INV_YDzDx : -1)>(k, Yq, plo(cpx[q]), phi(cpx[q]), R, Gg, B);
                                 Rv[q] = (int)(R >> C::SR(A)); Gv8[q] = (int)(Gg >> C::SR(A)); Bv[q] = (int)(B >> C::SR(A));
                             }
                     }
@@ -613,6 +648,7 @@ h2y_status make_invk(const h2y_inverse_params &p, InvK *k)
     if (p.matrix < H2Y_INV_YDzDx || p.matrix > H2Y_INV_Y500) return H2Y_ERR_ARG;
     k->w = p.width; k->h = p.height; k->bit_depth = p.bit_depth; k->matrix = p.matrix;
     k->fir = p.fir != 0; k->full_range = p.full_range != 0; k->alpha = p.alpha != 0;
+    k->int10 = p.matrix == H2Y_INV_2020 && p.bit_depth == 10;    // inv_pixel_int10
     k->ybar = p.ybar != 0 && p.matrix == H2Y_INV_YDzDx;          // -X only acts inside the Y'DzDx branch (yuv2tiff.cpp:389-399)
     k->SR = 16 - p.bit_depth;                                   // yuv2tiff.cpp:89, 139, 150
     k->Half = 1u << (p.bit_depth - 1);
@@ -649,7 +685,7 @@ h2y_status launch_inverse(h2y_ctx_impl *c, const InvK &k, const void *d_yuv, siz
         A.guard_g = H2Y_INV_GUARD_G / (float)(1 << (25 - k.bit_depth));
         const long rows_per_worker = A.total_crows / ((long)c->sm_count * RMINB * A.sub);
         // forced by tests and experiments (h2y_ctx_set_option); -X: tile kernel only
-        const bool want_rows = !k.ybar && (c->sw.inv_kernel ? c->sw.inv_kernel == 2 : rows_per_worker >= 48);
+        const bool want_rows = !k.ybar && (c->sw.inv_kernel ? c->sw.inv_kernel >= 2 : rows_per_worker >= 48);
         if (want_rows) {
             int grid = c->sm_count * RMINB;
             while (grid > 1 && A.total_crows / ((long)grid * A.sub) < 4) grid >>= 1;
@@ -669,7 +705,15 @@ h2y_status launch_inverse(h2y_ctx_impl *c, const InvK &k, const void *d_yuv, siz
     } while (0)
             const bool cfg10 = k.matrix == H2Y_INV_2020 && k.bit_depth == 10 && !k.full_range && k.fir && !k.alpha &&
                                !c->sw.no_specialised;
-            if (cfg10) {
+            if (c->sw.inv_kernel == 3 && mode == 1 && !k.alpha) {
+                if (k.fir) {
+                    H2Y_CUDA(c, cudaFuncSetAttribute(k_inverse_rows<1, true, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    k_inverse_rows<1, true, false, 0, true><<<grid, RTHREADS, smem, st>>>(A);
+                } else {
+                    H2Y_CUDA(c, cudaFuncSetAttribute(k_inverse_rows<1, false, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    k_inverse_rows<1, false, false, 0, true><<<grid, RTHREADS, smem, st>>>(A);
+                }
+            } else if (cfg10) {
                 H2Y_CUDA(c, cudaFuncSetAttribute(k_inverse_rows<1, true, false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 k_inverse_rows<1, true, false, 10><<<grid, RTHREADS, smem, st>>>(A);
             } else if (mode == 1) LRM(1); else if (mode == 2) LRM(2); else LRM(0);

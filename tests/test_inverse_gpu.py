@@ -133,11 +133,14 @@ def test_rows_kernel_on_every_10bit_triplet(ctx, m, fr, opt):
             frames.append(torch.cat([luma, cb, cr]).to(torch.int16))
         d_yuv = torch.stack(frames, 0).view(torch.uint8).view(-1)
         res = {}
-        for kernel in ("tile", "rows"):
+        # "exact": the rows kernel with every pixel through its exact routine, which for BT.2020 is the integer form
+        # (inv_pixel_int10): all 2^30 triplets reach it
+        for kernel in ("tile", "rows", "exact"):
             opt("H2Y_INVERSE_KERNEL", kernel)
             res[kernel] = _inverse_dev(ctx, d_yuv, batch, w, h, 10, m, 0, fr)
-        assert torch.equal(res["tile"][0], res["rows"][0]), (m, fr, f0)
-        assert torch.equal(res["tile"][1], res["rows"][1]), (m, fr, f0)
+        for kernel in ("rows", "exact"):
+            assert torch.equal(res["tile"][0], res[kernel][0]), (kernel, m, fr, f0)
+            assert torch.equal(res["tile"][1], res[kernel][1]), (kernel, m, fr, f0)
         total_invalid += int(res["tile"][1].sum().item())
         del res, d_yuv, frames
     assert total_invalid > 0                        # the lattice includes the out-of-gamut corners
