@@ -354,7 +354,7 @@ def algorithmic_bytes_per_px(wl):
 
 def fused_kernel_name(wl):
     if wl["kind"] == "inverse":
-        return "k_inverse_fused"
+        return "k_inverse_rows (h2y_inverse.cu)"
     exr = wl["src_kind"] == "half" and wl["dst"]["chroma"] == 1 and wl["dst"]["resampler"] == 1 and \
         wl["src"]["transfer"] != wl["dst"]["transfer"] and wl["dst"]["matrix"] in (1, 9, 11) and wl["dst"]["bit_depth"] <= 12
     return "k_forward_exr420_rows (h2y_forward2.cu)" if exr else "k_forward_fused (h2y_forward.cu)"
