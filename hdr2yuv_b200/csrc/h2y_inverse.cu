@@ -301,6 +301,9 @@ namespace {
 #define H2Y_INV_GUARD_C 6.0f         // guard bands in units of u = 2^(d-25); 16 / 16 was the single band of rounds 1-2
 #define H2Y_INV_GUARD_G 10.0f
 #endif
+#ifndef H2Y_INV_UNROLL_HALF
+#define H2Y_INV_UNROLL_HALF 0
+#endif
 #ifndef H2Y_INV_LUMA_STAGES
 #define H2Y_INV_LUMA_STAGES 2        // cp.async stages of the luma rows per warp: 2 = one trip ahead, 4 = three
 #endif
@@ -384,7 +387,7 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
         const int cs = (int)(max(g0, fbase) - fbase), ce = (int)(min(g1, fbase + hh) - fbase);
         const uint16_t *fy = reinterpret_cast<const uint16_t *>(A.yuv + (size_t)frame * A.yuv_stride);
         const uint16_t *fcb = fy + (size_t)w * h;
-        const ptrdiff_t crd = (ptrdiff_t)wh * hh;                               // Cr plane behind Cb, in samples
+        const unsigned crd = (unsigned)wh * (unsigned)hh * 2u;                  // Cr plane behind Cb, in bytes (far below 2^31)
         uint16_t *frgb = reinterpret_cast<uint16_t *>(A.rgb + (size_t)frame * A.rgb_stride);
         if (A.invalid && invalid_frame != frame) {
             if (invalid && invalid_frame >= 0) atomicAdd(&A.invalid[invalid_frame], invalid);
@@ -430,8 +433,8 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
             uint2 nb, nr;
             auto fetch_next = [&]() {
                 nb = __ldg(reinterpret_cast<const uint2 *>(pcb));
-                nr = __ldg(reinterpret_cast<const uint2 *>(pcb + crd));
-                if (rnext >= 0 && rnext < hh - 1) pcb += wh;
+                nr = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(pcb) + crd));
+                pcb += ((unsigned)rnext < (unsigned)(hh - 1)) ? wh : 0;         // rows above the picture and the last row: stay
                 rnext++;
             };
             for (int r = cs - 3; r <= cs + 3; r++) {
@@ -493,7 +496,11 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
                 if (c + 1 < ce) fetch_next();                            // row clamp(c + 5)
                 cp_async_wait<LSTAGES - 1>();                            // this trip's luma rows have landed
 
+#if H2Y_INV_UNROLL_HALF
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
                 for (int half = 0; half < 2; half++) {                  // not unrolled: the instruction cache is the limit
                     // both passes read dv[0]; the second row moves down at the end of the first pass
                     // (12 moves per chroma row instead of 12 selects per luma row, and no run-time array index)
