@@ -8,8 +8,11 @@ import collections
 import csv
 import io
 import re
+import signal
 import subprocess
 import sys
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)      # `... | head` is the usual way to read this
 
 
 def rows(rep):
