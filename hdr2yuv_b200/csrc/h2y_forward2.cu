@@ -1070,6 +1070,14 @@ static cudaError_t launch_rows_on(K kernel, int grid, size_t smem, cudaStream_t 
 // filtered rows in shared memory ([slot][half][lane] float4, only its own lanes touch it, no barrier), and every second
 // row it reads the window back and evaluates convert.cpp:365-374 in order.
 constexpr int VSLOTS = 12;
+__device__ __forceinline__ void ring_sts(unsigned a, u64 x, u64 y)
+{
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" :: "r"(a), "l"(x), "l"(y));
+}
+__device__ __forceinline__ void ring_lds(unsigned a, u64 &x, u64 &y)       // a = base + constant: ptxas folds the constant
+{
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(a));
+}
 
 template <int MK, int NCH, int FAM = 0>
 __global__ void __launch_bounds__(THREADS3, 1) k_forward_u16_420_rows(const Fwd3Args A)
@@ -1077,7 +1085,10 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_u16_420_rows(const Fwd3
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Fwd2Args &a = A.b;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float4 *ring = reinterpret_cast<float4 *>(smem_raw) + (size_t)warp * VSLOTS * 64 + lane;      // [slot][half][lane]
+    // [slot][half][lane] float4, by shared-window address held in an ordinary register (the asm hides that part of it is
+    // uniform: otherwise ptxas rebuilds the address from SR_TID / SR_CgaCtaId for every store and every window read)
+    unsigned ring_sa;
+    asm volatile("mov.u32 %0, %1;" : "=r"(ring_sa) : "r"((unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)warp * (VSLOTS * 1024u) + (unsigned)lane * 16u));
     const PixK &k = a.k;
     const int w = a.w, h = a.h, wh = w >> 1;
     const int hi_bits = MAGIC_BITS + (int)k.maxCV;
@@ -1113,7 +1124,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_u16_420_rows(const Fwd3
             uint16_t *yp = fY + (ptrdiff_t)rfirst * w + xl;
             uint16_t *cbp = fCb + ((ptrdiff_t)(rfirst >> 1) - 3) * wh + (xl >> 1);
             const int crd = (int)(fCr - fCb);
-            int slot = 0;                                            // ring slot of row r; row r - t sits t slots back
+            unsigned so = 0;                                         // ring slot of row r, times 1024; row r - t sits t slots back
 
             RawPx<NCH> raw;
             load_px8<NCH>(raw, sp, 0, 0, 0);
@@ -1150,22 +1161,23 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_u16_420_rows(const Fwd3
                 const u64 o1 = fir_h7_pair_ord(l5, l7, ch[1], ch[2], ch[3], ch[5], ch[7], hi_bits);
                 const u64 o2 = fir_h7_pair_ord(l7, ch[1], ch[3], ch[4], ch[5], ch[7], n1, hi_bits);
                 const u64 o3 = fir_h7_pair_ord(ch[1], ch[3], ch[5], ch[6], ch[7], n1, n3, hi_bits);
-                ring[slot * 64] = make_float4(plo(o0), phi(o0), plo(o1), phi(o1));
-                ring[slot * 64 + 32] = make_float4(plo(o2), phi(o2), plo(o3), phi(o3));
+                ring_sts(ring_sa + so, o0, o1);
+                ring_sts(ring_sa + so + 512u, o2, o3);
                 __syncwarp();
                 const int j = (r >> 1) - 3;                         // even row r = 2j+6 completes output row j
                 if ((r & 1) == 0 && j >= (ys >> 1) && j < (ye >> 1)) {
                     unsigned cbv[4], crv[4];
+                    // row r-11+t sits in slot (slot + 1 + t) mod 12: one of two bases per tap (a compare and a select),
+                    // the tap's offset is an immediate of the load; the twelve addresses serve both halves
+                    const unsigned a0 = ring_sa + so + 1024u, a1 = a0 - VSLOTS * 1024u;
+                    unsigned wa[12];
+#pragma unroll
+                    for (int t = 0; t < 12; t++) wa[t] = so >= (unsigned)(VSLOTS - 1 - t) * 1024u ? a1 : a0;
 #pragma unroll
                     for (int half = 0; half < 2; half++) {
                         u64 win[2][12];                             // rows 2j-5 .. 2j+6 of this lane's columns 2*half, 2*half+1
 #pragma unroll
-                        for (int t = 0; t < 12; t++) {
-                            int sl = slot - 11 + t;                 // row r-11+t
-                            sl += sl < 0 ? VSLOTS : 0;
-                            const float4 v = ring[sl * 64 + 32 * half];
-                            win[0][t] = pk(v.x, v.y); win[1][t] = pk(v.z, v.w);
-                        }
+                        for (int t = 0; t < 12; t++) ring_lds(wa[t] + (unsigned)(1024 * t + 512 * half), win[0][t], win[1][t]);
 #pragma unroll
                         for (int cc = 0; cc < 2; cc++) {
                             // clamp [0,maxCV] + truncation + write_yuv's shift and range clamp: one integer clamp of the floor
@@ -1181,7 +1193,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_u16_420_rows(const Fwd3
                     }
                 }
                 if ((r & 1) == 0) cbp += wh;
-                slot = slot + 1 == VSLOTS ? 0 : slot + 1;
+                so = so + 1024u == VSLOTS * 1024u ? 0u : so + 1024u;
             }
             __syncwarp();
         }
