@@ -559,27 +559,34 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
                             const u64 Yf2 = fadd2(pk(__uint_as_float(__byte_perm(yw[q >> 1], 0x4B000000u, 0x7610)),
                                                      __uint_as_float(__byte_perm(yw[q >> 1], 0x4B000000u, 0x7632))), pk(-TWO23, -TWO23));
                             const u64 Yg2 = fadd2(Yf2, pk(-guardC, -guardC));
-                            int B1[2], R1[2], B2[2], R2[2], Bc[2], Rc[2];
+                            int B1[2], R1[2], Bc[2], Rc[2];
+                            u64 dBR[2];                      // floor(upper end) - floor(lower end) per chain: 0.0f or 1.0f
 #pragma unroll
                             for (int e = 0; e < 2; e++) {
                                 const float Yg = e ? phi(Yg2) : plo(Yg2);
                                 const u64 tlo = ffma2(fadd2(cpx[q + e], pk(-C::hm(A), -C::hm(A))), pk(C::kb(A), C::kr(A)), pk(Yg, Yg));
-                                unpk(fadd2_rm(tlo, pk(MAGIC, MAGIC)), B1[e], R1[e]);
-                                unpk(fadd2_rm(fadd2(tlo, pk(2.0f * guardC, 2.0f * guardC)), pk(MAGIC, MAGIC)), B2[e], R2[e]);
+                                const u64 t1 = fadd2_rm(tlo, pk(MAGIC, MAGIC));
+                                dBR[e] = fsub2(fadd2_rm(fadd2(tlo, pk(2.0f * guardC, 2.0f * guardC)), pk(MAGIC, MAGIC)), t1);
+                                unpk(t1, B1[e], R1[e]);
                                 Bc[e] = min(B1[e], hi_bits); Rc[e] = min(R1[e], hi_bits);    // t > Full-1 -> Full-1 (406-412)
                             }
                             const u64 bf = fadd2(pk(__int_as_float(Bc[0]), __int_as_float(Bc[1])), pk(-MAGIC, -MAGIC));
                             const u64 rf = fadd2(pk(__int_as_float(Rc[0]), __int_as_float(Rc[1])), pk(-MAGIC, -MAGIC));
                             const u64 g2 = ffma2(pk(C::nwr(A), C::nwr(A)), rf, ffma2(pk(C::nwb(A), C::nwb(A)), bf, Yf2));
                             const u64 glo = ffma2(g2, pk(C::rwg(A), C::rwg(A)), pk(0.5f - guardG, 0.5f - guardG));
-                            int G1[2], G2[2];
-                            unpk(fadd2_rm(glo, pk(MAGIC, MAGIC)), G1[0], G1[1]);
-                            unpk(fadd2_rm(fadd2(glo, pk(2.0f * guardG, 2.0f * guardG)), pk(MAGIC, MAGIC)), G2[0], G2[1]);
+                            int G1[2];
+                            const u64 g1 = fadd2_rm(glo, pk(MAGIC, MAGIC));
+                            const u64 dG = fsub2(fadd2_rm(fadd2(glo, pk(2.0f * guardG, 2.0f * guardG)), pk(MAGIC, MAGIC)), g1);
+                            unpk(g1, G1[0], G1[1]);
 #pragma unroll
                             for (int e = 0; e < 2; e++) {
-                                // guarded (a floor changed inside the band) or negative (bit 22 of MAGIC_BITS + n clear)
-                                const bool slow = (((B1[e] ^ B2[e]) | (R1[e] ^ R2[e]) | (G1[e] ^ G2[e])) != 0) | (((B1[e] & R1[e] & G1[e]) & 0x00400000) == 0);
-                                if (slow) slow_mask |= 1u << (q + e);
+                                // guarded (a floor changed inside the band: the exact difference of the two floors is 1.0f,
+                                // taken on the packed-float pipe) or negative (bit 22 of MAGIC_BITS + n clear); the mask is
+                                // built without predicates, pixel q in bit 7 - q
+                                unsigned wq = (unsigned)ilo(dBR[e]) | (unsigned)ihi(dBR[e]) | (unsigned)(e ? ihi(dG) : ilo(dG));
+                                const unsigned nq = (unsigned)(B1[e] & R1[e] & G1[e]);
+                                wq |= ~nq & 0x00400000u;
+                                slow_mask = slow_mask * 2u + min(wq, 1u);
                                 // still biased by MAGIC_BITS, whose low half is zero: phase 3 packs the low halves
                                 Bv[q + e] = Bc[e]; Rv[q + e] = Rc[e];
                                 // G > Full-1 -> Full-1 (yuv2tiff.cpp:412); the video-range output clamp below is tighter
@@ -593,7 +600,7 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
                                 if (MODE == 2) {                                             // yuv2tiff.cpp:401-402
                                     const int off = Y - (int)(C::Full(A) - 1);
                                     Rp = 2 * (int)phi(cpx[q + e]) + off; Bp = 2 * (int)plo(cpx[q + e]) + off; Gp = Y;
-                                    if ((Rp | Bp) < 0) slow_mask |= 1u << (q + e);
+                                    if ((Rp | Bp) < 0) slow_mask |= 0x80u >> (q + e);
                                 }
                                 Rv[q + e] = Rp; Gv8[q + e] = Gp; Bv[q + e] = Bp;
                             }
@@ -604,7 +611,7 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
                     if (slow_mask) {
 #pragma unroll
                         for (int q = 0; q < 8; q++)
-                            if (slow_mask & (1u << q)) {
+                            if (slow_mask & (0x80u >> q)) {
                                 unsigned R, Gg, B;
                                 const int Yq = (int)((q & 1) ? yw[q >> 1] >> 16 : yw[q >> 1] & 0xffffu);
                                 if (MODE == 1 && (CFG == 10 || k.int10))
