@@ -73,6 +73,16 @@ WORKLOADS = {
     "inverse4k_b10_2020": dict(
         kind="inverse", w=3840, h=2160, frames=60, bit_depth=10, matrix=2, fir=1, full_range=0, alpha=0,
         text="yuv2tiff: 3840x2160 10-bit BT.2020 4:2:0 .yuv -> 4:4:4 FIR upsample -> 16-bit RGB rows, 60 frames"),
+    # further yuv2tiff modes (not BASELINE configurations): its default (12-bit Y'DzDx) and the other Y'CbCr depth / family
+    "inverse4k_b12_ydzdx": dict(
+        kind="inverse", w=3840, h=2160, frames=60, bit_depth=12, matrix=0, fir=1, full_range=0, alpha=0,
+        text="yuv2tiff defaults: 3840x2160 12-bit Y'DzDx 4:2:0 .yuv -> 4:4:4 FIR upsample -> 16-bit RGB rows, 60 frames"),
+    "inverse4k_b12_2020": dict(
+        kind="inverse", w=3840, h=2160, frames=60, bit_depth=12, matrix=2, fir=1, full_range=0, alpha=0,
+        text="yuv2tiff B12 2020: 3840x2160 12-bit BT.2020 4:2:0 .yuv -> 4:4:4 FIR upsample -> 16-bit RGB rows, 60 frames"),
+    "inverse4k_b10_709": dict(
+        kind="inverse", w=3840, h=2160, frames=60, bit_depth=10, matrix=1, fir=1, full_range=0, alpha=0,
+        text="yuv2tiff B10 709: 3840x2160 10-bit BT.709 4:2:0 .yuv -> 4:4:4 FIR upsample -> 16-bit RGB rows, 60 frames"),
 }
 DEFAULT_WORKLOAD = "exr4k_pq10_bt2020_420"
 LAYOUT_IDS = {"planar_u16": 0, "planar_f32": 1, "rgb16": 2, "rgba16": 3, "half_rgb": 4, "half_rgba": 5}

@@ -203,6 +203,10 @@ h2y_status launch_forward_fused(h2y_ctx_impl *c, const h2y_forward_params &p, co
 struct InvK {
     int w, h, bit_depth, matrix, fir, full_range, alpha, ybar;
     int int10;                  // `B10 2020`: the exact routine has an integer form (inv_pixel_int10)
+    // integer form for the other Y'CbCr depths / family (inv_pixel_int): B' = ((2 Cb - (Full-1)) ikb + 10000 Y') / 10000,
+    // R' likewise with ikr, G' = (igy Y' + igb B' + igr R' + igc) / igd; igm = floor(2^32 / igd)
+    int ikb, ikr, igy, igb, igr, igc, igd;
+    unsigned igm;
     int SR;
     unsigned Half, Full, maxCV;
     unsigned minVR, maxVR, minVRC, maxVRC;

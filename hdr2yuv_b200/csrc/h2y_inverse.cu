@@ -125,6 +125,49 @@ __device__ __forceinline__ int inv_pixel_int10(const InvK &k, int Y, int cb, int
     return invalid;
 }
 
+// The integer form at any depth (10 / 12 / 14 bits) and for both Y'CbCr families.  The quotients are the same exact
+// rationals (BT.709: 1.8556 / 2 = 0.9278, 1.5748 / 2 = 0.7874, and with the reference's literals 0.07222, 0.2126, 0.7152
+// G' = (50000 Y' - 3611 B' - 10630 R' + 17880) / 35760), but above 10 bits, and for BT.709's denominator already from
+// 256 up, the float rounding can reach the next integer: the reference's value is RN32(x + d), x = N / D the exact
+// quotient, |d| < 2e-11 from its double arithmetic.  With q = floor(|x|), r = |N| mod D and k = q + 1, the floats just
+// below k are 2^(e-23) apart, e = floor(log2(2k - 1)) - 1, so RN32 lands on k exactly when (D - r) / D < 2^(e-24), i.e.
+// when D - r <= D >> (24 - e): D 2^(e-24) is never an integer here, the nearest quotient to that boundary stays 0.09 / D
+// > 2.5e-6 away for every e up to 13 and each of the three denominators (10000, 13560, 35760), far more than d, and an
+// exact tie would need x to be a multiple of 2^(e-24) with e <= 13, which a quotient by 625, 1695 or 2235 times a power of
+// two cannot be unless it is an integer.  Negative quotients mirror this (RN32 and the truncation are odd functions).
+// Checked against inv_pixel(): every 10-bit BT.709 triplet and 2^27 random 12- and 14-bit pixels per family, each sent
+// here through H2Y_INVERSE_KERNEL=exact (tests/test_inverse_gpu.py).
+__device__ __forceinline__ int trunc_rn32_quot(int N, unsigned q, unsigned r, unsigned D)
+{
+    const int e = 30 - __clz((int)(2u * q + 1u));                // binade below k = q + 1: 2k - 1 = 2q + 1
+    q += (D - r) <= (D >> (24 - e)) ? 1u : 0u;                   // r = 0: D <= D >> n never holds (n >= 11)
+    return N < 0 ? -(int)q : (int)q;
+}
+__device__ __forceinline__ int inv_pixel_int(const InvK &k, int Y, int cb, int cr, unsigned &Ro, unsigned &Go, unsigned &Bo)
+{
+    const int top = (int)k.Full - 1, y4 = Y * 10000;
+    const int nb = (2 * cb - top) * k.ikb + y4, nr = (2 * cr - top) * k.ikr + y4;
+    const unsigned ab = (unsigned)abs(nb), ar = (unsigned)abs(nr);
+    int Bp = min(trunc_rn32_quot(nb, ab / 10000u, ab % 10000u, 10000u), top);
+    int Rp = min(trunc_rn32_quot(nr, ar / 10000u, ar % 10000u, 10000u), top);
+    const int ng = Y * k.igy + Bp * k.igb + Rp * k.igr + k.igc;
+    const unsigned ag = (unsigned)abs(ng), D = (unsigned)k.igd;
+    unsigned qg = __umulhi(ag, k.igm), rg = ag - qg * D;         // floor(2^32 / D) as multiplier: short by at most one
+    if (rg >= D) { qg++; rg -= D; }
+    int Gp = min(trunc_rn32_quot(ng, qg, rg, D), top);
+    int invalid = 0;
+    if (Gp < 0) { Gp = 0; invalid++; }
+    if (Rp < 0) { Rp = 0; if (Y != 0) invalid++; }
+    if (Bp < 0) { Bp = 0; if (Y != 0) invalid++; }
+    if (!k.full_range) {
+        Rp = iclamp(Rp, (int)k.minVR, (int)k.maxVR);
+        Gp = iclamp(Gp, (int)k.minVR, (int)k.maxVR);
+        Bp = iclamp(Bp, (int)k.minVR, (int)k.maxVR);
+    }
+    Ro = (unsigned)Rp << k.SR; Go = (unsigned)Gp << k.SR; Bo = (unsigned)Bp << k.SR;
+    return invalid;
+}
+
 template <bool FIR, bool ALPHA>
 __global__ void __launch_bounds__(256)
 k_inverse_fused(InvK k, const uint16_t *__restrict__ yuv, size_t yuv_stride_elems, uint16_t *__restrict__ rgb,
@@ -616,6 +659,8 @@ __global__ void __launch_bounds__(RTHREADS, RMINB) k_inverse_rows(const Inv2Args
                                 const int Yq = (int)((q & 1) ? yw[q >> 1] >> 16 : yw[q >> 1] & 0xffffu);
                                 if (MODE == 1 && (CFG == 10 || k.int10))
                                     invalid += (unsigned)inv_pixel_int10(k, Yq, (int)plo(cpx[q]), (int)phi(cpx[q]), R, Gg, B);
+                                else if (MODE == 1)
+                                    invalid += (unsigned)inv_pixel_int(k, Yq, (int)plo(cpx[q]), (int)phi(cpx[q]), R, Gg, B);
                                 else
                                     invalid += (unsigned)inv_pixel<MODE == 1 ? H2Y_INV_2020 : (MODE == 2 ? H2Y_INV_YDzDx : -1)>(k, Yq, plo(cpx[q]), phi(cpx[q]), R, Gg, B);
                                 Rv[q] = (int)(R >> C::SR(A)); Gv8[q] = (int)(Gg >> C::SR(A)); Bv[q] = (int)(B >> C::SR(A));
@@ -663,6 +708,13 @@ h2y_status make_invk(const h2y_inverse_params &p, InvK *k)
     k->w = p.width; k->h = p.height; k->bit_depth = p.bit_depth; k->matrix = p.matrix;
     k->fir = p.fir != 0; k->full_range = p.full_range != 0; k->alpha = p.alpha != 0;
     k->int10 = p.matrix == H2Y_INV_2020 && p.bit_depth == 10;    // inv_pixel_int10
+    k->ikb = k->ikr = k->igy = k->igb = k->igr = k->igc = 0; k->igd = 1; k->igm = 0;
+    if (p.matrix == H2Y_INV_2020) {          // inv_pixel_int: 0.9407, 0.7373; (2 (10000 Y - 593 B - 2627 R) + 6780) / 13560
+        k->ikb = 9407; k->ikr = 7373; k->igy = 20000; k->igb = -1186; k->igr = -5254; k->igc = 6780; k->igd = 13560;
+    } else if (p.matrix == H2Y_INV_709) {    // 0.9278, 0.7874; (50000 Y - 3611 B - 10630 R + 17880) / 35760
+        k->ikb = 9278; k->ikr = 7874; k->igy = 50000; k->igb = -3611; k->igr = -10630; k->igc = 17880; k->igd = 35760;
+    }
+    k->igm = (unsigned)(4294967296.0 / (double)k->igd);
     k->ybar = p.ybar != 0 && p.matrix == H2Y_INV_YDzDx;          // -X only acts inside the Y'DzDx branch (yuv2tiff.cpp:389-399)
     k->SR = 16 - p.bit_depth;                                   // yuv2tiff.cpp:89, 139, 150
     k->Half = 1u << (p.bit_depth - 1);

@@ -133,8 +133,8 @@ def test_rows_kernel_on_every_10bit_triplet(ctx, m, fr, opt):
             frames.append(torch.cat([luma, cb, cr]).to(torch.int16))
         d_yuv = torch.stack(frames, 0).view(torch.uint8).view(-1)
         res = {}
-        # "exact": the rows kernel with every pixel through its exact routine, which for BT.2020 is the integer form
-        # (inv_pixel_int10): all 2^30 triplets reach it
+        # "exact": the rows kernel with every pixel through its exact routine, the integer forms (inv_pixel_int10 for
+        # BT.2020, inv_pixel_int with its rounding thresholds for BT.709): all 2^30 triplets reach them
         for kernel in ("tile", "rows", "exact"):
             opt("H2Y_INVERSE_KERNEL", kernel)
             res[kernel] = _inverse_dev(ctx, d_yuv, batch, w, h, 10, m, 0, fr)
@@ -146,7 +146,7 @@ def test_rows_kernel_on_every_10bit_triplet(ctx, m, fr, opt):
     assert total_invalid > 0                        # the lattice includes the out-of-gamut corners
 
 
-@pytest.mark.parametrize("bd,m", [(10, O.INV_2020), (12, O.INV_2020), (12, O.INV_709), (14, O.INV_2020), (14, O.INV_709)])
+@pytest.mark.parametrize("bd,m", [(10, O.INV_2020), (10, O.INV_709), (12, O.INV_2020), (12, O.INV_709), (14, O.INV_2020), (14, O.INV_709)])
 def test_rows_kernel_dense_random_triplets(ctx, bd, m, opt):
     # The same comparison with the FIR upsampler (for 10-bit BT.2020 video range that is the instantiation with the
     # constants compiled in) and at the depths where the lattice is too large: 2^27 random pixels per case.
@@ -160,11 +160,14 @@ def test_rows_kernel_dense_random_triplets(ctx, bd, m, opt):
     d_yuv[n // 2:, w * h:] = (top // 2 + torch.randint(-top // 8, top // 8, (n // 2, w * h // 2), device="cuda", generator=g, dtype=torch.int32)).to(torch.int16)
     d_yuv = d_yuv.view(torch.uint8).view(-1)
     res = {}
-    for kernel in ("tile", "rows"):
+    # "exact": every pixel through the rows kernel's exact routine, i.e. the integer forms (inv_pixel_int10 / inv_pixel_int,
+    # with the float-rounding thresholds that only matter above 10 bits and for BT.709)
+    for kernel in ("tile", "rows", "exact"):
         opt("H2Y_INVERSE_KERNEL", kernel)
         res[kernel] = _inverse_dev(ctx, d_yuv, n, w, h, bd, m, 1, 0)
-    assert torch.equal(res["tile"][0], res["rows"][0])
-    assert torch.equal(res["tile"][1], res["rows"][1])
+    for kernel in ("rows", "exact"):
+        assert torch.equal(res["tile"][0], res[kernel][0]), kernel
+        assert torch.equal(res["tile"][1], res[kernel][1]), kernel
 
 
 def test_staged_upsample_matches_oracle(ctx):
