@@ -1118,6 +1118,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_u16_420_rows(const Fwd3
             const bool lane_interior = lane >= 1 && lane < 31 && xl < min(x0 + a.strip_w, w);
             const int xload = lane_in_pic ? xl : (xl < 0 ? 0 : w - 8);
             const bool left_edge = xl == 0, right_edge = xl + 8 >= w;
+            const bool strip_edge = __any_sync(0xffffffffu, left_edge || right_edge);    // warp-uniform: inner strips skip the selects
             const int rfirst = ys - 6, rlast = ye + 4;              // rows feeding outputs ys/2 .. ye/2-1 (rfirst even)
             const unsigned spitch = (unsigned)w * (2 * NCH);
             const uint8_t *sp = fsrc + (size_t)min(max(rfirst, 0), h - 1) * spitch + (size_t)xload * (2 * NCH);
@@ -1155,8 +1156,10 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_u16_420_rows(const Fwd3
                 float n1x = __shfl_down_sync(0xffffffffu, plo(ch[1]), 1), n1y = __shfl_down_sync(0xffffffffu, phi(ch[1]), 1);
                 float n3x = __shfl_down_sync(0xffffffffu, plo(ch[3]), 1), n3y = __shfl_down_sync(0xffffffffu, phi(ch[3]), 1);
                 u64 l3 = pk(l3x, l3y), l5 = pk(l5x, l5y), l7 = pk(l7x, l7y), n1 = pk(n1x, n1y), n3 = pk(n3x, n3y);
-                if (left_edge) l3 = l5 = l7 = ch[0];                // replicate s[0]     (convert.cpp:295-300)
-                if (right_edge) n1 = n3 = ch[7];                    // replicate s[W-1]
+                if (strip_edge) {
+                    if (left_edge) l3 = l5 = l7 = ch[0];            // replicate s[0]     (convert.cpp:295-300)
+                    if (right_edge) n1 = n3 = ch[7];                // replicate s[W-1]
+                }
                 const u64 o0 = fir_h7_pair_ord(l3, l5, l7, ch[0], ch[1], ch[3], ch[5], hi_bits);
                 const u64 o1 = fir_h7_pair_ord(l5, l7, ch[1], ch[2], ch[3], ch[5], ch[7], hi_bits);
                 const u64 o2 = fir_h7_pair_ord(l7, ch[1], ch[3], ch[4], ch[5], ch[7], n1, hi_bits);
