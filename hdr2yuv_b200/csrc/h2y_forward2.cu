@@ -686,6 +686,11 @@ struct Fwd3Args {
 };
 
 constexpr int THREADS3 = 512, WARPS3 = THREADS3 / 32;
+// Rows per row worker from which h2y_forward takes the rows kernels by itself.  A worker pays 11 halo rows per run, so
+// small batches are where the CTA-ring kernel used to win; measured again at the end of round 2 (profiles/r02/variants.md):
+// 4K EXR, two frames (29 rows per worker) 0.128 ms against 0.162 ms, one frame (14) 0.105 against 0.110; 1080p TIFF,
+// 16 frames (58) 0.130 against 0.192, 4 frames (14) 0.076 against 0.070.
+constexpr long ROWS_MIN_PER_WORKER = 24;
 // SPEC instantiations: the warps' code bounds sit behind the LUT copy (24 bytes per warp)
 constexpr unsigned SPEC_BOUNDS_BYTES = 24 * 16;
 template <bool TWO> __device__ __host__ constexpr unsigned spec_bounds_offset() { return (TWO ? 2u * LUT2_CODES : (unsigned)LUT_MAX_CODES) * 4u; }
@@ -1314,7 +1319,7 @@ h2y_status launch_forward_u16_420(h2y_ctx_impl *c, const h2y_forward_params &p, 
         A3.sub = WARPS3 / A3.wps;
         A3.total_rows = (long)nframes * a.h;
         const long rows_per_worker = A3.total_rows / ((long)c->sm_count * A3.sub);
-        const bool want_rows = c->sw.fwd_kernel ? c->sw.fwd_kernel == 2 : rows_per_worker >= 128;    // forced by tests and experiments
+        const bool want_rows = c->sw.fwd_kernel ? c->sw.fwd_kernel == 2 : rows_per_worker >= ROWS_MIN_PER_WORKER;    // forced by tests and experiments
         if (want_rows && A3.total_rows >= 2) {
             int g3 = c->sm_count;
             while (g3 > 1 && A3.total_rows / ((long)g3 * A3.sub) < 16) g3 >>= 1;   // forced on a tiny batch
@@ -1389,7 +1394,7 @@ static bool rows_plan(const h2y_ctx_impl *c, const Fwd2Args &a, int nframes, Fwd
     A3->sub = WARPS3 / A3->wps;
     A3->total_rows = (long)nframes * a.h;
     const long rows_per_worker = A3->total_rows / ((long)c->sm_count * A3->sub);
-    const bool want_rows = c->sw.fwd_kernel ? c->sw.fwd_kernel == 2 : rows_per_worker >= 128;
+    const bool want_rows = c->sw.fwd_kernel ? c->sw.fwd_kernel == 2 : rows_per_worker >= ROWS_MIN_PER_WORKER;
     if (!want_rows || A3->total_rows < 2) return false;
     *g3 = c->sm_count;
     while (*g3 > 1 && A3->total_rows / ((long)*g3 * A3->sub) < 16) *g3 >>= 1;       // forced on a tiny batch

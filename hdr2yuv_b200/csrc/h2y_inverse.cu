@@ -751,7 +751,9 @@ h2y_status launch_inverse(h2y_ctx_impl *c, const InvK &k, const void *d_yuv, siz
         A.guard_g = H2Y_INV_GUARD_G / (float)(1 << (25 - k.bit_depth));
         const long rows_per_worker = A.total_crows / ((long)c->sm_count * RMINB * A.sub);
         // forced by tests and experiments (h2y_ctx_set_option); -X: tile kernel only
-        const bool want_rows = !k.ybar && (c->sw.inv_kernel ? c->sw.inv_kernel >= 2 : rows_per_worker >= 48);
+        // (a worker's halo is seven chroma rows that are only fetched and stashed, so short runs cost little: one 4K frame,
+        // 7 chroma rows per worker, 0.036 ms against the tile kernel's 0.079 ms; eight frames 0.165 against 0.598 ms)
+        const bool want_rows = !k.ybar && (c->sw.inv_kernel ? c->sw.inv_kernel >= 2 : rows_per_worker >= 4);
         if (want_rows) {
             int grid = c->sm_count * RMINB;
             while (grid > 1 && A.total_crows / ((long)grid * A.sub) < 4) grid >>= 1;
