@@ -128,7 +128,8 @@ uint64_t h2y_kernel_launches(const h2y_ctx *ctx);         /* kernels this contex
 
 /* Test and experiment switches.  The library reads the environment exactly once, in h2y_ctx_create; afterwards the
  * switches belong to the context and are changed with this call (tests force each kernel of a route this way).
- * Names: "H2Y_FORWARD_KERNEL" = "ring" | "rows" | "", "H2Y_INVERSE_KERNEL" = "tile" | "rows" | "", "H2Y_FORCE_STAGED",
+ * Names: "H2Y_FORWARD_KERNEL" = "ring" | "rows" | "", "H2Y_INVERSE_KERNEL" = "tile" | "rows" | "exact" (the rows
+ * kernel with every pixel through its exact integer routine) | "", "H2Y_FORCE_STAGED",
  * "H2Y_FORCE_V1", "H2Y_NO_SPECIALISED", "H2Y_EXACT_MATH" = "1" | "0", "H2Y_STATS_GX" = n, "H2Y_PLAN_REUSE" = "0" never,
  * "1" whenever a previous plan exists, "" automatic (see h2y_forward).  name == NULL restores the defaults of
  * h2y_ctx_create.  Unknown names return H2Y_ERR_ARG. */
