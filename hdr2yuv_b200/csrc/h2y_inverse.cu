@@ -299,15 +299,16 @@ k_inverse_fused(InvK k, const uint16_t *__restrict__ yuv, size_t yuv_stride_elem
 }
 
 // =================================================================================================
-// Large-batch variant: warp-autonomous rows, same idea as k_forward_exr420_rows (h2y_forward2.cu).
+// Rows kernel (everything but tiny inputs): warp-autonomous, same idea as k_forward_exr420_rows (h2y_forward2.cu).
 // A warp owns a 240-pixel column strip (lane = 8 luma pixels = 4 chroma columns, lanes 0/31 are halo lanes of
 // the horizontal interpolation) and a long run of chroma rows.  The 7-row vertical window lives in a private
-// 8-slot shared-memory ring that only its own lanes touch (no barrier of any kind); both upsampling stages are
-// FFMA2 chains on {Cb,Cr} pairs (all terms are integers/256 below 2^23, so the order is free) with the
-// reference's clamp + truncation taken as a round-down add and an integer clamp.  The Y'CbCr inverse is
-// evaluated in fp32 with a guard band: each truncation is taken at x-G and x+G and the reference-exact
-// inv_pixel() (double arithmetic, true division) runs only for the rare pixel where the two disagree or a
-// component is negative (which also carries the invalidPixels bookkeeping).
+// 8-slot shared-memory ring that only its own lanes touch (no barrier of any kind); the luma rows arrive by
+// cp.async in per-lane stages one trip ahead; both upsampling stages are FFMA2 chains on {Cb,Cr} pairs (all
+// terms are integers/256 below 2^23, so the order is free) with the reference's clamp + truncation taken as a
+// round-down add and an integer clamp.  The Y'CbCr inverse is evaluated in fp32 with guard bands: each
+// truncation is taken at x-G and x+G, and an exact routine (the integer forms inv_pixel_int10 / inv_pixel_int
+// of the reference's double arithmetic; inv_pixel() itself for Y100 / Y500) runs only for the rare pixel
+// where the two disagree or a component is negative (which also carries the invalidPixels bookkeeping).
 //
 // Guard bands, in units of u = 2^(d-25) (half an fp32 ulp of values in [2^(d-1), 2^d)).  x = the exact real value of a
 // chain, t_ref = the reference's float (double arithmetic rounded once to float: |t_ref - x| <= 1u below 2^d; above
@@ -319,7 +320,7 @@ k_inverse_fused(InvK k, const uint16_t *__restrict__ yuv, size_t yuv_stride_elem
 //  * G': g2 = fma(-wr32, R', fma(-wb32, B', Y)) with integer B', R' (the accepted values): weight images u/8 + u/2, two
 //    roundings 2u: 2.625u; times 1/wg <= 1.475 is 3.87u; the image of 1/wg 2u; the fma's rounding 1u:
 //    |lo - (x - G)| <= 6.87u, so G >= 8.87u.  G = 10u.
-// (One band of 2^(d-21) = 16u for all three chains sent 2.2 times as many pixels to inv_pixel.)
+// (One band of 2^(d-21) = 16u for all three chains sent 2.2 times as many pixels to the exact routine.)
 struct Inv2Args {
     InvK k;
     const uint8_t *yuv;
