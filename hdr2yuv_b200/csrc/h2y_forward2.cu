@@ -71,7 +71,8 @@ struct Fwd2Args {
     int strip_w, nstrips, seg_rows, nsegs, nitems;
     float guard;             // G
     float wr, wg, wb, rdb, rdr;   // fp32 images of the double constants (their error is inside the guard budget)
-    float lumc, cbc, crc, twoG;   // 0.5-G; chroma constants with the lowered luma folded in; 2G
+    float lumc, cbc, crc;         // 0.5-Gy; chroma constants with the lowered luma folded in
+    float twoGy, twoGb, twoGr;    // band widths 2G of the luma, Cb and Cr chains
     PixK k;
     const FrameK *framek;
     const float *luts;
@@ -126,15 +127,17 @@ __device__ __forceinline__ void pixel_exact(float G, float B, float R, const Pix
 template <int CFG> struct KC {
     // CFG = 0: run time.  CFG = D (10 or 12): BT.2020nc at D-bit tmp/output depth, video range, no output shift
     static constexpr int D = CFG ? CFG : 10, S = 1 << (D - 8);
-    static constexpr float G = 1.0f / (float)(1 << (H2Y_GUARD_SHIFT - D));
+    // guard bands per chain, in units of u = 2^(D-25): 6u for luma (needs 5.125u), 7u for Cb (6.3u), 8u for Cr (7.2u);
+    // DESIGN.md 4, "Guard-band truncation"
+    static constexpr float G = 1.0f / (float)(1 << (H2Y_GUARD_SHIFT - D)), GY = 0.75f * G, GB = 0.875f * G, GR = G;
     static constexpr float RDB = (float)(1.0 / 1.8814), RDR = (float)(1.0 / 1.4746);
 #define KCF(name, rt, ct) __device__ __forceinline__ static float name(const Fwd2Args &a) { return CFG ? (ct) : (rt); }
 #define KCI(name, rt, ct) __device__ __forceinline__ static int name(const Fwd2Args &a) { return CFG ? (ct) : (int)(rt); }
     KCF(mulY, a.k.mulY, (float)(235 * S)) KCF(mulC, a.k.mulC, (float)(240 * S)) KCF(addY, a.k.addY, (float)(16 * S)) KCF(addC, a.k.addC, (float)(16 * S))
     KCF(wr, a.wr, (float)0.2627) KCF(wg, a.wg, (float)0.6780) KCF(wb, a.wb, (float)0.0593)
     KCF(rdb, a.rdb, RDB) KCF(rdr, a.rdr, RDR)
-    KCF(lumc, a.lumc, 0.5f - G) KCF(twoG, a.twoG, 2.0f * G)
-    KCF(cbc, a.cbc, 0.5f - G - G * RDB) KCF(crc, a.crc, 0.5f - G - G * RDR)
+    KCF(lumc, a.lumc, 0.5f - GY) KCF(twoGy, a.twoGy, 2.0f * GY) KCF(twoGb, a.twoGb, 2.0f * GB) KCF(twoGr, a.twoGr, 2.0f * GR)
+    KCF(cbc, a.cbc, 0.5f - GB - GY * RDB) KCF(crc, a.crc, 0.5f - GR - GY * RDR)
     KCI(maxCV, a.k.maxCV, (1 << D) - 1) KCI(half_m1, a.k.half_m1, (1 << (D - 1)) - 1) KCI(shift, a.k.down_shift, 0)
     KCI(loY, a.k.loY, 16 * S) KCI(hiY, a.k.hiY, 235 * S) KCI(loC, a.k.loC, 16 * S) KCI(hiC, a.k.hiC, 240 * S)
 #undef KCF
@@ -222,7 +225,8 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, unsigne
     return;
 #endif
     const u64 addY2 = pk(C::addY(a), C::addY(a)), addC2 = pk(C::addC(a), C::addC(a));
-    const u64 magic2 = pk(MAGIC, MAGIC), twoG2 = pk(C::twoG(a), C::twoG(a));
+    const u64 magic2 = pk(MAGIC, MAGIC);
+    const u64 twoGy2 = pk(C::twoGy(a), C::twoGy(a)), twoGb2 = pk(C::twoGb(a), C::twoGb(a)), twoGr2 = pk(C::twoGr(a), C::twoGr(a));
     const float wr = C::wr(a), wg = C::wg(a), wb = C::wb(a), rdb = C::rdb(a), rdr = C::rdr(a);
     const u64 wr2 = pk(wr, wr), wg2 = pk(wg, wg), wb2 = pk(wb, wb);
     const u64 rdb2 = pk(rdb, rdb), rdr2 = pk(rdr, rdr);
@@ -260,14 +264,14 @@ __device__ __forceinline__ void pixels8(const Fwd2Args &a, unsigned lut, unsigne
             if (MK == MK_YCBCR) {
                 const u64 slo = ffma2(wg2, G2[p], ffma2(wr2, R2[p], ffma2(wb2, B2[p], lumc2)));     // luma + 0.5 - G
                 y1 = fadd2_rm(slo, magic2);
-                y2 = fadd2_rm(fadd2(slo, twoG2), magic2);
+                y2 = fadd2_rm(fadd2(slo, twoGy2), magic2);
                 base = slo;
             } else {                                     // Y'DzDx: Y = (unsigned)G', exact
                 y1 = y2 = fadd2_rm(G2[p], magic2);
                 base = G2[p];
             }
             const u64 cbl = ffma2(fsub2(B2[p], base), rdb2, cbc2), crl = ffma2(fsub2(R2[p], base), rdr2, crc2);
-            const u64 cbh = fadd2(cbl, twoG2), crh = fadd2(crl, twoG2);
+            const u64 cbh = fadd2(cbl, twoGb2), crh = fadd2(crl, twoGr2);
             const u64 cb1 = fadd2_rm(cbl, magic2), cb2 = fadd2_rm(cbh, magic2);
             const u64 cr1 = fadd2_rm(crl, magic2), cr2 = fadd2_rm(crh, magic2);
             int Y1[2], Y2[2], B1[2], Bq[2], R1[2], Rq[2], xb[2], xr[2];
@@ -1431,10 +1435,13 @@ static void exr_args(const h2y_ctx_impl *c, const h2y_forward_params &p, const P
     a.rdb = k.mat_kind == MK_YCBCR ? (float)k.rdb : 0.5f;
     a.rdr = k.mat_kind == MK_YCBCR ? (float)k.rdr : 0.5f;
     // chroma is taken against the lowered luma (sf - G) on the Y'CbCr route: fold the +G*rd back into the constant
-    a.lumc = 0.5f - a.guard;
-    a.twoG = 2.0f * a.guard;
-    a.cbc = k.mat_kind == MK_YCBCR ? 0.5f - a.guard - a.guard * a.rdb : 0.5f - a.guard;
-    a.crc = k.mat_kind == MK_YCBCR ? 0.5f - a.guard - a.guard * a.rdr : 0.5f - a.guard;
+    // per chain: luma 6u, Cb 7u, Cr 8u = a.guard (the bound of each chain: DESIGN.md 4); one width for all when an
+    // experiment sets it
+    const float gy = c->sw.guard_log2 >= 0 ? a.guard : 0.75f * a.guard, gb = c->sw.guard_log2 >= 0 ? a.guard : 0.875f * a.guard, gr = a.guard;
+    a.lumc = 0.5f - gy;
+    a.twoGy = 2.0f * gy; a.twoGb = 2.0f * gb; a.twoGr = 2.0f * gr;
+    a.cbc = k.mat_kind == MK_YCBCR ? 0.5f - gb - gy * a.rdb : 0.5f - gb;
+    a.crc = k.mat_kind == MK_YCBCR ? 0.5f - gr - gy * a.rdr : 0.5f - gr;
     a.strip_w = 240;
     a.nstrips = (a.w + a.strip_w - 1) / a.strip_w;
     const int grid_max = c->sm_count;
