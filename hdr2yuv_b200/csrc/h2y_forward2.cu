@@ -385,8 +385,16 @@ __device__ __forceinline__ u64 fir_h7_pair(u64 m5, u64 m3, u64 m1, u64 c, u64 p1
 // observable, so this route keeps the general kernel's FP64 colour difference
 // (reciprocal multiply with 14 guard bits, exact division when unsure) and the reference's float operation order
 // in both filters; it shares the ring / register-blocked vertical stage of k_forward_exr420.
+// write_yuv's shift mask and packed luma range for pixels8_u16 (a caller may keep them in registers across its loop)
+struct LumaPack { unsigned keep, lo2, hi2; };
+__device__ __forceinline__ LumaPack luma_pack(const PixK &k)
+{
+    LumaPack p;
+    p.keep = (0xffffu >> k.down_shift) * 0x10001u; p.lo2 = k.loY * 0x10001u; p.hi2 = k.hiY * 0x10001u;
+    return p;
+}
 template <int MK, int FAM = 0>
-__device__ __forceinline__ void pixels8_u16(const PixK &k, const unsigned g[8], const unsigned b[8], const unsigned r[8],
+__device__ __forceinline__ void pixels8_u16(const PixK &k, const LumaPack &lp, const unsigned g[8], const unsigned b[8], const unsigned r[8],
                                             uint4 &ypack, u64 chroma[8], unsigned &fallbacks)
 {
     unsigned yv[8];
@@ -413,7 +421,7 @@ __device__ __forceinline__ void pixels8_u16(const PixK &k, const unsigned g[8], 
         }
     }
     // write_yuv on luma: >> shift and the range clamp on two packed codes per instruction (Y <= maxCV < 2^16)
-    const unsigned keep = (0xffffu >> k.down_shift) * 0x10001u, lo2 = k.loY * 0x10001u, hi2 = k.hiY * 0x10001u;
+    const unsigned keep = lp.keep, lo2 = lp.lo2, hi2 = lp.hi2;
     unsigned wv[4];
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -544,7 +552,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_forward_exr420(const Fwd2Args a)
                 split_codes<NCH>(raw, g, b, r);
                 uint4 ypack;
                 if (SRC == 0) { unsigned yb[8]; pixels8<MK>(a, lut_sa, lut_sa, lut_sa, g, b, r, yb, ch); ypack = pack_luma<0>(a, yb); }
-                else pixels8_u16<MK>(a.k, g, b, r, ypack, ch, fallbacks);
+                else pixels8_u16<MK>(a.k, luma_pack(a.k), g, b, r, ypack, ch, fallbacks);
                 if (lane_interior && row >= ys && row < ye) *reinterpret_cast<uint4 *>(fY + (size_t)row * w + xl) = ypack;
             }
             {   // prefetch the next step's row
@@ -1104,6 +1112,12 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_u16_420_rows(const Fwd3
     const int shift = k.down_shift;
     const int clo = (int)k.loC + (MAGIC_BITS >> shift), chi = (int)k.hiC + (MAGIC_BITS >> shift);
     unsigned fallbacks = 0;
+    // the packed clip limits stay in registers (otherwise they are rebuilt from the constant bank for every row)
+    unsigned clip_lo2, clip_hi2;
+    asm volatile("mov.u32 %0, %1;" : "=r"(clip_lo2) : "r"(k.loadLo * 0x10001u));
+    asm volatile("mov.u32 %0, %1;" : "=r"(clip_hi2) : "r"(k.loadHi * 0x10001u));
+    LumaPack lpack = luma_pack(k);
+    asm volatile("" : "+r"(lpack.keep), "+r"(lpack.lo2), "+r"(lpack.hi2));
 
     const int wk = warp / A.wps, sfirst = warp - wk * A.wps;
     if (wk >= A.sub) return;
@@ -1141,7 +1155,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_u16_420_rows(const Fwd3
 #pragma unroll 1
             for (int r = rfirst; r <= rlast; r++) {
                 if (k.clip_on_load) {                                               // read_tiff's clip (tiff.cpp:296-304)
-                    const unsigned lo2 = k.loadLo * 0x10001u, hi2 = k.loadHi * 0x10001u;
+                    const unsigned lo2 = clip_lo2, hi2 = clip_hi2;
 #pragma unroll
                     for (int i = 0; i < NCH; i++) {
                         unsigned *wv = reinterpret_cast<unsigned *>(&raw.v[i]);
@@ -1156,7 +1170,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_forward_u16_420_rows(const Fwd3
                 if (r < rlast) load_px8<NCH>(raw, sp, 0, 0, 0);                     // prefetch the next row
                 uint4 ypack;
                 u64 ch[8];
-                pixels8_u16<MK, FAM>(k, g, b, rr, ypack, ch, fallbacks);
+                pixels8_u16<MK, FAM>(k, lpack, g, b, rr, ypack, ch, fallbacks);
                 if (lane_interior && r >= ys && r < ye) *reinterpret_cast<uint4 *>(yp) = ypack;
                 yp += w;
                 float l3x = __shfl_up_sync(0xffffffffu, plo(ch[3]), 1), l3y = __shfl_up_sync(0xffffffffu, phi(ch[3]), 1);
